@@ -1,0 +1,156 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates tests/golden/*.pt by executing the UNMODIFIED reference
+(/root/reference, through oracle/shims) on seeded synthetic inputs.  Runs only in the build container;
+the fixtures travel to the GPU box.  Usage: python oracle/gen_golden.py
+Every fixture stores the inputs (or the seeds that regenerate them through oracle/synth.py) and the
+reference's outputs."""
+import os
+import sys
+import copy
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness as rh       # noqa: E402
+import ase_oracle as O         # noqa: E402
+import synth                   # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+
+
+def _sample_idx(numel, k=256):
+    g = torch.Generator().manual_seed(numel)
+    return torch.randint(0, numel, (min(k, numel),), generator=g)
+
+
+def gen_obs():
+    humanoid, humanoid_amp, _ = rh.import_env_fns()
+    s = synth.rigid_body_state(64, seed=11, edge_cases=True)
+    out = {'inputs': s}
+    for lro in (True, False):
+        for rho in (True, False):
+            out[f'obs_l{int(lro)}_h{int(rho)}'] = humanoid.compute_humanoid_observations_max(
+                s['body_pos'], s['body_rot'], s['body_vel'], s['body_ang_vel'], lro, rho)
+            kp = s['body_pos'][:, O.KEY_BODY_IDS_SWORD_SHIELD]
+            out[f'amp_l{int(lro)}_h{int(rho)}'] = humanoid_amp.build_amp_observations(
+                s['body_pos'][:, 0], s['body_rot'][:, 0], s['body_vel'][:, 0], s['body_ang_vel'][:, 0],
+                s['dof_pos'], s['dof_vel'], kp, lro, rho, 78, O.DOF_OFFSETS_SWORD_SHIELD)
+    torch.save(out, os.path.join(OUT, 'obs_build.pt'))
+    print('obs_build.pt', {k: tuple(v.shape) for k, v in out.items() if torch.is_tensor(v)})
+
+
+def _load_params(agent, P, ase):
+    sd = {'a2c_network.' + k: v.clone() for k, v in P.items()}
+    if ase:
+        for k in list(sd):
+            if '_disc_mlp' in k:
+                sd[k.replace('_disc_mlp', '_enc_mlp')] = sd[k]
+    agent.model.load_state_dict(sd, strict=True)
+
+
+def _run_steps(kind, shapes_kw, net_over, B, Ba, nsteps, seed, full):
+    """kind: 'ase' | 'amp'.  Runs nsteps consecutive reference calc_gradients calls."""
+    import ref_harness
+    agent, params = None, None
+    # network dims are YAML-driven: patch the YAML dict before the builder reads it
+    orig = ref_harness.load_train_cfg
+
+    def patched(name):
+        c = orig(name)
+        for sect, units in net_over.items():
+            c['params']['network'][sect]['units'] = list(units)
+        return c
+    ref_harness.load_train_cfg = patched
+    try:
+        agent, params = rh.make_ref_agent(kind, num_envs=B // 32, overrides={'minibatch_size': B, 'amp_minibatch_size': Ba})
+    finally:
+        ref_harness.load_train_cfg = orig
+    shapes = (O.ase_param_shapes if kind == 'ase' else O.amp_param_shapes)(**shapes_kw)
+    P = synth.params(shapes, seed=seed)
+    _load_params(agent, P, kind == 'ase')
+    cfg = dict(O.DEFAULT_CFG); cfg['amp_minibatch_size'] = Ba
+    if kind == 'amp':
+        cfg['enc_coef'] = 0.0; cfg['amp_diversity_bonus'] = 0.0
+    st = O.LearnerState(P, 253, 1400, kind)
+    steps = []
+    for s in range(nsteps):
+        d, new_z = synth.minibatch(st, cfg, B, Ba, seed=seed * 100 + s, kind=kind)
+        if kind == 'ase':
+            agent._sample_latents = (lambda nz: (lambda n: nz))(new_z)
+        agent.calc_gradients(d)
+        tr = agent.train_result
+        rec = {'scalars': {k: float(v) for k, v in tr.items() if torch.is_tensor(v) and v.numel() == 1},
+               'disc_agent_logit': tr['disc_agent_logit'].flatten().clone(),
+               'disc_demo_logit': tr['disc_demo_logit'].flatten().clone(),
+               'actor_clipped': tr['actor_clipped'].float().clone()}
+        g_full, p_full, g_norm, g_samp, p_samp = {}, {}, {}, {}, {}
+        for n, prm in agent.model.named_parameters():
+            k = n[len('a2c_network.'):]
+            if k == 'sigma' or '_enc_mlp' in k:
+                continue
+            gr = prm.grad.detach()
+            idx = _sample_idx(gr.numel())
+            g_norm[k] = float(gr.double().norm())
+            g_samp[k] = gr.flatten()[idx].clone()
+            p_samp[k] = prm.detach().flatten()[idx].clone()
+            if full and s == nsteps - 1:
+                g_full[k] = gr.clone()
+        rec.update(grad_norm=g_norm, grad_sample=g_samp, param_sample=p_samp)
+        if full and s == nsteps - 1:
+            rec.update(grads=g_full)
+        rec['rms'] = {'obs_mean': agent.running_mean_std.running_mean.clone(), 'obs_var': agent.running_mean_std.running_var.clone(),
+                      'obs_count': agent.running_mean_std.count.clone(),
+                      'amp_mean': agent._amp_input_mean_std.running_mean.clone(), 'amp_var': agent._amp_input_mean_std.running_var.clone(),
+                      'amp_count': agent._amp_input_mean_std.count.clone()}
+        steps.append(rec)
+        # advance the oracle state in lock-step so synth.minibatch (which uses st for old_logp) tracks the reference
+        O.calc_gradients(st, d, cfg, new_z)
+    meta = dict(kind=kind, shapes_kw=shapes_kw, B=B, Ba=Ba, seed=seed, nsteps=nsteps, cfg=cfg,
+                param_checksum={k: float(v.double().sum()) for k, v in P.items()})
+    return {'meta': meta, 'steps': steps}
+
+
+def gen_calc_gradients():
+    small = dict(units=(64, 48, 32), disc_units=(48, 40, 24))
+    r = _run_steps('ase', dict(units=small['units'], disc_units=small['disc_units']),
+                   {'mlp': small['units'], 'disc': small['disc_units']}, B=64, Ba=16, nsteps=2, seed=5, full=True)
+    torch.save(r, os.path.join(OUT, 'calc_grad_ase_small.pt'))
+    print('calc_grad_ase_small', r['steps'][-1]['scalars'])
+    r = _run_steps('ase', {}, {}, B=256, Ba=64, nsteps=2, seed=7, full=False)
+    torch.save(r, os.path.join(OUT, 'calc_grad_ase_cfg1.pt'))
+    print('calc_grad_ase_cfg1', r['steps'][-1]['scalars'])
+    r = _run_steps('amp', {}, {}, B=256, Ba=64, nsteps=2, seed=9, full=False)
+    torch.save(r, os.path.join(OUT, 'calc_grad_amp_cfg.pt'))
+    print('calc_grad_amp_cfg', r['steps'][-1]['scalars'])
+
+
+def gen_rollout_math():
+    agent, _ = rh.make_ref_agent('ase', num_envs=8, overrides={'minibatch_size': 256, 'amp_minibatch_size': 64})
+    g = torch.Generator().manual_seed(21)
+    H, N = 32, 8
+    fd = (torch.rand(H, N, generator=g) < 0.1).float()
+    v = torch.randn(H, N, 1, generator=g); nv = torch.randn(H, N, 1, generator=g); r = torch.rand(H, N, 1, generator=g)
+    adv = agent.discount_values(fd, v, r, nv)
+    mask = (torch.rand(H * N, generator=g) < 0.8).float()
+    ret = O.swap_and_flatten01(adv + v); vals = O.swap_and_flatten01(v)
+    advs_n = agent._calc_advs({'returns': ret, 'values': vals, 'rand_action_mask': mask})
+    logits = torch.randn(64, 1, generator=g) * 4
+    agent._eval_disc = lambda x: logits
+    dr = agent._calc_disc_rewards(None)
+    z = torch.nn.functional.normalize(torch.randn(64, 64, generator=g), dim=-1)
+    ep = torch.nn.functional.normalize(torch.randn(64, 64, generator=g), dim=-1)
+    agent._eval_enc = lambda x: ep
+    er = agent._calc_enc_rewards(None, z)
+    comb = agent._combine_rewards(torch.zeros_like(dr), {'disc_rewards': dr, 'enc_rewards': er})
+    out = dict(fdones=fd, values=v, next_values=nv, rewards=r, advs=adv, mask=mask, advs_norm=advs_n,
+               logits=logits, disc_r=dr, z=z, enc_pred=ep, enc_r=er, combined=comb)
+    torch.save(out, os.path.join(OUT, 'rollout_math.pt'))
+    print('rollout_math.pt ok')
+
+
+if __name__ == '__main__':
+    os.makedirs(OUT, exist_ok=True)
+    torch.set_num_threads(8)
+    gen_obs()
+    gen_rollout_math()
+    gen_calc_gradients()

@@ -1,0 +1,181 @@
+"""[recollection of rl_games 1.1.4 algos_torch/network_builder.py] (MLP-only subset).
+The `Sequential(Linear, act, Linear, act, ...)` index pattern `.0/.2/.4` is confirmed by the
+shipped checkpoints' key names."""
+import torch
+import torch.nn as nn
+from rl_games.common import object_factory
+
+
+def _create_initializer(func, **kwargs):
+    return lambda v: func(v, **kwargs)
+
+
+class NetworkBuilder:
+    def __init__(self, **kwargs):
+        pass
+
+    def load(self, params):
+        pass
+
+    def build(self, name, **kwargs):
+        pass
+
+    def __call__(self, name, **kwargs):
+        return self.build(name, **kwargs)
+
+    class BaseNetwork(nn.Module):
+        def __init__(self, **kwargs):
+            nn.Module.__init__(self, **kwargs)
+            self.activations_factory = object_factory.ObjectFactory()
+            self.activations_factory.register_builder('relu', lambda **kwargs: nn.ReLU(**kwargs))
+            self.activations_factory.register_builder('tanh', lambda **kwargs: nn.Tanh(**kwargs))
+            self.activations_factory.register_builder('sigmoid', lambda **kwargs: nn.Sigmoid(**kwargs))
+            self.activations_factory.register_builder('elu', lambda **kwargs: nn.ELU(**kwargs))
+            self.activations_factory.register_builder('selu', lambda **kwargs: nn.SELU(**kwargs))
+            self.activations_factory.register_builder('softplus', lambda **kwargs: nn.Softplus(**kwargs))
+            self.activations_factory.register_builder('None', lambda **kwargs: nn.Identity())
+
+            self.init_factory = object_factory.ObjectFactory()
+            self.init_factory.register_builder('const_initializer', lambda **kwargs: _create_initializer(nn.init.constant_, **kwargs))
+            self.init_factory.register_builder('orthogonal_initializer', lambda **kwargs: _create_initializer(nn.init.orthogonal_, **kwargs))
+            self.init_factory.register_builder('glorot_normal_initializer', lambda **kwargs: _create_initializer(nn.init.xavier_normal_, **kwargs))
+            self.init_factory.register_builder('glorot_uniform_initializer', lambda **kwargs: _create_initializer(nn.init.xavier_uniform_, **kwargs))
+            self.init_factory.register_builder('random_uniform_initializer', lambda **kwargs: _create_initializer(nn.init.uniform_, **kwargs))
+            self.init_factory.register_builder('kaiming_normal', lambda **kwargs: _create_initializer(nn.init.kaiming_normal_, **kwargs))
+            self.init_factory.register_builder('orthogonal', lambda **kwargs: _create_initializer(nn.init.orthogonal_, **kwargs))
+            self.init_factory.register_builder('default', lambda **kwargs: nn.Identity())
+
+        def is_separate_critic(self):
+            return False
+
+        def is_rnn(self):
+            return False
+
+        def get_default_rnn_state(self):
+            return None
+
+        def _calc_input_size(self, input_shape, cnn_layers=None):
+            assert cnn_layers is None
+            return input_shape[0]
+
+        def _build_sequential_mlp(self, input_size, units, activation, dense_func,
+                                  norm_only_first_layer=False, norm_func_name=None):
+            in_size = input_size
+            layers = []
+            for unit in units:
+                layers.append(dense_func(in_size, unit))
+                layers.append(self.activations_factory.create(activation))
+                in_size = unit
+            return nn.Sequential(*layers)
+
+        def _build_mlp(self, input_size, units, activation, dense_func,
+                       norm_only_first_layer=False, norm_func_name=None, d2rl=False):
+            assert not d2rl
+            return self._build_sequential_mlp(input_size, units, activation, dense_func,
+                                              norm_func_name=None)
+
+
+class A2CBuilder(NetworkBuilder):
+    def __init__(self, **kwargs):
+        NetworkBuilder.__init__(self)
+
+    def load(self, params):
+        self.params = params
+
+    class Network(NetworkBuilder.BaseNetwork):
+        def __init__(self, params, **kwargs):
+            actions_num = kwargs.pop('actions_num')
+            input_shape = kwargs.pop('input_shape')
+            self.value_size = kwargs.pop('value_size', 1)
+            self.num_seqs = num_seqs = kwargs.pop('num_seqs', 1)
+            NetworkBuilder.BaseNetwork.__init__(self)
+            self.load(params)
+            self.actor_cnn = nn.Sequential()
+            self.critic_cnn = nn.Sequential()
+            self.actor_mlp = nn.Sequential()
+            self.critic_mlp = nn.Sequential()
+            assert not self.has_cnn and not self.has_rnn
+            mlp_input_shape = self._calc_input_size(input_shape, None)
+            in_mlp_shape = mlp_input_shape
+            if len(self.units) == 0:
+                out_size = mlp_input_shape
+            else:
+                out_size = self.units[-1]
+            mlp_args = {
+                'input_size': in_mlp_shape,
+                'units': self.units,
+                'activation': self.activation,
+                'norm_func_name': self.normalization,
+                'dense_func': torch.nn.Linear,
+                'd2rl': self.is_d2rl,
+                'norm_only_first_layer': self.norm_only_first_layer
+            }
+            self.actor_mlp = self._build_mlp(**mlp_args)
+            if self.separate:
+                self.critic_mlp = self._build_mlp(**mlp_args)
+
+            self.value = torch.nn.Linear(out_size, self.value_size)
+            self.value_act = self.activations_factory.create(self.value_activation)
+
+            assert self.is_continuous
+            self.mu = torch.nn.Linear(out_size, actions_num)
+            self.mu_act = self.activations_factory.create(self.space_config['mu_activation'])
+            mu_init = self.init_factory.create(**self.space_config['mu_init'])
+            self.sigma_act = self.activations_factory.create(self.space_config['sigma_activation'])
+            sigma_init = self.init_factory.create(**self.space_config['sigma_init'])
+
+            if self.space_config['fixed_sigma']:
+                self.sigma = nn.Parameter(torch.zeros(actions_num, requires_grad=True, dtype=torch.float32), requires_grad=True)
+            else:
+                self.sigma = torch.nn.Linear(out_size, actions_num)
+
+            mlp_init = self.init_factory.create(**self.initializer)
+            for m in self.modules():
+                if isinstance(m, nn.Linear):
+                    mlp_init(m.weight)
+                    if getattr(m, "bias", None) is not None:
+                        torch.nn.init.zeros_(m.bias)
+
+            mu_init(self.mu.weight)
+            if self.space_config['fixed_sigma']:
+                sigma_init(self.sigma)
+            else:
+                sigma_init(self.sigma.weight)
+
+        def forward(self, obs_dict):
+            raise NotImplementedError  # AMPBuilder.Network overrides forward
+
+        def is_separate_critic(self):
+            return self.separate
+
+        def is_rnn(self):
+            return self.has_rnn
+
+        def load(self, params):
+            self.separate = params.get('separate', False)
+            self.units = params['mlp']['units']
+            self.activation = params['mlp']['activation']
+            self.initializer = params['mlp']['initializer']
+            self.is_d2rl = params['mlp'].get('d2rl', False)
+            self.norm_only_first_layer = params['mlp'].get('norm_only_first_layer', False)
+            self.value_activation = params.get('value_activation', 'None')
+            self.normalization = params.get('normalization', None)
+            self.has_rnn = 'rnn' in params
+            self.has_space = 'space' in params
+            self.central_value = params.get('central_value', False)
+            self.joint_obs_actions_config = params.get('joint_obs_actions', None)
+            if self.has_space:
+                self.is_multi_discrete = 'multi_discrete' in params['space']
+                self.is_discrete = 'discrete' in params['space']
+                self.is_continuous = 'continuous' in params['space']
+                if self.is_continuous:
+                    self.space_config = params['space']['continuous']
+            else:
+                self.is_discrete = False
+                self.is_continuous = False
+                self.is_multi_discrete = False
+            self.has_cnn = 'cnn' in params
+
+    def build(self, name, **kwargs):
+        net = A2CBuilder.Network(self.params, **kwargs)
+        return net

@@ -1,0 +1,5 @@
+class RLScheduler:
+    def update(self, current_lr, entropy_coef, epoch, frames, **kwargs): pass
+class IdentityScheduler(RLScheduler):
+    def update(self, current_lr, entropy_coef, epoch, frames, kl_dist, **kwargs):
+        return current_lr, entropy_coef

@@ -1,0 +1,65 @@
+"""CPU suite, part 1: the travelling oracle (oracle/ase_oracle.py) against the committed outputs of the
+reference's own code (tests/golden/*.pt, produced by oracle/gen_golden.py in the build container)."""
+import torch
+import pytest
+
+import ase_oracle as O
+import synth
+import golden_util as G
+
+TOL = 2e-6   # oracle and reference are both fp32 torch CPU; expect (near) bit equality
+
+
+def test_obs_build_matches_reference_golden():
+    fx = G.load('obs_build.pt')
+    s = fx['inputs']
+    for lro in (True, False):
+        for rho in (True, False):
+            o = O.compute_humanoid_observations_max(s['body_pos'], s['body_rot'], s['body_vel'], s['body_ang_vel'], lro, rho)
+            assert torch.allclose(o, fx[f'obs_l{int(lro)}_h{int(rho)}'], rtol=1e-5, atol=1e-5)
+            kp = s['body_pos'][:, O.KEY_BODY_IDS_SWORD_SHIELD]
+            a = O.build_amp_observations(s['body_pos'][:, 0], s['body_rot'][:, 0], s['body_vel'][:, 0], s['body_ang_vel'][:, 0],
+                                         s['dof_pos'], s['dof_vel'], kp, lro, rho, O.DOF_OFFSETS_SWORD_SHIELD)
+            assert torch.allclose(a, fx[f'amp_l{int(lro)}_h{int(rho)}'], rtol=1e-5, atol=1e-5)
+
+
+def test_rollout_math_matches_reference_golden():
+    fx = G.load('rollout_math.pt')
+    adv = O.discount_values(fx['fdones'], fx['values'], fx['rewards'], fx['next_values'], 0.99, 0.95)
+    assert torch.allclose(adv, fx['advs'], rtol=1e-6, atol=1e-6)
+    ret = O.swap_and_flatten01(fx['advs'] + fx['values']); vals = O.swap_and_flatten01(fx['values'])
+    assert torch.allclose(O.calc_advs(ret, vals, fx['mask']), fx['advs_norm'], rtol=1e-5, atol=1e-6)
+    assert torch.allclose(O.disc_rewards(fx['logits'], 2.0), fx['disc_r'], rtol=1e-6, atol=1e-7)
+    assert torch.allclose(O.enc_rewards(fx['enc_pred'], fx['z'], 1.0), fx['enc_r'], rtol=1e-6, atol=1e-7)
+    assert torch.allclose(0.5 * fx['disc_r'] + 0.5 * fx['enc_r'], fx['combined'], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize('name', ['calc_grad_ase_small.pt', 'calc_grad_ase_cfg1.pt', 'calc_grad_amp_cfg.pt'])
+def test_calc_gradients_matches_reference_golden(name):
+    meta, steps, shapes, P = G.calc_grad_case(name)
+    st = O.LearnerState(P, 253, 1400, meta['kind'])
+    cfg = meta['cfg']
+    for s, rec in enumerate(steps):
+        d, new_z = synth.minibatch(st, cfg, meta['B'], meta['Ba'], seed=meta['seed'] * 100 + s, kind=meta['kind'])
+        res, grads = O.calc_gradients(st, d, cfg, new_z)
+        for k, v in rec['scalars'].items():
+            assert abs(float(res[k]) - v) <= 1e-5 * max(1.0, abs(v)), (k, float(res[k]), v)
+        assert torch.allclose(res['disc_agent_logit'].flatten(), rec['disc_agent_logit'], rtol=1e-5, atol=1e-5)
+        for k, g in grads.items():
+            idx = G.sample_idx(g.numel())
+            assert G.rel_err(g.flatten()[idx], rec['grad_sample'][k]) < 1e-4 or float(rec['grad_sample'][k].abs().max()) < 1e-12, k
+            assert abs(float(g.double().norm()) - rec['grad_norm'][k]) <= 1e-4 * max(rec['grad_norm'][k], 1e-12), k
+            assert torch.allclose(st.p[k].flatten()[idx], rec['param_sample'][k], rtol=1e-6, atol=1e-7), k
+            if 'grads' in rec:
+                assert G.rel_err(g, rec['grads'][k]) < 1e-4, k
+        assert torch.allclose(st.obs_rms.mean, rec['rms']['obs_mean']) and torch.allclose(st.obs_rms.var, rec['rms']['obs_var'])
+        assert torch.allclose(st.amp_rms.mean, rec['rms']['amp_mean']) and torch.allclose(st.amp_rms.var, rec['rms']['amp_var'])
+        assert float(st.amp_rms.count) == float(rec['rms']['amp_count'])
+
+
+def test_rms_count_arithmetic_matches_checkpoint_identity():
+    """AMP RMS is updated 3x per minibatch with amp_minibatch rows, count starts at 1."""
+    r = O.RMS(4)
+    for _ in range(3):
+        r.train_forward(torch.randn(16, 4))
+    assert float(r.count) == 1 + 3 * 16
