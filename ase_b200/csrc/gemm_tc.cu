@@ -1,0 +1,376 @@
+// tcgen05 3xTF32 GEMM for sm_100a: fp32-accurate products on the 5th-gen tensor cores.
+//
+//   C[M,N] = epi(alpha * A . B^T),  A = A_hi + A_lo, B = B_hi + B_lo   (each part exactly representable in TF32)
+//   A.B^T ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo       (dropped A_lo.B_lo term is 2^-24 relative)
+//
+// Pipeline (one 128 x BN output tile per CTA, 192 threads):
+//   prep kernels : split (and transpose when the caller's operand is MN-major) each operand into K-major
+//                  hi/lo planes [rows, Kp] in the caller-provided workspace (Kp = K rounded up to 32, zero padded)
+//   warp 0       : TMA producer  -- cp.async.bulk.tensor 2D tiles (128B-swizzled, 32 fp32 = 128 B per row) into a
+//                  3-stage shared-memory ring, completion on mbarriers
+//   warp 1       : MMA issuer    -- one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8), 3 MMAs per k-slice,
+//                  accumulating in TMEM; tcgen05.commit frees the smem stage / signals the epilogue
+//   warps 2..5   : epilogue      -- tcgen05.ld 32x32b (one accumulator row per thread), fused bias / ReLU / tanh /
+//                  mask / alpha, direct global stores (or fp32 RED for split-K accumulation)
+// Descriptor formats follow the PTX ISA "tcgen05 shared memory descriptor" / "instruction descriptor" tables
+// (cross-checked against cute/arch/mma_sm100_desc.hpp in the image's CUTLASS headers).
+#include <cuda.h>
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ase {
+
+constexpr int TC_BM = 128;
+constexpr int TC_BK = 32;                 // fp32 elements per k-block = one 128-byte swizzle row
+constexpr int TC_THREADS = 192;
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(addr), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread `lane` receives row (lane_base + lane), columns [col, col+32)
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte swizzle: 8-row x 128 B atoms, 1024 B between 8-row groups.
+//   bits [0,14) start address >> 4 | [16,30) LBO >> 4 (=1, unused for swizzled K-major) | [32,46) SBO >> 4 (=64)
+//   bits [46,48) version = 1 (sm_100) | [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+struct TcEpi {
+  float* C; int64_t ldc;
+  int M, N;
+  int kb_total, kb_per_split;
+  float alpha;
+  const float* bias;
+  int act;
+  const float* mask_src; int64_t ldm; int mask_mode;
+  int accumulate;
+};
+
+template <int BN, int STAGES>
+struct TcSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 4;           // 16 KB per plane
+  static constexpr int B_BYTES = BN * TC_BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const TcEpi e) {
+  using SM = TcSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tmem_full = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int kb_begin = blockIdx.z * e.kb_per_split;
+  const int nkb = min(e.kb_per_split, e.kb_total - kb_begin);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], SM::STAGE_BYTES);
+        uint8_t* st = smem + s * SM::STAGE_BYTES;
+        const int k0 = (kb_begin + kb) * TC_BK;
+        tma_load_2d(st, &tmAhi, &full[s], k0, m0);
+        tma_load_2d(st + SM::A_BYTES, &tmAlo, &full[s], k0, m0);
+        tma_load_2d(st + 2 * SM::A_BYTES, &tmBhi, &full[s], k0, n0);
+        tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmBlo, &full[s], k0, n0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2), K-major A/B, N>>3 at 17, M>>4 at 24
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
+        const uint32_t a_hi = sa, a_lo = sa + SM::A_BYTES, b_hi = sa + 2 * SM::A_BYTES, b_lo = b_hi + SM::B_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          const uint32_t ko = k * 32;   // 8 tf32 = 32 bytes along the swizzled row
+          const uint64_t dah = make_smem_desc(a_hi + ko), dal = make_smem_desc(a_lo + ko);
+          const uint64_t dbh = make_smem_desc(b_hi + ko), dbl = make_smem_desc(b_lo + ko);
+          tc_mma_tf32(tmem_base, dal, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);   // small terms first
+          tc_mma_tf32(tmem_base, dah, dbl, idesc, 1u);
+          tc_mma_tf32(tmem_base, dah, dbh, idesc, 1u);
+        }
+        tc_commit(&empty[s]);          // frees this smem stage once the MMAs above have read it
+      }
+      tc_commit(tmem_full);            // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // epilogue warps 2..5 own TMEM lane groups (warp % 4)
+    const int lg = warp & 3;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    const int m = m0 + lg * 32 + lane;
+    const bool row_ok = m < e.M;
+    const bool vec_ok = ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0);
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      float v[32];
+      tc_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, v);
+      const int nb = n0 + c;
+      if (!row_ok || nb >= e.N) continue;
+      float* crow = e.C + (int64_t)m * e.ldc + nb;
+      const int nvalid = min(32, e.N - nb);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float x = e.alpha * v[j];
+        if (j < nvalid) {
+          if (e.accumulate) {
+            if (e.bias && blockIdx.z == 0) x += e.bias[nb + j];
+          } else {
+            if (e.bias) x += e.bias[nb + j];
+            if (e.act == 1) x = fmaxf(x, 0.0f);
+            else if (e.act == 2) x = tanhf(x);
+            if (e.mask_mode == 1) x = (e.mask_src[(int64_t)m * e.ldm + nb + j] > 0.0f) ? x : 0.0f;
+            else if (e.mask_mode == 2) { const float s = e.mask_src[(int64_t)m * e.ldm + nb + j]; x *= (1.0f - s * s); }
+          }
+        }
+        v[j] = x;
+      }
+      if (e.accumulate) {
+        for (int j = 0; j < nvalid; ++j) atomicAdd(crow + j, v[j]);
+      } else if (vec_ok && nvalid == 32) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      } else {
+        for (int j = 0; j < nvalid; ++j) crow[j] = v[j];
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ operand prep
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  const float r = x - hi;                       // exact
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
+  lo = __uint_as_float(l);
+}
+
+// source is K-major: src[r*ld + k]
+__global__ void __launch_bounds__(256)
+tc_prep_plain_kernel(const float* __restrict__ src, int64_t ld, int rows, int K, int Kp, float* __restrict__ hi, float* __restrict__ lo) {
+  const int64_t total = (int64_t)rows * Kp;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / Kp), k = (int)(i - (int64_t)r * Kp);
+    float h = 0.0f, l = 0.0f;
+    if (k < K) split_tf32(src[(int64_t)r * ld + k], h, l);
+    hi[i] = h; lo[i] = l;
+  }
+}
+
+// source is MN-major: src[k*ld + r]  ->  dst[r*Kp + k]   (32x32 tiles through shared memory)
+__global__ void __launch_bounds__(256)
+tc_prep_transpose_kernel(const float* __restrict__ src, int64_t ld, int rows, int K, int Kp, float* __restrict__ hi, float* __restrict__ lo) {
+  __shared__ float tile[32][33];
+  const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int k = k0 + i, r = r0 + tx;
+    tile[i][tx] = (k < K && r < rows) ? src[(int64_t)k * ld + r] : 0.0f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int r = r0 + i, k = k0 + tx;
+    if (r < rows && k < Kp) {
+      float h, l;
+      split_tf32(tile[tx][i], h, l);
+      hi[(int64_t)r * Kp + k] = h; lo[(int64_t)r * Kp + k] = l;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+static int make_map(CUtensorMap* tm, const float* base, int rows, int Kp, int box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return ASE_ERR_UNSUPPORTED; }
+  cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)Kp * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %d, Kp %d)", (int)r, rows, Kp); return ASE_ERR_CUDA; }
+  return ASE_OK;
+}
+
+static inline int kpad(int K) { return (K + TC_BK - 1) / TC_BK * TC_BK; }
+
+int64_t gemm_tc_workspace_bytes(int M, int N, int K) {
+  const int64_t Kp = kpad(K);
+  return 2 * align_up((int64_t)M * Kp * 4, 1024) + 2 * align_up((int64_t)N * Kp * 4, 1024);
+}
+
+bool gemm_tc_supported(const AseGemmParams& p) {
+  if (p.M < 128 || p.N < 64 || p.K < 32) return false;
+  if (!p.workspace || p.workspace_bytes < gemm_tc_workspace_bytes(p.M, p.N, p.K)) return false;
+  if (reinterpret_cast<uintptr_t>(p.workspace) & 1023) return false;
+  return true;
+}
+
+static int prep_operand(const float* src, int64_t ld, int trans, int rows, int K, int Kp, float* hi, float* lo, cudaStream_t st) {
+  if (!trans) {
+    const int64_t total = (int64_t)rows * Kp;
+    tc_prep_plain_kernel<<<(int)imin64((total + 255) / 256, 148 * 16), 256, 0, st>>>(src, ld, rows, K, Kp, hi, lo);
+  } else {
+    dim3 grid(ceil_div(rows, 32), Kp / 32);
+    tc_prep_transpose_kernel<<<grid, 256, 0, st>>>(src, ld, rows, K, Kp, hi, lo);
+  }
+  ASE_LAUNCH_OK();
+  return ASE_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcEpi& e,
+                     int splits, cudaStream_t st) {
+  using SM = TcSmem<BN, STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ASE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(e.N, BN), ceil_div(e.M, TC_BM), splits);
+  gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, SM::TOTAL, st>>>(ah, al, bh, bl, e);
+  ASE_LAUNCH_OK();
+  return ASE_OK;
+}
+
+int gemm_tc(const AseGemmParams& p, cudaStream_t st) {
+  const int Kp = kpad(p.K);
+  char* ws = (char*)p.workspace;
+  float* Ahi = (float*)ws; ws += align_up((int64_t)p.M * Kp * 4, 1024);
+  float* Alo = (float*)ws; ws += align_up((int64_t)p.M * Kp * 4, 1024);
+  float* Bhi = (float*)ws; ws += align_up((int64_t)p.N * Kp * 4, 1024);
+  float* Blo = (float*)ws;
+  // A operand: K-major already when a_trans == 0 ([M,K]); B operand: K-major when b_trans == 0 ([N,K])
+  int rc = prep_operand(p.A, p.lda, p.a_trans, p.M, p.K, Kp, Ahi, Alo, st);
+  if (rc) return rc;
+  rc = prep_operand(p.B, p.ldb, p.b_trans, p.N, p.K, Kp, Bhi, Blo, st);
+  if (rc) return rc;
+  const int BN = (p.N >= 128) ? 128 : 64;
+  CUtensorMap ah, al, bh, bl;
+  if ((rc = make_map(&ah, Ahi, p.M, Kp, TC_BM))) return rc;
+  if ((rc = make_map(&al, Alo, p.M, Kp, TC_BM))) return rc;
+  if ((rc = make_map(&bh, Bhi, p.N, Kp, BN))) return rc;
+  if ((rc = make_map(&bl, Blo, p.N, Kp, BN))) return rc;
+  TcEpi e;
+  e.C = p.C; e.ldc = p.ldc; e.M = p.M; e.N = p.N; e.alpha = p.alpha; e.bias = p.bias; e.act = p.act;
+  e.mask_src = p.mask_src; e.ldm = p.ldm; e.mask_mode = p.mask_src ? p.mask_mode : 0; e.accumulate = p.accumulate;
+  e.kb_total = Kp / TC_BK;
+  int splits = (p.accumulate && p.split_k > 1) ? p.split_k : 1;
+  splits = min(splits, e.kb_total);
+  e.kb_per_split = ceil_div(e.kb_total, splits);
+  splits = ceil_div(e.kb_total, e.kb_per_split);
+  if (BN == 128) return launch_tc<128, 3>(ah, al, bh, bl, e, splits, st);
+  return launch_tc<64, 4>(ah, al, bh, bl, e, splits, st);
+}
+
+}  // namespace ase

@@ -1,0 +1,67 @@
+// Internal (non-ABI) declarations shared by the .cu files of libase_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/ase_b200.h"
+
+namespace ase {
+
+// ------------------------------------------------------------------ RunningMeanStd
+struct RmsBatchList { const float* x[3]; int64_t ld[3]; int rows; };
+struct RmsDst { float* y[3]; int64_t ld[3]; };
+int64_t rms_scratch_bytes(int cols, int rows, int nbatch);
+int rms_update_batches(const RmsBatchList& bl, int nbatch, int cols, double* mean, double* var, double* count, float eps,
+                       int update, void* scratch, float** meanf_out, float** stdf_out, cudaStream_t st);
+int rms_normalize(const float* x, int64_t ldx, int rows, int cols, const float* meanf, const float* stdf, int unnorm,
+                  const RmsDst& dst, cudaStream_t st);
+int rms_apply(const float* x, int64_t ldx, int rows, int cols, const double* mean, const double* var, float eps, int unnorm,
+              float* y, int64_t ldy, cudaStream_t st);
+int copy_cols(const float* x, int64_t ldx, int rows, int cols, float* y, int64_t ldy, cudaStream_t st);
+
+// ------------------------------------------------------------------ GEMM backends
+int gemm_simt(const AseGemmParams& p, cudaStream_t st);
+int gemm_tc(const AseGemmParams& p, cudaStream_t st);          // tcgen05 3xTF32 (gemm_tc.cu)
+bool gemm_tc_supported(const AseGemmParams& p);
+int64_t gemm_tc_workspace_bytes(int M, int N, int K);
+int gemm_dispatch(const AseGemmParams& p, cudaStream_t st);    // picks the backend named in p.backend (falls back to SIMT for shapes tc rejects)
+
+// ------------------------------------------------------------------ loss-side accumulators (doubles)
+enum {
+  ACC_MSUM = 0, ACC_ALOSS, ACC_CLOSS, ACC_BLOSS, ACC_CLIPPED, ACC_KL, ACC_DIV,
+  ACC_BCE_AGENT, ACC_BCE_DEMO, ACC_ACC_AGENT, ACC_ACC_DEMO, ACC_LOGIT_AGENT, ACC_LOGIT_DEMO,
+  ACC_GP, ACC_WLOGIT2, ACC_WDISC2, ACC_ENC, ACC_COUNT = 24
+};
+
+struct PpoHeadArgs {
+  const float* mu; int64_t ld_mu;      // [B or 2B, A]; rows B.. hold the diversity pass
+  const float* values;                 // [B]
+  const float* actions; const float* old_logp; const float* adv; const float* old_mu; const float* old_sigma;
+  const float* returns; const float* mask; const float* logstd;
+  const float* z; const float* z2; int Z;
+  int B, A;
+  int has_div;
+  float e_clip, critic_coef, bounds_coef, div_bonus, div_tar;
+  float* dmu;                          // same layout as mu
+  float* dv;                           // [B]
+  double* acc;
+};
+
+struct FinalizeArgs {
+  const double* acc; float* out; const float* logstd;
+  int kind, B, Ba, A;
+  float critic_coef, entropy_coef, bounds_coef, disc_coef, logit_reg, gp_coef, weight_decay, enc_coef, div_bonus;
+};
+
+int launch_mask_sum(const float* mask, int rows, double* acc, cudaStream_t st);
+int launch_ppo_head(const PpoHeadArgs& a, cudaStream_t st);
+int launch_disc_head(const float* logit, int Ba, float disc_coef, float* dlogit, double* acc, float* out_agent, float* out_demo, cudaStream_t st);
+int launch_enc_head(const float* e, int rows, int Z, const float* z, float enc_coef, float* de, float* enc_pred, double* acc, cudaStream_t st);
+int launch_gp_u_last(const float* h, int64_t ldh, int rows, int cols, const float* w, float* u, cudaStream_t st);
+int launch_gp_scale(float* g, int64_t total, float scale, double* acc, cudaStream_t st);
+int launch_colsum(const float* dz, int64_t ld, int rows, int cols, float* db, cudaStream_t st);
+int launch_weight_reg(const float* w, float* g, int64_t n, float coef, double* acc, int idx, int idx2, cudaStream_t st);
+int launch_finalize(const FinalizeArgs& f, cudaStream_t st);
+int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float grad_scale, float b1, float b2, float lr, float eps,
+                int64_t step, cudaStream_t st);
+
+}  // namespace ase

@@ -1,0 +1,188 @@
+// RunningMeanStd (rl_games 1.1.4 algos_torch/running_mean_std.py): fp64 running moments, fp32 data.
+// Column statistics are accumulated in fp64 (threads map to columns => coalesced row reads), merged with
+// the parallel-Welford rule of the reference, and the normalise/clamp pass uses the UPDATED statistics
+// exactly as the reference's train-mode forward does.  Up to 3 batches can be merged sequentially in one
+// launch (the three AMP batches of calc_gradients, ase_agent.py:170-181).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace ase {
+
+constexpr int RMS_COLS_PER_BLOCK = 128;
+constexpr int RMS_ROWS_PER_BLOCK = 64;
+
+// partial[(batch*chunks + chunk)*cols + col] = (sum, sumsq) over the chunk's rows
+__global__ void __launch_bounds__(RMS_COLS_PER_BLOCK)
+rms_colstats_kernel(RmsBatchList bl, int cols, int chunks, double2* __restrict__ partial) {
+  const int col = blockIdx.x * RMS_COLS_PER_BLOCK + threadIdx.x;
+  const int chunk = blockIdx.y, batch = blockIdx.z;
+  if (col >= cols) return;
+  const float* x = bl.x[batch];
+  const int64_t ld = bl.ld[batch];
+  const int rows = bl.rows;
+  const int r0 = chunk * RMS_ROWS_PER_BLOCK, r1 = min(rows, r0 + RMS_ROWS_PER_BLOCK);
+  double s = 0.0, ss = 0.0;
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r) {
+    const double v = (double)x[(int64_t)r * ld + col];
+    s += v; ss += v * v;
+  }
+  partial[((int64_t)batch * chunks + chunk) * cols + col] = make_double2(s, ss);
+}
+
+// One thread per column: reduce the chunk partials, merge batch after batch, emit fp32 mean / std per batch.
+__global__ void rms_finalize_kernel(const double2* __restrict__ partial, int cols, int chunks, int nbatch, int rows,
+                                    double* __restrict__ mean, double* __restrict__ var, const double* __restrict__ count,
+                                    float eps, float* __restrict__ meanf, float* __restrict__ stdf, int update) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= cols) return;
+  double m = mean[col], v = var[col], c = count[0];
+  for (int b = 0; b < nbatch; ++b) {
+    if (update) {
+      double s = 0.0, ss = 0.0;
+      for (int k = 0; k < chunks; ++k) {
+        const double2 p = partial[((int64_t)b * chunks + k) * cols + col];
+        s += p.x; ss += p.y;
+      }
+      const double n = (double)rows;
+      // the reference's batch moments are fp32 tensors (input.mean(0), input.var(0)): round like it does
+      const double bm = (double)(float)(s / n);
+      double bvar = (ss - s * s / n) / (n - 1.0);
+      if (bvar < 0.0) bvar = 0.0;
+      bvar = (double)(float)bvar;
+      const double delta = bm - m, tot = c + n;
+      const double m2 = v * c + bvar * n + delta * delta * c * n / tot;
+      m = m + delta * n / tot;
+      v = m2 / tot;
+      c = tot;
+    }
+    meanf[b * cols + col] = (float)m;
+    stdf[b * cols + col] = sqrtf((float)v + eps);
+  }
+  if (update) { mean[col] = m; var[col] = v; }
+}
+
+__global__ void rms_count_add_kernel(double* count, double inc) { count[0] += inc; }
+
+// y = clamp((x-mean)/std, -5, 5) written to up to 3 destinations (unnorm: std*clamp(x,+-5)+mean)
+__global__ void __launch_bounds__(256)
+rms_normalize_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols,
+                     const float* __restrict__ meanf, const float* __restrict__ stdf, int unnorm, RmsDst dst) {
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+    const float v = x[(int64_t)r * ldx + c];
+    float y;
+    if (unnorm) y = stdf[c] * fminf(fmaxf(v, -5.0f), 5.0f) + meanf[c];
+    else y = fminf(fmaxf((v - meanf[c]) / stdf[c], -5.0f), 5.0f);
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      if (dst.y[d]) dst.y[d][(int64_t)r * dst.ld[d] + c] = y;
+  }
+}
+
+// just copy columns (used to place latents next to the normalised observations)
+__global__ void __launch_bounds__(256)
+copy_cols_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, float* __restrict__ y, int64_t ldy) {
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+    y[(int64_t)r * ldy + c] = x[(int64_t)r * ldx + c];
+  }
+}
+
+int64_t rms_scratch_bytes(int cols, int rows, int nbatch) {
+  const int chunks = ceil_div(rows, RMS_ROWS_PER_BLOCK);
+  return align_up((int64_t)nbatch * chunks * cols * sizeof(double2), 256) + align_up((int64_t)2 * nbatch * cols * sizeof(float), 256);
+}
+
+// Merge `nbatch` batches sequentially into (mean,var,count); meanf/stdf[b] are the fp32 stats valid after batch b.
+int rms_update_batches(const RmsBatchList& bl, int nbatch, int cols, double* mean, double* var, double* count, float eps,
+                       int update, void* scratch, float** meanf_out, float** stdf_out, cudaStream_t st) {
+  const int rows = bl.rows;
+  const int chunks = ceil_div(rows, RMS_ROWS_PER_BLOCK);
+  double2* partial = (double2*)scratch;
+  float* meanf = (float*)((char*)scratch + align_up((int64_t)nbatch * chunks * cols * sizeof(double2), 256));
+  float* stdf = meanf + (int64_t)nbatch * cols;
+  if (update) {
+    ASE_CHECK_ARG(rows >= 2, "RunningMeanStd update needs >= 2 rows (unbiased variance)");
+    dim3 grid(ceil_div(cols, RMS_COLS_PER_BLOCK), chunks, nbatch);
+    rms_colstats_kernel<<<grid, RMS_COLS_PER_BLOCK, 0, st>>>(bl, cols, chunks, partial);
+    ASE_LAUNCH_OK();
+  }
+  rms_finalize_kernel<<<ceil_div(cols, 128), 128, 0, st>>>(partial, cols, chunks, nbatch, rows, mean, var, count, eps, meanf, stdf, update);
+  ASE_LAUNCH_OK();
+  if (update) {
+    rms_count_add_kernel<<<1, 1, 0, st>>>(count, (double)rows * nbatch);
+    ASE_LAUNCH_OK();
+  }
+  *meanf_out = meanf; *stdf_out = stdf;
+  return ASE_OK;
+}
+
+int rms_normalize(const float* x, int64_t ldx, int rows, int cols, const float* meanf, const float* stdf, int unnorm,
+                  const RmsDst& dst, cudaStream_t st) {
+  const int64_t total = (int64_t)rows * cols;
+  const int blocks = (int)imin64((total + 255) / 256, 148 * 16);
+  rms_normalize_kernel<<<blocks, 256, 0, st>>>(x, ldx, rows, cols, meanf, stdf, unnorm, dst);
+  ASE_LAUNCH_OK();
+  return ASE_OK;
+}
+
+int copy_cols(const float* x, int64_t ldx, int rows, int cols, float* y, int64_t ldy, cudaStream_t st) {
+  const int64_t total = (int64_t)rows * cols;
+  const int blocks = (int)imin64((total + 255) / 256, 148 * 16);
+  copy_cols_kernel<<<blocks, 256, 0, st>>>(x, ldx, rows, cols, y, ldy);
+  ASE_LAUNCH_OK();
+  return ASE_OK;
+}
+
+}  // namespace ase
+
+using namespace ase;
+
+extern "C" int64_t ase_rms_scratch_bytes(int rows, int cols) { return rms_scratch_bytes(cols, rows, 1); }
+
+extern "C" int ase_rms_update(const float* x, int64_t ldx, int rows, int cols, double* mean, double* var, double* count,
+                              float eps, float* y, int64_t ldy, void* scratch, void* stream) {
+  ASE_CHECK_ARG(x && mean && var && count && scratch, "ase_rms_update: null pointer");
+  RmsBatchList bl; bl.x[0] = x; bl.ld[0] = ldx; bl.rows = rows;
+  float *meanf, *stdf;
+  int rc = rms_update_batches(bl, 1, cols, mean, var, count, eps, 1, scratch, &meanf, &stdf, (cudaStream_t)stream);
+  if (rc) return rc;
+  if (y) {
+    RmsDst d = {}; d.y[0] = y; d.ld[0] = ldy;
+    return rms_normalize(x, ldx, rows, cols, meanf, stdf, 0, d, (cudaStream_t)stream);
+  }
+  return ASE_OK;
+}
+
+namespace ase {
+// eval-mode normalisation straight from the fp64 stats (no scratch): used by rollout inference
+__global__ void __launch_bounds__(256)
+rms_apply_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, const double* __restrict__ mean,
+                 const double* __restrict__ var, float eps, int unnorm, float* __restrict__ y, int64_t ldy) {
+  const int64_t total = (int64_t)rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+    const float v = x[(int64_t)r * ldx + c];
+    const float m = (float)mean[c], s = sqrtf((float)var[c] + eps);
+    y[(int64_t)r * ldy + c] = unnorm ? (s * fminf(fmaxf(v, -5.0f), 5.0f) + m) : fminf(fmaxf((v - m) / s, -5.0f), 5.0f);
+  }
+}
+int rms_apply(const float* x, int64_t ldx, int rows, int cols, const double* mean, const double* var, float eps, int unnorm,
+              float* y, int64_t ldy, cudaStream_t st) {
+  const int64_t total = (int64_t)rows * cols;
+  if (total == 0) return ASE_OK;
+  const int blocks = (int)imin64((total + 255) / 256, 148 * 16);
+  rms_apply_kernel<<<blocks, 256, 0, st>>>(x, ldx, rows, cols, mean, var, eps, unnorm, y, ldy);
+  ASE_LAUNCH_OK();
+  return ASE_OK;
+}
+}  // namespace ase
+
+extern "C" int ase_rms_apply(const float* x, int64_t ldx, int rows, int cols, const double* mean, const double* var,
+                             float eps, int unnorm, float* y, int64_t ldy, void* stream) {
+  ASE_CHECK_ARG(x && mean && var && y, "ase_rms_apply: null pointer");
+  return rms_apply(x, ldx, rows, cols, mean, var, eps, unnorm, y, ldy, (cudaStream_t)stream);
+}

@@ -1,0 +1,243 @@
+/*
+ * ase_b200.h -- C ABI of the B200-native ASE/AMP training engine (libase_b200.so).
+ *
+ * The reference (nv-tlabs/ASE) is pure Python and has no FFI; each entry point below replaces a
+ * Python/torch call site of the reference (cited as file:line relative to /root/reference/ase/).
+ * Conventions
+ *   - every pointer is a DEVICE pointer borrowed from the caller (PyTorch keeps ownership); the
+ *     library never allocates or frees user-visible memory; the only internal memory is the
+ *     caller-provided workspace handed to ase_learner_create;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, no hidden host syncs;
+ *   - matrices are row-major fp32 with an explicit leading dimension where noted; RunningMeanStd
+ *     statistics are fp64 (rl_games checkpoint contract); dones are uint8;
+ *   - return value: 0 on success, negative AseStatus on failure; ase_last_error() gives the text.
+ */
+#ifndef ASE_B200_H_
+#define ASE_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ASE_ABI_VERSION 1
+#define ASE_MAX_LAYERS 4
+
+typedef enum {
+  ASE_OK = 0,
+  ASE_ERR_INVALID = -1,     /* bad argument / unsupported shape */
+  ASE_ERR_CUDA = -2,        /* a CUDA runtime / driver call failed */
+  ASE_ERR_WORKSPACE = -3,   /* workspace too small or misaligned */
+  ASE_ERR_UNSUPPORTED = -4  /* feature needs sm_100a hardware that is not present */
+} AseStatus;
+
+int ase_abi_version(void);
+const char* ase_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches counter) */
+uint64_t ase_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Observation build (env side).  Replaces the TorchScript functions
+ *   compute_humanoid_observations_max   env/tasks/humanoid.py:591-635  (+ _compute_humanoid_obs :395-409)
+ *   build_amp_observations + dof_to_obs env/tasks/humanoid_amp.py:282-316, humanoid.py:522-552
+ *   _update_hist_amp_obs                env/tasks/humanoid_amp.py:248-255
+ * Rigid-body state is the Isaac Gym layout [N, bodies_per_env, 13] = pos3, quat xyzw 4, vel3, angvel3
+ * (humanoid.py:82-89); strides are in floats so strided views are accepted.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* body_state;    /* [N, *, 13] */
+  int64_t env_stride;         /* floats between envs */
+  int64_t body_stride;        /* floats between bodies (13 for the native layout) */
+  int num_envs;
+  int num_bodies;             /* J (17 for amp_humanoid_sword_shield.xml) */
+  int local_root_obs;         /* humanoid.py:622-624 quirk reproduced when non-zero */
+  int root_height_obs;
+  const int32_t* env_ids;     /* optional subset (reset path, humanoid.py:395-409); NULL = all */
+  int num_env_ids;
+  float* obs;                 /* [N, obs_ld]; row e (or env_ids[i]) is written */
+  int64_t obs_ld;             /* >= 1 + (J-1)*3 + J*6 + J*3 + J*3 */
+} AseObsBuildParams;
+int ase_obs_build(const AseObsBuildParams* p, void* stream);
+
+typedef struct {
+  const float* body_state; int64_t env_stride; int64_t body_stride;
+  const float* dof_pos; int64_t dof_pos_ld;   /* [N, num_dofs] */
+  const float* dof_vel; int64_t dof_vel_ld;
+  int num_envs;
+  int num_dofs;                /* 31 */
+  int num_joints;              /* 13 */
+  const int32_t* dof_offsets;  /* HOST pointer, num_joints+1 entries (humanoid.py:192); joint size 1 or 3 */
+  int num_key_bodies;          /* 6 */
+  const int32_t* key_body_ids; /* HOST pointer */
+  int local_root_obs; int root_height_obs;
+  const int32_t* env_ids; int num_env_ids;  /* optional subset (reset path, humanoid_amp.py:257-275) */
+  float* amp_obs;              /* [N, hist_steps, step_dim] contiguous (humanoid_amp.py:42-44) */
+  int hist_steps;              /* 10 */
+  int step_dim;                /* 13 + 6*num_joints + num_dofs + 3*num_key_bodies = 140 */
+  int shift_history;           /* 1: slots i -> i+1 first (post_physics_step path, humanoid_amp.py:50-59) */
+} AseAmpObsBuildParams;
+int ase_amp_obs_build(const AseAmpObsBuildParams* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * RunningMeanStd  (rl_games 1.1.4 algos_torch/running_mean_std.py; call sites common_agent.py:364,
+ * amp_agent.py:535-538, ase_agent.py:118,170-181).  mean/var/count are fp64 device buffers
+ * (count is a 1-element buffer).  scratch: >= ase_rms_scratch_bytes(rows, cols) bytes.
+ * ---------------------------------------------------------------------------------------------- */
+int64_t ase_rms_scratch_bytes(int rows, int cols);
+/* train-mode forward: update stats with the unbiased batch moments of x[rows, cols], then (if y)
+ * y = clamp((x-mean)/sqrt(var+eps), -5, 5) with the UPDATED stats. */
+int ase_rms_update(const float* x, int64_t ldx, int rows, int cols,
+                   double* mean, double* var, double* count, float eps,
+                   float* y, int64_t ldy, void* scratch, void* stream);
+/* eval-mode forward (unnorm=0) or value de-normalisation (unnorm=1: sqrt(var+eps)*clamp(x,+-5)+mean) */
+int ase_rms_apply(const float* x, int64_t ldx, int rows, int cols,
+                  const double* mean, const double* var, float eps, int unnorm,
+                  float* y, int64_t ldy, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Rollout-side math
+ * ---------------------------------------------------------------------------------------------- */
+/* discount_values, learning/common_agent.py:437-449.  All inputs [H, N] (value_size 1), dones uint8.
+ * Writes advs[H,N] and (if non-NULL) returns = advs + values. */
+int ase_gae(const uint8_t* dones, const float* values, const float* rewards, const float* next_values,
+            int horizon, int num_envs, float gamma, float tau, float* advs, float* returns, void* stream);
+/* _calc_disc_rewards amp_agent.py:570-577, _calc_enc_rewards ase_agent.py:404-411,469-472,
+ * _combine_rewards ase_agent.py:484-490.  enc_pred/latents may be NULL (AMP). */
+int ase_amp_rewards(const float* disc_logits, const float* enc_pred, const float* latents, int latent_dim,
+                    int rows, float disc_scale, float enc_scale,
+                    const float* task_rewards, float task_w, float disc_w, float enc_w,
+                    float* disc_r, float* enc_r, float* combined, void* stream);
+/* _calc_advs amp_agent.py:551-561 (+ torch_ext.normalization_with_masks); mask NULL => plain
+ * mean / unbiased std (common_agent.py:536-546).  scratch >= 64 bytes. */
+int ase_adv_normalize(const float* returns, const float* values, const float* mask, int rows,
+                      float* advs, void* scratch, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * GEMM primitives (exposed for tests / profiling; the learner drives them internally).
+ *   C[M,N] = epilogue( alpha * op(A) . op(B) )          fp32 in, fp32 accumulate, fp32 out
+ *   a_trans = 0: A is [M,K] row-major (lda);  1: A is [K,M] row-major
+ *   b_trans = 0: B is [N,K] row-major (ldb) (torch Linear weight);  1: B is [K,N] row-major
+ *   epilogue: + bias[N]; act 0 none / 1 relu / 2 tanh; mask_mode 1: *= (mask_src>0), 2: *= (1-mask_src^2);
+ *   accumulate 1: C += result (atomic when split_k > 1)
+ *   backend 0: SIMT fp32 FFMA kernel; 1: tcgen05 3xTF32 tensor-core kernel (sm_100a; operands are
+ *   split on the fly into TF32 hi/lo pairs -- see DESIGN.md "GEMM").
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float* A; int64_t lda; int a_trans;
+  const float* B; int64_t ldb; int b_trans;
+  float* C; int64_t ldc;
+  int M, N, K;
+  float alpha;
+  const float* bias;
+  int act;
+  const float* mask_src; int64_t ldm; int mask_mode;
+  int accumulate;
+  int split_k;              /* 0/1 = none */
+  int backend;
+  void* workspace; int64_t workspace_bytes;   /* backend 1 only: >= ase_gemm_tc_workspace_bytes() */
+} AseGemmParams;
+int ase_gemm(const AseGemmParams* p, void* stream);
+int64_t ase_gemm_tc_workspace_bytes(int M, int N, int K);
+
+/* ------------------------------------------------------------------------------------------------
+ * Learner: one PPO + adversarial minibatch update.  Replaces
+ *   ASEAgent.calc_gradients    learning/ase_agent.py:159-308   (kind ASE)
+ *   AMPAgent.calc_gradients    learning/amp_agent.py:266-390   (kind AMP)
+ *   CommonAgent.calc_gradients learning/common_agent.py:353-435 (kind PPO; HRL high-level policy)
+ * including the networks of learning/{amp,ase}_network_builder.py, the Gaussian head of rl_games
+ * ModelA2CContinuousLogStd, RunningMeanStd train-mode updates, every loss term and torch.optim.Adam
+ * (common_agent.py:45).
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum { ASE_KIND_PPO = 0, ASE_KIND_AMP = 1, ASE_KIND_ASE = 2 } AseKind;
+
+typedef struct {
+  int kind;
+  int obs_dim, act_dim, amp_dim, latent_dim;
+  int n_units;       int units[ASE_MAX_LAYERS];        /* actor / critic trunk (mlp.units) */
+  int n_disc_units;  int disc_units[ASE_MAX_LAYERS];   /* disc (= enc) trunk (disc.units) */
+  int n_style_units; int style_units[ASE_MAX_LAYERS];  /* [512,256] (ase_network_builder.py:160) */
+  int batch;          /* minibatch_size */
+  int amp_batch;      /* amp_minibatch_size */
+  /* hyper-parameters (data/cfg/train/rlg/ase_humanoid.yaml:59-114) */
+  float e_clip, critic_coef, entropy_coef, bounds_loss_coef;
+  float disc_coef, disc_logit_reg, disc_grad_penalty, disc_weight_decay;
+  float enc_coef, amp_diversity_bonus, amp_diversity_tar;
+  float lr, beta1, beta2, adam_eps;
+  float rms_eps;      /* 1e-5 */
+  int gemm_backend;   /* 0 SIMT, 1 tcgen05 3xTF32 */
+} AseLearnerConfig;
+
+/* Parameter arena: one flat fp32 buffer; tensor i (in the reference's model.parameters() order without
+ * the frozen `sigma`, i.e. Adam state order) lives at float offset ase_learner_param_offset(i). */
+typedef struct AseLearner AseLearner;
+
+int ase_learner_num_params(const AseLearnerConfig* cfg);                      /* tensor count */
+int ase_learner_param_desc(const AseLearnerConfig* cfg, int index, int64_t* offset, int* rows, int* cols);
+int64_t ase_learner_arena_floats(const AseLearnerConfig* cfg);
+int64_t ase_learner_workspace_bytes(const AseLearnerConfig* cfg);
+int ase_learner_create(const AseLearnerConfig* cfg, void* workspace, int64_t workspace_bytes, AseLearner** out);
+void ase_learner_destroy(AseLearner* l);
+
+typedef struct {
+  float* params; float* grads; float* exp_avg; float* exp_avg_sq;   /* arenas, ase_learner_arena_floats() each */
+  const float* logstd;            /* [act_dim] frozen `sigma` parameter (-2.9) */
+  double* obs_mean; double* obs_var; double* obs_count;             /* running_mean_std */
+  double* amp_mean; double* amp_var; double* amp_count;             /* _amp_input_mean_std (NULL for PPO) */
+} AseLearnerState;
+
+typedef struct {
+  /* minibatch, reference key names (ase_agent.py:162-186) */
+  const float* obs;               /* [B, obs_dim] */
+  const float* actions;           /* [B, act_dim] */
+  const float* old_logp_actions;  /* [B] */
+  const float* advantages;        /* [B] */
+  const float* old_mu;            /* [B, act_dim] */
+  const float* old_sigma;         /* [B, act_dim] */
+  const float* returns;           /* [B] */
+  const float* old_values;        /* [B] (unused: clip_value False) */
+  const float* rand_action_mask;  /* [B]  (NULL for PPO) */
+  const float* ase_latents;       /* [B, latent_dim] (ASE) */
+  const float* new_latents;       /* [B, latent_dim] the z' of _diversity_loss (ase_agent.py:451) */
+  const float* amp_obs;           /* [Ba, amp_dim] */
+  const float* amp_obs_replay;    /* [Ba, amp_dim] */
+  const float* amp_obs_demo;      /* [Ba, amp_dim] */
+  int update_rms;                 /* 1 = train mode (reference behaviour) */
+} AseMinibatch;
+
+/* train_result (ase_agent.py:296-306, amp_agent.py:470-478): written as floats into `scalars` */
+enum {
+  ASE_TR_ACTOR_LOSS = 0, ASE_TR_CRITIC_LOSS, ASE_TR_B_LOSS, ASE_TR_ENTROPY, ASE_TR_CLIP_FRAC, ASE_TR_KL,
+  ASE_TR_DISC_LOSS, ASE_TR_DISC_GRAD_PENALTY, ASE_TR_DISC_LOGIT_LOSS, ASE_TR_DISC_AGENT_ACC,
+  ASE_TR_DISC_DEMO_ACC, ASE_TR_DISC_AGENT_LOGIT_MEAN, ASE_TR_DISC_DEMO_LOGIT_MEAN,
+  ASE_TR_ENC_LOSS, ASE_TR_DIVERSITY_LOSS, ASE_TR_TOTAL_LOSS, ASE_TR_COUNT = 16
+};
+
+typedef struct {
+  float* scalars;            /* [ASE_TR_COUNT] */
+  float* disc_agent_logit;   /* optional [2*Ba] (agent then replay rows) */
+  float* disc_demo_logit;    /* optional [Ba] */
+  float* mu;                 /* optional [B, act_dim] current-policy means */
+  float* values;             /* optional [B] */
+} AseTrainResult;
+
+/* forward + losses + backward: fills state->grads (sum over local rows; no Adam) */
+int ase_learner_calc_gradients(AseLearner* l, const AseLearnerState* st, const AseMinibatch* mb,
+                               const AseTrainResult* out, void* stream);
+/* Adam on the whole arena: grads are multiplied by grad_scale first (1/world after an NCCL sum-allreduce,
+ * amp_agent.py:357-363 Horovod averaging); step is the 1-based Adam step count. */
+int ase_learner_adam_step(AseLearner* l, const AseLearnerState* st, int64_t step, float grad_scale, void* stream);
+
+/* Rollout-side inference with the same weights (eval mode, no RMS update):
+ *   get_action_values ase_agent.py:117-148 / amp_agent.py:139-169; _eval_critic ase_agent.py:385-393;
+ *   _eval_disc/_eval_enc ase_agent.py:395-411. Any output pointer may be NULL. rows <= infer_rows given
+ *   at create time via ase_learner_workspace_bytes (max(2*batch, 3*amp_batch)). */
+int ase_learner_eval_actor_critic(AseLearner* l, const AseLearnerState* st, const float* obs, const float* latents,
+                                  int rows, float* mu, float* value_normed, void* stream);
+int ase_learner_eval_disc_enc(AseLearner* l, const AseLearnerState* st, const float* amp_obs, int rows,
+                              float* disc_logits, float* enc_pred, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* ASE_B200_H_ */

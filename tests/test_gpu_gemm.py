@@ -1,0 +1,100 @@
+"""GPU parity tests for the GEMM backends through ase_gemm (C ABI).
+  backend 0 (SIMT fp32)    vs torch fp64 matmul: <= 1e-5 relative to max|C| (fp32 accumulation order only)
+  backend 1 (tcgen05 3xTF32) vs torch fp64 matmul: <= 2e-5 relative to max|C|  -- i.e. fp32-class accuracy,
+  two orders of magnitude tighter than single-pass TF32 (~2e-3) so a broken hi/lo split cannot hide."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(A, B, a_trans, b_trans, bias, act, mask_src, mask_mode, alpha):
+    a = A.double().t() if a_trans else A.double()
+    b = B.double() if b_trans else B.double().t()
+    c = alpha * (a @ b)
+    if bias is not None:
+        c = c + bias.double()
+    if act == 1:
+        c = torch.relu(c)
+    elif act == 2:
+        c = torch.tanh(c)
+    if mask_mode == 1:
+        c = c * (mask_src > 0).double()
+    elif mask_mode == 2:
+        c = c * (1 - mask_src.double() ** 2)
+    return c
+
+
+def _run(M, N, K, a_trans, b_trans, backend, bias=False, act=0, mask_mode=0, accumulate=False, split_k=0, alpha=1.0, seed=0,
+         lda_pad=0, tol=1e-5):
+    from ase_b200 import ops
+    g = torch.Generator().manual_seed(seed + M + 7 * N + 13 * K)
+    A = torch.randn((K, M + lda_pad) if a_trans else (M, K + lda_pad), generator=g).cuda()
+    B = torch.randn((K, N + lda_pad) if b_trans else (N, K + lda_pad), generator=g).cuda()
+    Av = A[:, :M] if a_trans else A[:, :K]
+    Bv = B[:, :N] if b_trans else B[:, :K]
+    bias_t = torch.randn(N, generator=g).cuda() if bias else None
+    mask_src = torch.randn(M, N, generator=g).cuda().clamp(-0.9, 0.9) if mask_mode else None
+    out = None
+    base = 0
+    if accumulate:
+        out = torch.randn(M, N, generator=g).cuda()
+        base = out.double().clone()
+    C = ops.gemm(Av, Bv, a_trans, b_trans, bias_t, act, mask_src, mask_mode, out, accumulate, split_k, alpha, backend)
+    torch.cuda.synchronize()
+    ref = _ref(Av, Bv, a_trans, b_trans, bias_t, act, mask_src, mask_mode, alpha) + base
+    err = float((C.double() - ref).abs().max() / ref.abs().max())
+    assert err < tol, (M, N, K, a_trans, b_trans, backend, err)
+
+
+@pytest.mark.parametrize('a_trans,b_trans', [(False, False), (False, True), (True, False), (True, True)])
+def test_simt_layouts_ragged(a_trans, b_trans):
+    _run(200, 150, 77, a_trans, b_trans, 0)
+    _run(128, 128, 8, a_trans, b_trans, 0)
+    _run(1, 1, 1, a_trans, b_trans, 0)
+    _run(259, 31, 317, a_trans, b_trans, 0, lda_pad=3)      # unaligned leading dimensions -> scalar loads
+
+
+def test_simt_epilogues():
+    _run(300, 200, 64, False, False, 0, bias=True, act=1)
+    _run(300, 64, 256, False, False, 0, bias=True, act=2, tol=2e-5)
+    _run(300, 200, 64, False, True, 0, mask_mode=1)
+    _run(300, 64, 100, False, True, 0, mask_mode=2)
+    _run(96, 200, 4096, True, True, 0, accumulate=True, split_k=7, tol=2e-5)
+    _run(300, 1, 512, False, False, 0, bias=True)           # value / logit heads (N = 1)
+    _run(4096, 512, 1, False, True, 0, mask_mode=1)         # K = 1 outer product (dV . w_value)
+    _run(64, 64, 64, False, False, 0, alpha=0.37)
+
+
+def test_simt_learner_shapes():
+    _run(512, 1024, 1400, False, False, 0, bias=True, act=1)
+    _run(512, 1400, 1024, False, True, 0)
+    _run(1024, 317, 2048, True, True, 0, accumulate=True, split_k=4, tol=2e-5)
+
+
+@pytest.mark.parametrize('a_trans,b_trans', [(False, False), (False, True), (True, True)])
+def test_tc_matches_fp64(a_trans, b_trans):
+    _run(256, 256, 64, a_trans, b_trans, 1, tol=2e-5)
+    _run(384, 192, 317, a_trans, b_trans, 1, lda_pad=3, tol=2e-5)     # ragged K (zero padded to 320), N tail with BN=128
+    _run(1000, 100, 96, a_trans, b_trans, 1, tol=2e-5)                # BN = 64 path, ragged M and N
+
+
+def test_tc_epilogues_and_split_k():
+    _run(512, 256, 512, False, False, 1, bias=True, act=1, tol=2e-5)
+    _run(256, 128, 256, False, False, 1, bias=True, act=2, tol=3e-5)
+    _run(512, 320, 256, False, True, 1, mask_mode=1, tol=2e-5)
+    _run(256, 64, 128, False, True, 1, mask_mode=2, tol=2e-5)
+    _run(1024, 512, 4096, True, True, 1, accumulate=True, split_k=5, tol=3e-5)
+    _run(256, 256, 2048, False, False, 1, alpha=0.25, tol=2e-5)      # > STAGES k-blocks: ring wrap-around + phase flips
+
+
+def test_tc_accuracy_is_fp32_class_not_tf32():
+    """Inputs chosen so that single-pass TF32 would miss by ~1e-3: all products need the low halves."""
+    from ase_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    A = (1.0 + torch.rand(256, 1024, generator=g) * 1e-3).cuda()      # values whose information sits below TF32's 10 mantissa bits
+    B = (1.0 + torch.rand(128, 1024, generator=g) * 1e-3).cuda()
+    C = ops.gemm(A, B, backend=1)
+    ref = A.double() @ B.double().t()
+    spread = (ref - ref.mean()).abs().max()
+    assert float((C.double() - ref).abs().max()) < 0.02 * float(spread)
