@@ -1,0 +1,609 @@
+"""Host-side mirror of the reference's rl_games agents for the training hot path:
+
+    CommonAgent  learning/common_agent.py:25-564   (plain PPO; HRL high-level policy learner)
+    AMPAgent     learning/amp_agent.py:21-628
+    ASEAgent     learning/ase_agent.py:12-538
+
+Same public surface (`play_steps`, `prepare_dataset`, `train_actor_critic` / `calc_gradients`, `train_epoch`,
+`train`, `get_full_state_weights` / `set_full_state_weights`, `train_result` keys) and the same config keys
+(data/cfg/train/rlg/*.yaml), so `run.py`'s `algo_factory.register_builder('ase', lambda **kw: ASEAgent(**kw))`
+works unchanged.  All arithmetic runs in libase_b200.so through `Learner` / `ops`; torch is
+used for device buffers, indexing (gathers, ring buffers), RNG draws and torch.distributed.
+
+Differences from the reference that do not change results:
+  * no per-minibatch `.item()`: train_result scalars stay on the device (lr_schedule is `constant`);
+  * demo / replay AMP observations are gathered per minibatch (amp_minibatch_size rows) through composed
+    indices instead of materialising two [batch, 1400] copies per epoch (same rows, same order);
+  * the diversity loss' second actor pass is batched with the first (2B rows)."""
+import math
+import time
+
+import numpy as np
+import torch
+
+from . import ops
+from .learner import Learner
+from .replay_buffer import ReplayBuffer
+
+
+def swap_and_flatten01(x):
+    """rl_games a2c_common.swap_and_flatten01: env-major flatten, row = env * H + t."""
+    s = x.shape
+    return x.transpose(0, 1).reshape(s[0] * s[1], *s[2:])
+
+
+class AMPDataset:
+    """learning/amp_datasets.py:4-31: one global permutation, contiguous slices, reshuffle when exhausted."""
+
+    def __init__(self, batch_size, minibatch_size, device):
+        self.batch_size, self.minibatch_size, self.device = batch_size, minibatch_size, device
+        self.length = batch_size // minibatch_size
+        self._idx_buf = torch.randperm(batch_size, device=device)
+        self.values_dict = {}
+
+    def __len__(self):
+        return self.length
+
+    def update_values_dict(self, d):
+        self.values_dict = d
+
+    def sample_indices(self, idx):
+        start, end = idx * self.minibatch_size, (idx + 1) * self.minibatch_size
+        sample_idx = self._idx_buf[start:end].clone()
+        if end >= self.batch_size:
+            self._idx_buf[:] = torch.randperm(self.batch_size, device=self.device)
+        return sample_idx
+
+
+class CommonAgent:
+    kind = 'ppo'
+
+    def __init__(self, base_name, config):
+        self.config = config
+        self.name = base_name
+        self.ppo_device = torch.device(config.get('device', 'cuda:0'))
+        self.vec_env = config.get('vec_env')
+        if self.vec_env is None:     # drop-in path: rl_games creates the env exactly as A2CBase does
+            from rl_games.common import vecenv
+            self.vec_env = vecenv.create_vec_env(config['env_name'], config['num_actors'], **config.get('env_config', {}))
+        self.env_info = config.get('env_info') or self.vec_env.get_env_info()
+        self.num_actors = config['num_actors']
+        self.num_agents = self.env_info.get('agents', 1)
+        self.value_size = self.env_info.get('value_size', 1)
+        assert self.value_size == 1 and self.num_agents == 1
+        self.obs_shape = self.env_info['observation_space'].shape
+        self.actions_num = self.env_info['action_space'].shape[0]
+        self.horizon_length = config['horizon_length']
+        self.batch_size = self.horizon_length * self.num_actors
+        self.batch_size_envs = self.batch_size
+        self.minibatch_size = config['minibatch_size']
+        self.mini_epochs_num = config['mini_epochs']
+        assert self.batch_size % self.minibatch_size == 0
+        self.normalize_input = config['normalize_input']
+        self.normalize_value = config.get('normalize_value', False)
+        self.normalize_advantage = config['normalize_advantage']
+        assert self.normalize_input and self.normalize_value, "the engine implements the shipped configs (normalize_* True)"
+        self.gamma, self.tau = config['gamma'], config['tau']
+        self.e_clip = config['e_clip']
+        assert not config.get('clip_value', False) and not config.get('truncate_grads', False), "clip_value/truncate_grads are False in every shipped config"
+        self.last_lr = float(config['learning_rate'])
+        assert config.get('lr_schedule', 'constant') in ('constant', None)
+        self.max_epochs = config.get('max_epochs', 1e6)
+        self.save_freq = config.get('save_frequency', 0)
+        self.print_stats = config.get('print_stats', True)
+        self.clip_actions = config.get('clip_actions', True)
+        self.multi_gpu = config.get('multi_gpu', False)
+        self.rank, self.rank_size = 0, 1
+        if self.multi_gpu:
+            import torch.distributed as dist
+            self.rank, self.rank_size = dist.get_rank(), dist.get_world_size()
+        self._load_config_params(config)
+        self.model = self._build_learner(config)
+        self.dataset = AMPDataset(self.batch_size, self.minibatch_size, self.ppo_device)
+        self.epoch_num = 0
+        self.frame = 0
+        self.train_result = None
+        self.rnn_states = None
+        self.is_rnn = False
+        self.has_central_value = False
+        self._eval_mode = False
+        self._timing = {}
+
+    # ------------------------------------------------------------------ construction helpers
+    def _load_config_params(self, config):
+        pass
+
+    def _net_params(self, config):
+        """YAML `network` section: from rl_games' model builder when dropped into run.py, else config['net_params']."""
+        net = config.get('network')
+        if net is not None and hasattr(net, 'network_builder'):
+            return net.network_builder.params
+        return config['net_params']
+
+    def _learner_kwargs(self, config):
+        np_ = self._net_params(config)
+        hp = {k: config[k] for k in ('e_clip', 'critic_coef', 'entropy_coef', 'bounds_loss_coef', 'learning_rate') if k in config}
+        sigma = np_['space']['continuous']['sigma_init'].get('val', 0.0)
+        return dict(obs_dim=self.obs_shape[0], act_dim=self.actions_num, batch=self.minibatch_size, units=tuple(np_['mlp']['units']),
+                    hparams=hp, device=self.ppo_device, gemm_backend=config.get('gemm_backend', 1), sigma_init=sigma)
+
+    def _build_learner(self, config):
+        kw = self._learner_kwargs(config)
+        ln = Learner(self.kind, **kw)
+        ln.init_reference(seed=config.get('seed', 0) or 0)
+        return ln
+
+    # ------------------------------------------------------------------ rl_games-style state
+    def set_eval(self):
+        self._eval_mode = True
+        for r in self._rms_modules():
+            r.eval()
+
+    def set_train(self):
+        self._eval_mode = False
+        for r in self._rms_modules():
+            r.train()
+
+    def _rms_modules(self):
+        m = [self.model.running_mean_std, self.model.value_mean_std]
+        if self.model.amp_input_mean_std is not None:
+            m.append(self.model.amp_input_mean_std)
+        return m
+
+    @property
+    def running_mean_std(self): return self.model.running_mean_std
+    @property
+    def value_mean_std(self): return self.model.value_mean_std
+
+    def get_stats_weights(self):
+        return self.model.get_stats_weights()
+
+    def get_full_state_weights(self):
+        """rl_games A2CBase.get_full_state_weights: the on-disk contract."""
+        st = self.get_stats_weights()
+        st['model'] = self.model.state_dict()
+        st['epoch'] = self.epoch_num
+        st['optimizer'] = self._optimizer_state_dict()
+        st['frame'] = self.frame
+        st['last_mean_rewards'] = -100500
+        return st
+
+    def set_full_state_weights(self, w):
+        self.model.load_state_dict(w['model'])
+        self.model.set_stats_weights(w)
+        self.epoch_num = w.get('epoch', 0)
+        self.frame = w.get('frame', 0)
+        if 'optimizer' in w:
+            self._load_optimizer_state_dict(w['optimizer'])
+
+    def _optimizer_state_dict(self):
+        """torch.optim.Adam.state_dict() layout: param index 0 is the frozen sigma (no state), 1.. follow parameters()."""
+        state = {}
+        names = list(self.model.named_parameters().keys())
+        for i, k in enumerate(names):
+            v = self.model.named_parameters()[k]
+            off = v.storage_offset()
+            sl = slice(off, off + v.numel())
+            state[i + 1] = {'step': self.model.step, 'exp_avg': self.model.exp_avg[sl].view(v.shape).clone(),
+                            'exp_avg_sq': self.model.exp_avg_sq[sl].view(v.shape).clone()}
+        hp = self.model.hp
+        return {'state': state, 'param_groups': [{'lr': self.last_lr, 'betas': (hp['beta1'], hp['beta2']), 'eps': hp['adam_eps'],
+                                                  'weight_decay': 0.0, 'amsgrad': False, 'params': list(range(len(names) + 1))}]}
+
+    def _load_optimizer_state_dict(self, sd):
+        names = list(self.model.named_parameters().keys())
+        step = 0
+        for i, k in enumerate(names):
+            s = sd['state'].get(i + 1)
+            if s is None:
+                continue
+            v = self.model.named_parameters()[k]
+            off = v.storage_offset()
+            self.model.exp_avg[off:off + v.numel()].copy_(s['exp_avg'].reshape(-1))
+            self.model.exp_avg_sq[off:off + v.numel()].copy_(s['exp_avg_sq'].reshape(-1))
+            step = int(s['step'])
+        self.model.step = step
+
+    # ------------------------------------------------------------------ buffers
+    def init_tensors(self):
+        H, N, dev = self.horizon_length, self.num_actors, self.ppo_device
+        f = lambda *s: torch.zeros((H, N) + s, device=dev, dtype=torch.float32)
+        obs = self.obs_shape[0]
+        self.experience_buffer = {
+            'obses': f(obs), 'next_obses': f(obs), 'rewards': f(1), 'values': f(1), 'next_values': f(1), 'neglogpacs': f(),
+            'dones': torch.zeros(H, N, device=dev, dtype=torch.uint8), 'actions': f(self.actions_num), 'mus': f(self.actions_num),
+            'sigmas': f(self.actions_num)}
+        self.update_list = ['actions', 'neglogpacs', 'values', 'mus', 'sigmas']
+        self.tensor_list = self.update_list + ['obses', 'dones', 'next_obses']
+        self.current_rewards = torch.zeros(N, 1, device=dev)
+        self.current_lengths = torch.zeros(N, device=dev)
+        self.dones = torch.ones(N, dtype=torch.uint8, device=dev)
+
+    def env_reset(self, env_ids=None):
+        obs = self.vec_env.reset(env_ids)
+        return {'obs': obs}
+
+    def env_step(self, actions):
+        if self.clip_actions:
+            actions = torch.clamp(actions, -1.0, 1.0)     # rescale_actions is the identity for +-1 bounds (vec_task.py:22)
+        obs, rewards, dones, infos = self.vec_env.step(actions)
+        return {'obs': obs}, rewards.unsqueeze(1), dones, infos
+
+    # ------------------------------------------------------------------ rollout (learning/common_agent.py:244-307)
+    def _latents(self):
+        return None
+
+    def _pre_action(self):
+        pass
+
+    def _rand_action_probs_tensor(self):
+        return None
+
+    def get_action_values(self, obs_dict, latents=None, rand_action_probs=None):
+        """ase_agent.py:117-148 / amp_agent.py:139-169 (eval mode): actor+critic forward, sample, eps-greedy mask."""
+        mu, v = self.model.eval_actor_critic(obs_dict['obs'], latents)
+        noise = torch.randn(mu.shape, device=mu.device, dtype=torch.float32)
+        mask = None if rand_action_probs is None else torch.bernoulli(rand_action_probs)
+        actions, nlp, sig = ops.policy_sample(mu, self.model.sigma, noise, mask)
+        values = self.model.value_mean_std(v, unnorm=True)
+        res = {'actions': actions, 'neglogpacs': nlp, 'values': values, 'mus': mu, 'sigmas': sig}
+        if mask is not None:
+            res['rand_action_mask'] = mask
+        return res
+
+    def _eval_critic(self, obs_dict, latents=None):
+        _, v = self.model.eval_actor_critic(obs_dict['obs'], latents, want_value=True, want_actor=False)
+        return self.model.value_mean_std(v, unnorm=True)
+
+    def _extra_buffer_writes(self, n, res_dict, infos):
+        pass
+
+    def play_steps(self):
+        self.set_eval()
+        eb = self.experience_buffer
+        done_indices = None
+        for n in range(self.horizon_length):
+            self.obs = self.env_reset(done_indices)
+            eb['obses'][n] = self.obs['obs']
+            self._pre_action()
+            res = self.get_action_values(self.obs, self._latents(), self._rand_action_probs_tensor())
+            for k in self.update_list:
+                eb[k][n] = res[k] if k != 'values' else res[k]
+            self.obs, rewards, self.dones, infos = self.env_step(res['actions'])
+            eb['rewards'][n] = rewards
+            eb['next_obses'][n] = self.obs['obs']
+            eb['dones'][n] = self.dones
+            self._extra_buffer_writes(n, res, infos)
+            terminated = infos['terminate'].float().unsqueeze(-1)
+            next_vals = self._eval_critic(self.obs, self._latents())
+            next_vals = next_vals * (1.0 - terminated)
+            eb['next_values'][n] = next_vals
+            self.current_rewards += rewards
+            self.current_lengths += 1
+            done_indices = self.dones.nonzero(as_tuple=False)[:, 0]      # (host sync, as in the reference: ase_agent.py:78-79)
+            not_dones = 1.0 - self.dones.float()
+            self.current_rewards = self.current_rewards * not_dones.unsqueeze(1)
+            self.current_lengths = self.current_lengths * not_dones
+        mb_rewards, extra = self._final_rewards()
+        mb_advs = ops.discount_values(eb['dones'], eb['values'], mb_rewards, eb['next_values'], self.gamma, self.tau)
+        mb_returns = mb_advs + eb['values']
+        batch_dict = {k: swap_and_flatten01(eb[k]) for k in self.tensor_list}
+        batch_dict['returns'] = swap_and_flatten01(mb_returns)
+        batch_dict['played_frames'] = self.batch_size
+        for k, v in extra.items():
+            batch_dict[k] = swap_and_flatten01(v)
+        return batch_dict
+
+    def _final_rewards(self):
+        return self.experience_buffer['rewards'], {}
+
+    def discount_values(self, mb_fdones, mb_values, mb_rewards, mb_next_values):
+        return ops.discount_values(mb_fdones.to(torch.uint8), mb_values, mb_rewards, mb_next_values, self.gamma, self.tau)
+
+    # ------------------------------------------------------------------ dataset (common_agent.py:309-351)
+    def _calc_advs(self, batch_dict):
+        return ops.calc_advs(batch_dict['returns'], batch_dict['values'], None)
+
+    def prepare_dataset(self, batch_dict):
+        advantages = self._calc_advs(batch_dict)
+        values = self.model.value_mean_std(batch_dict['values'])        # train mode: two sequential updates
+        returns = self.model.value_mean_std(batch_dict['returns'])
+        d = {'old_values': values, 'old_logp_actions': batch_dict['neglogpacs'], 'advantages': advantages, 'returns': returns,
+             'actions': batch_dict['actions'], 'obs': batch_dict['obses'], 'mu': batch_dict['mus'], 'sigma': batch_dict['sigmas']}
+        self.dataset.update_values_dict(d)
+
+    def _minibatch(self, i):
+        idx = self.dataset.sample_indices(i)
+        return {k: v[idx] for k, v in self.dataset.values_dict.items() if v is not None}, idx
+
+    # ------------------------------------------------------------------ update (common_agent.py:353-435)
+    def _new_latents(self, n):
+        return None
+
+    def calc_gradients(self, input_dict):
+        self.set_train()
+        out = self.model.calc_gradients(input_dict, self._new_latents(input_dict['obs'].shape[0]), update_rms=True)
+        scale = 1.0
+        if self.multi_gpu:
+            import torch.distributed as dist
+            dist.all_reduce(self.model.grads)               # one flat NCCL sum per minibatch (Horovod averaged: amp_agent.py:357-363)
+            scale = 1.0 / self.rank_size
+        self.model.adam_step(grad_scale=scale)
+        row = self._tr_buf[self._tr_i % self._tr_buf.shape[0]]
+        row.copy_(out['scalars'])
+        self._tr_i += 1
+        from .lib import TR_NAMES
+        tr = {name: row[j] for j, name in enumerate(TR_NAMES)}
+        tr['last_lr'] = self.last_lr
+        tr['lr_mul'] = 1.0
+        if 'disc_agent_logit' in out:
+            tr['disc_agent_logit'] = out['disc_agent_logit']
+            tr['disc_demo_logit'] = out['disc_demo_logit']
+        self.train_result = tr
+
+    def train_actor_critic(self, input_dict):
+        self.calc_gradients(input_dict)
+        return self.train_result
+
+    def _pre_update(self, batch_dict):
+        pass
+
+    def _post_update(self, batch_dict):
+        pass
+
+    def train_epoch(self):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        ev[0].record()
+        with torch.no_grad():
+            batch_dict = self.play_steps()
+        ev[1].record()
+        self._pre_update(batch_dict)
+        self.set_train()
+        self.curr_frames = batch_dict.pop('played_frames')
+        self.prepare_dataset(batch_dict)
+        nmb = self.mini_epochs_num * len(self.dataset)
+        if getattr(self, '_tr_buf', None) is None or self._tr_buf.shape[0] != nmb:
+            from .lib import TR_COUNT
+            self._tr_buf = torch.zeros(nmb, TR_COUNT, device=self.ppo_device)
+        self._tr_i = 0
+        for _ in range(self.mini_epochs_num):
+            for i in range(len(self.dataset)):
+                mb, idx = self._minibatch(i)
+                self.train_actor_critic(mb)
+        self._post_update(batch_dict)
+        ev[2].record()
+        self._events = ev
+        from .lib import TR_NAMES
+        info = {name: self._tr_buf[:, j] for j, name in enumerate(TR_NAMES)}     # per-minibatch series, on device
+        return info
+
+    def epoch_times(self):
+        """(play_time, update_time, total_time) in seconds from CUDA events (syncs)."""
+        ev = self._events
+        ev[2].synchronize()
+        p, u = ev[0].elapsed_time(ev[1]) / 1e3, ev[1].elapsed_time(ev[2]) / 1e3
+        return p, u, p + u
+
+    def update_epoch(self):
+        self.epoch_num += 1
+        return self.epoch_num
+
+    def _init_train(self):
+        pass
+
+    def _sync_stats(self):
+        """Horovod sync_stats [recollection of rl_games]: RunningMeanStd buffers are averaged across ranks once per epoch."""
+        import torch.distributed as dist
+        for r in self._rms_modules():
+            for t in (r.running_mean, r.running_var, r.count):
+                dist.all_reduce(t)
+                t /= self.rank_size
+
+    def train(self):
+        """common_agent.py:82-155 (logging / checkpoint cadence kept; TensorBoard scalars are the caller's business)."""
+        self.init_tensors()
+        self.obs = self.env_reset()
+        if self.multi_gpu:
+            import torch.distributed as dist
+            dist.broadcast(self.model.params, 0)
+        self._init_train()
+        total_time = 0.0
+        while True:
+            epoch_num = self.update_epoch()
+            self.train_epoch()
+            play_time, update_time, sum_time = self.epoch_times()
+            total_time += sum_time
+            if self.multi_gpu:
+                self._sync_stats()
+            self.frame += self.curr_frames * self.rank_size
+            if self.rank == 0 and self.print_stats:
+                print(f'fps step: {self.curr_frames / play_time:.1f} fps total: {self.curr_frames / sum_time:.1f}')
+            if epoch_num >= self.max_epochs:
+                return -100500, epoch_num
+
+
+class AMPAgent(CommonAgent):
+    kind = 'amp'
+
+    def _load_config_params(self, config):
+        self._enable_eps_greedy = bool(config['enable_eps_greedy'])
+        self._task_reward_w = config['task_reward_w']
+        self._disc_reward_w = config['disc_reward_w']
+        self._amp_observation_space = self.env_info['amp_observation_space']
+        self._amp_batch_size = int(config['amp_batch_size'])
+        self._amp_minibatch_size = int(config['amp_minibatch_size'])
+        assert self._amp_minibatch_size <= self.minibatch_size
+        self._disc_reward_scale = config['disc_reward_scale']
+        assert config.get('normalize_amp_input', True)
+
+    def _learner_kwargs(self, config):
+        kw = super()._learner_kwargs(config)
+        np_ = self._net_params(config)
+        for k in ('disc_coef', 'disc_logit_reg', 'disc_grad_penalty', 'disc_weight_decay'):
+            kw['hparams'][k] = config[k]
+        kw.update(amp_dim=self._amp_observation_space.shape[0], amp_batch=self._amp_minibatch_size, disc_units=tuple(np_['disc']['units']))
+        return kw
+
+    def init_tensors(self):
+        super().init_tensors()
+        H, N, dev = self.horizon_length, self.num_actors, self.ppo_device
+        eb = self.experience_buffer
+        eb['amp_obs'] = torch.zeros(H, N, self._amp_observation_space.shape[0], device=dev)
+        eb['rand_action_mask'] = torch.zeros(H, N, device=dev)
+        self._amp_obs_demo_buffer = ReplayBuffer(int(self.config['amp_obs_demo_buffer_size']), dev)
+        self._amp_replay_keep_prob = self.config['amp_replay_keep_prob']
+        self._amp_replay_buffer = ReplayBuffer(int(self.config['amp_replay_buffer_size']), dev)
+        self._build_rand_action_probs()
+        self.tensor_list += ['amp_obs', 'rand_action_mask']
+
+    def _build_rand_action_probs(self):
+        """amp_agent.py:424-435: p_env = 1 - exp(10 (i/(N-1) - 1)), p_0 = 1, p_{N-1} = 0."""
+        n = self.vec_env.env.task.num_envs
+        ids = torch.arange(n, dtype=torch.float32, device=self.ppo_device)
+        p = 1.0 - torch.exp(10 * (ids / (n - 1.0) - 1.0))
+        p[0] = 1.0; p[-1] = 0.0
+        if not self._enable_eps_greedy:
+            p[:] = 1.0
+        self._rand_action_probs = p
+
+    def _rand_action_probs_tensor(self):
+        return self._rand_action_probs
+
+    def _extra_buffer_writes(self, n, res, infos):
+        self.experience_buffer['amp_obs'][n] = infos['amp_obs']
+        self.experience_buffer['rand_action_mask'][n] = res['rand_action_mask']
+
+    def _calc_amp_rewards(self, amp_obs, latents=None):
+        """amp_agent.py:563-577 / ase_agent.py:395-411: disc (+enc) trunk over the whole rollout, then the reward kernels."""
+        H, N = amp_obs.shape[0], amp_obs.shape[1]
+        logits, enc = self.model.eval_disc_enc(amp_obs.reshape(H * N, -1), want_enc=self.kind == 'ase')
+        z = None if latents is None else latents.reshape(H * N, -1)
+        dr, er, comb = ops.amp_rewards(logits, enc, z, self._disc_reward_scale, getattr(self, '_enc_reward_scale', 1.0),
+                                       self.experience_buffer['rewards'].reshape(H * N), self._task_reward_w, self._disc_reward_w,
+                                       getattr(self, '_enc_reward_w', 0.0))
+        out = {'disc_rewards': dr.reshape(H, N, 1)}
+        if er is not None:
+            out['enc_rewards'] = er.reshape(H, N, 1)
+        return comb.reshape(H, N, 1), out
+
+    def _final_rewards(self):
+        return self._calc_amp_rewards(self.experience_buffer['amp_obs'], None)
+
+    def _calc_advs(self, batch_dict):
+        return ops.calc_advs(batch_dict['returns'], batch_dict['values'], batch_dict['rand_action_mask'])
+
+    def _init_train(self):
+        """amp_agent.py:436-440,520-528: fill the demo buffer."""
+        size = self._amp_obs_demo_buffer.get_buffer_size()
+        for _ in range(int(math.ceil(size / self._amp_batch_size))):
+            self._amp_obs_demo_buffer.store({'amp_obs': self.vec_env.env.fetch_amp_obs_demo(self._amp_batch_size)})
+
+    def _pre_update(self, batch_dict):
+        """amp_agent.py:194-202: refresh demos, draw the epoch's demo / replay sample (as indices)."""
+        self._amp_obs_demo_buffer.store({'amp_obs': self.vec_env.env.fetch_amp_obs_demo(self._amp_batch_size)})
+        n = batch_dict['amp_obs'].shape[0]
+        self._demo_idx = self._amp_obs_demo_buffer.sample_indices(n).to(self.ppo_device)
+        self._replay_idx = None if self._amp_replay_buffer.get_total_count() == 0 else self._amp_replay_buffer.sample_indices(n).to(self.ppo_device)
+
+    def prepare_dataset(self, batch_dict):
+        super().prepare_dataset(batch_dict)
+        vd = self.dataset.values_dict
+        vd['rand_action_mask'] = batch_dict['rand_action_mask']
+        self._amp_obs_flat = batch_dict['amp_obs']
+
+    def _minibatch(self, i):
+        mb, idx = super()._minibatch(i)
+        a = idx[:self._amp_minibatch_size]          # only amp_minibatch_size rows are consumed (ase_agent.py:172-181)
+        mb['amp_obs'] = self._amp_obs_flat[a]
+        mb['amp_obs_demo'] = self._amp_obs_demo_buffer.rows('amp_obs', self._demo_idx[a])
+        mb['amp_obs_replay'] = mb['amp_obs'] if self._replay_idx is None else self._amp_replay_buffer.rows('amp_obs', self._replay_idx[a])
+        return mb, idx
+
+    def _post_update(self, batch_dict):
+        """amp_agent.py:579-593 _store_replay_amp_obs."""
+        amp_obs = batch_dict['amp_obs']
+        size = self._amp_replay_buffer.get_buffer_size()
+        if self._amp_replay_buffer.get_total_count() > size:
+            keep = torch.bernoulli(torch.full((amp_obs.shape[0],), self._amp_replay_keep_prob, device=self.ppo_device)) == 1.0
+            amp_obs = amp_obs[keep]
+        if amp_obs.shape[0] > size:
+            amp_obs = amp_obs[torch.randperm(amp_obs.shape[0], device=self.ppo_device)[:size]]
+        if amp_obs.shape[0] > 0:
+            self._amp_replay_buffer.store({'amp_obs': amp_obs})
+
+
+class ASEAgent(AMPAgent):
+    kind = 'ase'
+
+    def _load_config_params(self, config):
+        super()._load_config_params(config)
+        self._latent_dim = config['latent_dim']
+        self._latent_steps_min = config.get('latent_steps_min', np.inf)
+        self._latent_steps_max = config.get('latent_steps_max', np.inf)
+        self._enc_reward_scale = config['enc_reward_scale']
+        self._enc_reward_w = config['enc_reward_w']
+        assert config.get('enc_weight_decay', 0) == 0 and config.get('enc_grad_penalty', 0) == 0, "0 in the shipped config (ase_humanoid.yaml:108-110)"
+
+    def _learner_kwargs(self, config):
+        kw = super()._learner_kwargs(config)
+        for k in ('enc_coef', 'amp_diversity_bonus', 'amp_diversity_tar'):
+            kw['hparams'][k] = config[k]
+        kw.update(latent_dim=self._latent_dim)
+        return kw
+
+    def init_tensors(self):
+        super().init_tensors()
+        H, N, dev = self.horizon_length, self.num_actors, self.ppo_device
+        self.experience_buffer['ase_latents'] = torch.zeros(H, N, self._latent_dim, device=dev)
+        self._ase_latents = torch.zeros(N, self._latent_dim, device=dev)
+        self.tensor_list += ['ase_latents']
+        self._latent_reset_steps = torch.zeros(N, dtype=torch.int32, device=dev)
+        self._reset_latent_step_count(torch.arange(N, device=dev))
+
+    def _sample_latents(self, n):
+        """ase_network_builder.py:221-225."""
+        z = torch.randn(n, self._latent_dim, device=self.ppo_device)
+        return torch.nn.functional.normalize(z, dim=-1)
+
+    def _new_latents(self, n):
+        return self._sample_latents(n)
+
+    def _reset_latents(self, env_ids):
+        self._ase_latents[env_ids] = self._sample_latents(len(env_ids))
+
+    def _reset_latent_step_count(self, env_ids):
+        self._latent_reset_steps[env_ids] = torch.randint(self._latent_steps_min, self._latent_steps_max, (len(env_ids),),
+                                                          dtype=torch.int32, device=self.ppo_device)
+
+    def env_reset(self, env_ids=None):
+        obs = super().env_reset(env_ids)
+        if env_ids is None:
+            env_ids = torch.arange(self.num_actors, device=self.ppo_device)
+        if len(env_ids) > 0:
+            self._reset_latents(env_ids)
+            self._reset_latent_step_count(env_ids)
+        return obs
+
+    def _latents(self):
+        return self._ase_latents
+
+    def _pre_action(self):
+        """ase_agent.py:366-381 _update_latents."""
+        new = self._latent_reset_steps <= self.vec_env.env.task.progress_buf
+        ids = new.nonzero(as_tuple=False).flatten()
+        if ids.numel() > 0:
+            self._reset_latents(ids)
+            self._latent_reset_steps[ids] += torch.randint(self._latent_steps_min, self._latent_steps_max, (ids.numel(),),
+                                                           dtype=torch.int32, device=self.ppo_device)
+
+    def _extra_buffer_writes(self, n, res, infos):
+        super()._extra_buffer_writes(n, res, infos)
+        self.experience_buffer['ase_latents'][n] = self._ase_latents
+
+    def _final_rewards(self):
+        eb = self.experience_buffer
+        return self._calc_amp_rewards(eb['amp_obs'], eb['ase_latents'])
+
+    def prepare_dataset(self, batch_dict):
+        super().prepare_dataset(batch_dict)
+        self.dataset.values_dict['ase_latents'] = batch_dict['ase_latents']

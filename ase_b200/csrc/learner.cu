@@ -247,12 +247,12 @@ relu_mask_inplace_kernel(float* __restrict__ g, const float* __restrict__ h, int
 
 static int forward_actor_critic(const G& g, int rows_a, int rows_c) {
   AseLearner& L = g.L; const Net& n = L.net; const AseLearnerConfig& c = L.cfg;
-  if (L.ase) {   // style branch: tanh(dense(relu-mlp(z))) written next to the normalised obs (ase_network_builder.py:305-324)
+  if (L.ase && rows_a > 0) {   // style branch: tanh(dense(relu-mlp(z))) written next to the normalised obs (ase_network_builder.py:305-324)
     const float* x = L.Zc; int64_t ld = c.latent_dim;
     for (int k = 0; k < n.n_style; ++k) { RC(g.fwd(x, ld, rows_a, n.style[k], L.S[k], n.style[k].out, 1)); x = L.S[k]; ld = n.style[k].out; }
     RC(g.fwd(x, ld, rows_a, n.style_dense, L.Xa + c.obs_dim, L.ldx, 2));
   }
-  {
+  if (rows_a > 0) {
     const float* x = L.Xa; int64_t ld = L.ldx;
     for (int k = 0; k < n.n_actor; ++k) { RC(g.fwd(x, ld, rows_a, n.actor[k], L.H[k], n.actor[k].out, 1)); x = L.H[k]; ld = n.actor[k].out; }
     RC(g.fwd(x, ld, rows_a, n.mu, L.MU, c.act_dim, 0));
@@ -501,7 +501,7 @@ extern "C" int ase_learner_eval_actor_critic(AseLearner* lp, const AseLearnerSta
     RC(copy_cols(latents, c.latent_dim, rows, c.latent_dim, L.Xc + c.obs_dim, L.ldx, st));
     RC(copy_cols(latents, c.latent_dim, rows, c.latent_dim, L.Zc, c.latent_dim, st));
   }
-  RC(forward_actor_critic(g, rows, value_normed ? rows : 0));
+  RC(forward_actor_critic(g, mu ? rows : 0, value_normed ? rows : 0));
   if (mu) ASE_CUDA_OK(cudaMemcpyAsync(mu, L.MU, (size_t)rows * c.act_dim * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (value_normed) ASE_CUDA_OK(cudaMemcpyAsync(value_normed, L.V, (size_t)rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
   return ASE_OK;

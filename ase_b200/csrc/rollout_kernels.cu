@@ -49,6 +49,27 @@ amp_rewards_kernel(const float* __restrict__ logits, const float* __restrict__ e
   }
 }
 
+// Gaussian sampling head (eval mode) + eps-greedy override; one warp per row.
+__global__ void __launch_bounds__(256)
+policy_sample_kernel(const float* __restrict__ mu, const float* __restrict__ logstd, const float* __restrict__ noise,
+                     const float* __restrict__ rand_mask, int rows, int A, float* __restrict__ actions,
+                     float* __restrict__ neglogp, float* __restrict__ sigma_out) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const bool det = rand_mask && rand_mask[row] == 0.0f;
+  float s = 0.0f, sumlog = 0.0f;
+  for (int j = lane; j < A; j += 32) {
+    const float ls = logstd[j], sg = expf(ls), m = mu[(int64_t)row * A + j];
+    const float a = m + sg * noise[(int64_t)row * A + j];
+    const float t = (a - m) / sg;
+    s += t * t; sumlog += ls;
+    actions[(int64_t)row * A + j] = det ? m : a;
+    if (sigma_out) sigma_out[(int64_t)row * A + j] = sg;
+  }
+  s = warp_sum(s); sumlog = warp_sum(sumlog);
+  if (lane == 0 && neglogp) neglogp[row] = 0.5f * s + (float)(0.5 * 1.8378770664093453 * (double)A) + sumlog;
+}
+
 // stats[0..2] = sum(m), sum(v*m), sum((v*m)^2) ; unmasked: m = 1
 __global__ void __launch_bounds__(256)
 adv_stats_kernel(const float* __restrict__ ret, const float* __restrict__ val, const float* __restrict__ mask, int rows,
@@ -116,6 +137,16 @@ extern "C" int ase_adv_normalize(const float* returns, const float* values, cons
   adv_stats_kernel<<<blocks, 256, 0, st>>>(returns, values, mask, rows, (double*)scratch);
   ASE_LAUNCH_OK();
   adv_apply_kernel<<<blocks, 256, 0, st>>>(returns, values, rows, (const double*)scratch, advs);
+  ASE_LAUNCH_OK();
+  return ASE_OK;
+}
+
+extern "C" int ase_policy_sample(const float* mu, const float* logstd, const float* noise, const float* rand_mask, int rows,
+                                 int act_dim, float* actions, float* neglogp, float* sigma_out, void* stream) {
+  ASE_CHECK_ARG(mu && logstd && noise && actions, "ase_policy_sample: null pointer");
+  if (rows <= 0) return ASE_OK;
+  policy_sample_kernel<<<ceil_div((int64_t)rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(mu, logstd, noise, rand_mask, rows, act_dim,
+                                                                                           actions, neglogp, sigma_out);
   ASE_LAUNCH_OK();
   return ASE_OK;
 }

@@ -246,17 +246,17 @@ class Learner:
         s = out['scalars'].tolist()
         return dict(zip(L.TR_NAMES, s))
 
-    def eval_actor_critic(self, obs, latents=None, want_value=True):
-        """Eval-mode actor (+critic) forward (ase_agent.py:117-148,385-393) -> (mu [n,act], normalised value [n,1] or None)."""
+    def eval_actor_critic(self, obs, latents=None, want_value=True, want_actor=True):
+        """Eval-mode actor and/or critic forward (ase_agent.py:117-148,385-393) -> (mu [n,act] or None, normalised value [n,1] or None)."""
         n = obs.shape[0]
         obs = self._c(obs); lat = self._c(latents)
-        mu = torch.empty(n, self.act_dim, dtype=torch.float32, device=self.device)
+        mu = torch.empty(n, self.act_dim, dtype=torch.float32, device=self.device) if want_actor else None
         val = torch.empty(n, 1, dtype=torch.float32, device=self.device) if want_value else None
         st = self._state()
         for s in range(0, n, self.batch):
             e = min(n, s + self.batch)
             check(lib.ase_learner_eval_actor_critic(self._h, C.byref(st), obs[s:e].data_ptr(), lat[s:e].data_ptr() if lat is not None else None,
-                                                    e - s, mu[s:e].data_ptr(), val[s:e].data_ptr() if want_value else None, _stream()),
+                                                    e - s, mu[s:e].data_ptr() if want_actor else None, val[s:e].data_ptr() if want_value else None, _stream()),
                   'ase_learner_eval_actor_critic')
         return mu, val
 

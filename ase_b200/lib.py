@@ -67,7 +67,7 @@ class TrainResult(C.Structure):
 
 # every symbol declared in include/ase_b200.h (tests/test_abi.py checks the two lists agree)
 EXPORTS = ['ase_abi_version', 'ase_last_error', 'ase_launch_count', 'ase_obs_build', 'ase_amp_obs_build',
-           'ase_rms_scratch_bytes', 'ase_rms_update', 'ase_rms_apply', 'ase_gae', 'ase_amp_rewards', 'ase_adv_normalize',
+           'ase_rms_scratch_bytes', 'ase_rms_update', 'ase_rms_apply', 'ase_gae', 'ase_amp_rewards', 'ase_policy_sample', 'ase_adv_normalize',
            'ase_gemm', 'ase_gemm_tc_workspace_bytes', 'ase_learner_num_params', 'ase_learner_param_desc',
            'ase_learner_arena_floats', 'ase_learner_workspace_bytes', 'ase_learner_create', 'ase_learner_destroy',
            'ase_learner_calc_gradients', 'ase_learner_adam_step', 'ase_learner_eval_actor_critic',
@@ -93,6 +93,7 @@ def _load():
     lib.ase_rms_apply.argtypes = [vp, i64, i32, i32, vp, vp, f32, i32, vp, i64, vp]
     lib.ase_gae.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp]
     lib.ase_amp_rewards.argtypes = [vp, vp, vp, i32, i32, f32, f32, vp, f32, f32, f32, vp, vp, vp, vp]
+    lib.ase_policy_sample.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
     lib.ase_adv_normalize.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     lib.ase_obs_build.argtypes = [C.POINTER(ObsBuildParams), vp]
     lib.ase_amp_obs_build.argtypes = [C.POINTER(AmpObsBuildParams), vp]

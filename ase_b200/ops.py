@@ -138,6 +138,17 @@ def amp_rewards(disc_logits, enc_pred=None, latents=None, disc_scale=2.0, enc_sc
     return dr, er, comb
 
 
+def policy_sample(mu, logstd, noise, rand_mask=None):
+    """Eval-mode Gaussian head + eps-greedy override (amp_agent.py:139-169) -> (actions, neglogpacs, sigmas)."""
+    rows, a = mu.shape
+    mu = _f32c(mu, 'mu'); noise = _f32c(noise, 'noise')
+    actions = torch.empty_like(mu); sig = torch.empty_like(mu)
+    nlp = torch.empty(rows, device=mu.device, dtype=torch.float32)
+    check(lib.ase_policy_sample(_p(mu), _p(logstd), _p(noise), _p(rand_mask), rows, a, _p(actions), _p(nlp), _p(sig), _stream()),
+          'ase_policy_sample')
+    return actions, nlp, sig
+
+
 def calc_advs(returns, values, mask=None):
     """amp_agent.py:551-561 / common_agent.py:536-546 (value_size 1)."""
     rows = returns.shape[0]

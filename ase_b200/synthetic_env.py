@@ -1,0 +1,126 @@
+"""Stand-in for the Isaac Gym vec-env (run.py:100-145 RLGPUEnv over HumanoidAMP) for benchmarks and tests:
+Isaac Gym is bypassed with synthetic rigid-body-state tensors of the named shape (BASELINE.json north_star),
+everything downstream of the simulator -- compute_humanoid_observations_max, the 10-frame AMP observation
+history, resets -- runs through the CUDA kernels exactly as post_physics_step would
+(env/tasks/humanoid.py:430-440, env/tasks/humanoid_amp.py:50-59).
+
+`state_source`:
+  'device' : a pool of pre-generated states resident in HBM (bench `value`)
+  'host'   : states arrive from PINNED HOST memory every step (bench `e2e`; H2D copy inside the step)"""
+import numpy as np
+import torch
+
+from . import ops
+
+
+class _Box:
+    def __init__(self, low, high):
+        self.low = np.asarray(low, dtype=np.float32); self.high = np.asarray(high, dtype=np.float32); self.shape = self.low.shape
+
+
+class _Task:
+    def __init__(self, n, device):
+        self.num_envs = n
+        self.progress_buf = torch.zeros(n, dtype=torch.long, device=device)
+        self.viewer = None
+
+
+class SyntheticHumanoidEnv:
+    NUM_BODIES, NUM_DOFS, AMP_STEPS, AMP_STEP_DIM = 17, 31, 10, 140
+
+    def __init__(self, num_envs, device='cuda', seed=0, pool=8, state_source='device', done_prob=1.0 / 300.0,
+                 local_root_obs=True, root_height_obs=True, demo_pool=8192):
+        self.device = torch.device(device)
+        self.num_envs = num_envs
+        self.local_root_obs, self.root_height_obs = local_root_obs, root_height_obs
+        self.state_source = state_source
+        self.done_prob = done_prob
+        self.task = _Task(num_envs, self.device)
+        self.env = self                      # agents reach vec_env.env.task / vec_env.env.fetch_amp_obs_demo
+        self.num_obs = 1 + 16 * 3 + 17 * 6 + 17 * 3 + 17 * 3
+        self.num_amp_obs = self.AMP_STEPS * self.AMP_STEP_DIM
+        self.observation_space = _Box(-np.inf * np.ones(self.num_obs), np.inf * np.ones(self.num_obs))
+        self.amp_observation_space = _Box(-np.inf * np.ones(self.num_amp_obs), np.inf * np.ones(self.num_amp_obs))
+        self.action_space = _Box(-np.ones(self.NUM_DOFS), np.ones(self.NUM_DOFS))
+        g = torch.Generator().manual_seed(seed)
+        self._gen = torch.Generator(device=self.device).manual_seed(seed + 1) if self.device.type == 'cuda' else g
+        n, J, D = num_envs, self.NUM_BODIES, self.NUM_DOFS
+        pos = torch.randn(pool, n, J, 3, generator=g); pos[:, :, 0, 2] = 0.5 + 0.7 * torch.rand(pool, n, generator=g)
+        rot = torch.nn.functional.normalize(torch.randn(pool, n, J, 4, generator=g), dim=-1)
+        vel = torch.randn(pool, n, J, 3, generator=g); ang = torch.randn(pool, n, J, 3, generator=g)
+        body = torch.cat([pos, rot, vel, ang], dim=-1).contiguous()                 # [pool, N, J, 13]
+        dof = torch.cat([torch.rand(pool, n, D, generator=g) * 2 - 1, torch.randn(pool, n, D, generator=g) * 2], dim=-1).contiguous()
+        self.h2d_bytes_per_step = 0
+        if state_source == 'host':
+            self._body_pool = body.pin_memory(); self._dof_pool = dof.pin_memory()
+            self.h2d_bytes_per_step = body[0].numel() * 4 + dof[0].numel() * 4
+        else:
+            self._body_pool = body.to(self.device); self._dof_pool = dof.to(self.device)
+        self._pool = pool
+        self._t = 0
+        self._body = torch.empty(n, J, 13, device=self.device)      # what gym.acquire_rigid_body_state_tensor would expose
+        self._dof = torch.empty(n, 2 * D, device=self.device)
+        self.obs_buf = torch.zeros(n, self.num_obs, device=self.device)
+        self._amp_obs_buf = torch.zeros(n, self.AMP_STEPS, self.AMP_STEP_DIM, device=self.device)
+        self.rew_buf = torch.zeros(n, device=self.device)
+        self.reset_buf = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        self._terminate_buf = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        self.extras = {}
+        # demo AMP observations: a fixed pool built by the same kernel from synthetic "motion" states
+        dn = demo_pool
+        dpos = torch.randn(dn, J, 3, generator=g); dpos[:, 0, 2] = 0.8 + 0.1 * torch.rand(dn, generator=g)
+        drot = torch.nn.functional.normalize(torch.randn(dn, J, 4, generator=g) * 0.3 + torch.tensor([0., 0., 0., 1.]), dim=-1)
+        dbody = torch.cat([dpos, drot, 0.5 * torch.randn(dn, J, 3, generator=g), 0.5 * torch.randn(dn, J, 3, generator=g)], dim=-1).to(self.device)
+        ddof_p = (torch.rand(dn, D, generator=g) - 0.5).to(self.device); ddof_v = torch.randn(dn, D, generator=g).to(self.device)
+        self._demo_pool = torch.zeros(dn, self.AMP_STEPS, self.AMP_STEP_DIM, device=self.device)
+        for _ in range(self.AMP_STEPS):
+            ops.build_amp_observations(dbody, ddof_p, ddof_v, self._demo_pool, local_root_obs, root_height_obs, shift_history=True)
+            dbody = dbody + 0.01 * torch.randn(dbody.shape, device=self.device, generator=self._gen)
+            dbody[:, :, 3:7] = torch.nn.functional.normalize(dbody[:, :, 3:7], dim=-1)
+        self._demo_pool = self._demo_pool.view(dn, -1)
+        self._load_state()
+        self._compute_observations(shift=False)
+        self._amp_obs_buf[:, 1:] = self._amp_obs_buf[:, 0:1]
+
+    # ---- what RLGPUEnv exposes (run.py:100-145) -------------------------------------------------------
+    def get_env_info(self):
+        return {'action_space': self.action_space, 'observation_space': self.observation_space,
+                'amp_observation_space': self.amp_observation_space}
+
+    def fetch_amp_obs_demo(self, num_samples):
+        idx = torch.randint(0, self._demo_pool.shape[0], (num_samples,), device=self.device, generator=self._gen)
+        return self._demo_pool[idx]
+
+    def _load_state(self):
+        i = self._t % self._pool
+        self._body.copy_(self._body_pool[i], non_blocking=True)
+        self._dof.copy_(self._dof_pool[i], non_blocking=True)
+        self._t += 1
+
+    def _compute_observations(self, shift, env_ids=None):
+        D = self.NUM_DOFS
+        ops.compute_humanoid_observations_max(self._body, self.local_root_obs, self.root_height_obs, out=self.obs_buf, env_ids=env_ids)
+        ops.build_amp_observations(self._body, self._dof[:, :D], self._dof[:, D:], self._amp_obs_buf, self.local_root_obs,
+                                   self.root_height_obs, shift_history=shift, env_ids=env_ids)
+
+    def step(self, actions):
+        """base_task.py:119-137: physics (bypassed: next synthetic state) then post_physics_step."""
+        self._load_state()
+        self.task.progress_buf += 1
+        self._compute_observations(shift=True)
+        r = torch.rand(self.num_envs, device=self.device, generator=self._gen)
+        self.reset_buf = (r < self.done_prob).to(torch.uint8)
+        self._terminate_buf = (r < 0.5 * self.done_prob).to(torch.uint8)        # terminate is a subset of dones
+        self.extras['terminate'] = self._terminate_buf
+        self.extras['amp_obs'] = self._amp_obs_buf.view(self.num_envs, -1)
+        return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
+
+    def reset(self, env_ids=None):
+        """vec_task_wrappers.py:24-26 -> task.reset(env_ids): obs + AMP history re-initialised for those envs
+        (humanoid_amp.py:146-166,206-218 default-state path: history := current frame)."""
+        if env_ids is not None and len(env_ids) > 0:
+            ids = env_ids.to(torch.int32)
+            self.task.progress_buf[env_ids] = 0
+            self._compute_observations(shift=False, env_ids=ids)
+            self._amp_obs_buf[env_ids, 1:] = self._amp_obs_buf[env_ids, 0:1]
+        return self.obs_buf

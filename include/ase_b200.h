@@ -108,6 +108,12 @@ int ase_amp_rewards(const float* disc_logits, const float* enc_pred, const float
                     int rows, float disc_scale, float enc_scale,
                     const float* task_rewards, float task_w, float disc_w, float enc_w,
                     float* disc_r, float* enc_r, float* combined, void* stream);
+/* Gaussian head in eval mode (rl_games ModelA2CContinuousLogStd.forward, is_train False) + the eps-greedy
+ * override of get_action_values (amp_agent.py:164-167): a = mu + exp(logstd)*noise, neglogp(a); rows whose
+ * rand_mask is 0 act deterministically (a := mu) but keep the sampled action's neglogp, as the reference does.
+ * sigma_out (optional) receives exp(logstd) broadcast to [rows, act_dim]. */
+int ase_policy_sample(const float* mu, const float* logstd, const float* noise, const float* rand_mask,
+                      int rows, int act_dim, float* actions, float* neglogp, float* sigma_out, void* stream);
 /* _calc_advs amp_agent.py:551-561 (+ torch_ext.normalization_with_masks); mask NULL => plain
  * mean / unbiased std (common_agent.py:536-546).  scratch >= 64 bytes. */
 int ase_adv_normalize(const float* returns, const float* values, const float* mask, int rows,
@@ -230,8 +236,8 @@ int ase_learner_adam_step(AseLearner* l, const AseLearnerState* st, int64_t step
 
 /* Rollout-side inference with the same weights (eval mode, no RMS update):
  *   get_action_values ase_agent.py:117-148 / amp_agent.py:139-169; _eval_critic ase_agent.py:385-393;
- *   _eval_disc/_eval_enc ase_agent.py:395-411. Any output pointer may be NULL. rows <= infer_rows given
- *   at create time via ase_learner_workspace_bytes (max(2*batch, 3*amp_batch)). */
+ *   _eval_disc/_eval_enc ase_agent.py:395-411.  Any output pointer may be NULL (mu NULL skips the actor,
+ *   value_normed NULL skips the critic).  rows <= batch (actor/critic), rows <= 3*amp_batch (disc/enc). */
 int ase_learner_eval_actor_critic(AseLearner* l, const AseLearnerState* st, const float* obs, const float* latents,
                                   int rows, float* mu, float* value_normed, void* stream);
 int ase_learner_eval_disc_enc(AseLearner* l, const AseLearnerState* st, const float* amp_obs, int rows,

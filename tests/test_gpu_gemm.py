@@ -57,7 +57,7 @@ def test_simt_layouts_ragged(a_trans, b_trans):
 
 def test_simt_epilogues():
     _run(300, 200, 64, False, False, 0, bias=True, act=1)
-    _run(300, 64, 256, False, False, 0, bias=True, act=2, tol=2e-5)
+    _run(300, 64, 256, False, False, 0, bias=True, act=2, alpha=1.0 / 16, tol=2e-5)
     _run(300, 200, 64, False, True, 0, mask_mode=1)
     _run(300, 64, 100, False, True, 0, mask_mode=2)
     _run(96, 200, 4096, True, True, 0, accumulate=True, split_k=7, tol=2e-5)
@@ -81,7 +81,7 @@ def test_tc_matches_fp64(a_trans, b_trans):
 
 def test_tc_epilogues_and_split_k():
     _run(512, 256, 512, False, False, 1, bias=True, act=1, tol=2e-5)
-    _run(256, 128, 256, False, False, 1, bias=True, act=2, tol=3e-5)
+    _run(256, 128, 256, False, False, 1, bias=True, act=2, alpha=1.0 / 16, tol=3e-5)   # O(1) pre-activations
     _run(512, 320, 256, False, True, 1, mask_mode=1, tol=2e-5)
     _run(256, 64, 128, False, True, 1, mask_mode=2, tol=2e-5)
     _run(1024, 512, 4096, True, True, 1, accumulate=True, split_k=5, tol=3e-5)
@@ -96,5 +96,6 @@ def test_tc_accuracy_is_fp32_class_not_tf32():
     B = (1.0 + torch.rand(128, 1024, generator=g) * 1e-3).cuda()
     C = ops.gemm(A, B, backend=1)
     ref = A.double() @ B.double().t()
-    spread = (ref - ref.mean()).abs().max()
-    assert float((C.double() - ref).abs().max()) < 0.02 * float(spread)
+    # single-pass TF32 rounds every operand to 10 mantissa bits: |err| ~ 0.25 on these sums of ~1025.
+    # 3xTF32 leaves only the tensor core's truncating fp32 accumulation (measured 0.006 = 5e-6 relative, one-sided).
+    assert float((C.double() - ref).abs().max()) < 0.03
