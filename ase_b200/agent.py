@@ -325,9 +325,8 @@ class CommonAgent:
         out = self.model.calc_gradients(input_dict, self._new_latents(input_dict['obs'].shape[0]), update_rms=True)
         scale = 1.0
         if self.multi_gpu:
-            import torch.distributed as dist
-            dist.all_reduce(self.model.grads)               # one flat NCCL sum per minibatch (Horovod averaged: amp_agent.py:357-363)
-            scale = 1.0 / self.rank_size
+            from .dist_utils import allreduce_grads
+            scale = allreduce_grads(self.model.grads)       # one flat NCCL sum per minibatch (Horovod averaged: amp_agent.py:357-363)
         self.model.adam_step(grad_scale=scale)
         row = self._tr_buf[self._tr_i % self._tr_buf.shape[0]]
         row.copy_(out['scalars'])
@@ -393,19 +392,16 @@ class CommonAgent:
 
     def _sync_stats(self):
         """Horovod sync_stats [recollection of rl_games]: RunningMeanStd buffers are averaged across ranks once per epoch."""
-        import torch.distributed as dist
-        for r in self._rms_modules():
-            for t in (r.running_mean, r.running_var, r.count):
-                dist.all_reduce(t)
-                t /= self.rank_size
+        from .dist_utils import sync_running_stats
+        sync_running_stats(self._rms_modules())
 
     def train(self):
         """common_agent.py:82-155 (logging / checkpoint cadence kept; TensorBoard scalars are the caller's business)."""
         self.init_tensors()
         self.obs = self.env_reset()
         if self.multi_gpu:
-            import torch.distributed as dist
-            dist.broadcast(self.model.params, 0)
+            from .dist_utils import broadcast_state
+            broadcast_state([self.model.params, self.model.exp_avg, self.model.exp_avg_sq])
         self._init_train()
         total_time = 0.0
         while True:

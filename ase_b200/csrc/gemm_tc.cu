@@ -15,6 +15,7 @@
 // Descriptor formats follow the PTX ISA "tcgen05 shared memory descriptor" / "instruction descriptor" tables
 // (cross-checked against cute/arch/mma_sm100_desc.hpp in the image's CUTLASS headers).
 #include <cuda.h>
+#include <vector>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -328,6 +329,25 @@ static int prep_operand(const float* src, int64_t ld, int trans, int rows, int K
   return ASE_OK;
 }
 
+// Optional per-launch timing of the main kernel (bench.py's live roofline measurement): CUDA events recorded on
+// the launching stream around every gemm_tc_kernel launch; read back (with a sync) by ase_gemm_tc_profile_read.
+struct TcProfile {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // pairs
+  size_t used = 0;
+  double flops = 0.0;
+};
+static TcProfile g_prof;
+
+static void prof_mark(cudaStream_t st) {
+  if (g_prof.used == g_prof.ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) { g_prof.on = false; return; }
+    g_prof.ev.push_back(e);
+  }
+  cudaEventRecord(g_prof.ev[g_prof.used++], st);
+}
+
 template <int BN, int STAGES>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcEpi& e,
                      int splits, cudaStream_t st) {
@@ -338,7 +358,10 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
     attr_set = true;
   }
   dim3 grid(ceil_div(e.N, BN), ceil_div(e.M, TC_BM), splits);
+  const bool prof = g_prof.on;
+  if (prof) prof_mark(st);
   gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, SM::TOTAL, st>>>(ah, al, bh, bl, e);
+  if (prof) { prof_mark(st); g_prof.flops += 2.0 * (double)e.M * (double)e.N * (double)e.kb_total * TC_BK; }
   ASE_LAUNCH_OK();
   return ASE_OK;
 }
@@ -374,3 +397,26 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st) {
 }
 
 }  // namespace ase
+
+extern "C" int ase_gemm_tc_profile(int enable) {
+  ase::g_prof.on = enable != 0;
+  ase::g_prof.used = 0;
+  ase::g_prof.flops = 0.0;
+  return ASE_OK;
+}
+
+extern "C" int ase_gemm_tc_profile_read(double* total_ms, int64_t* launches, double* flops) {
+  using namespace ase;
+  double tot = 0.0;
+  const size_t n = g_prof.used / 2;
+  for (size_t i = 0; i < n; ++i) {
+    float ms = 0.0f;
+    ASE_CUDA_OK(cudaEventSynchronize(g_prof.ev[2 * i + 1]));
+    ASE_CUDA_OK(cudaEventElapsedTime(&ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]));
+    tot += ms;
+  }
+  if (total_ms) *total_ms = tot;
+  if (launches) *launches = (int64_t)n;
+  if (flops) *flops = g_prof.flops;
+  return ASE_OK;
+}

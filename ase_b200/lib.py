@@ -68,7 +68,7 @@ class TrainResult(C.Structure):
 # every symbol declared in include/ase_b200.h (tests/test_abi.py checks the two lists agree)
 EXPORTS = ['ase_abi_version', 'ase_last_error', 'ase_launch_count', 'ase_obs_build', 'ase_amp_obs_build',
            'ase_rms_scratch_bytes', 'ase_rms_update', 'ase_rms_apply', 'ase_gae', 'ase_amp_rewards', 'ase_policy_sample', 'ase_adv_normalize',
-           'ase_gemm', 'ase_gemm_tc_workspace_bytes', 'ase_learner_num_params', 'ase_learner_param_desc',
+           'ase_gemm', 'ase_gemm_tc_workspace_bytes', 'ase_gemm_tc_profile', 'ase_gemm_tc_profile_read', 'ase_learner_num_params', 'ase_learner_param_desc',
            'ase_learner_arena_floats', 'ase_learner_workspace_bytes', 'ase_learner_create', 'ase_learner_destroy',
            'ase_learner_calc_gradients', 'ase_learner_adam_step', 'ase_learner_eval_actor_critic',
            'ase_learner_eval_disc_enc']
@@ -99,6 +99,8 @@ def _load():
     lib.ase_amp_obs_build.argtypes = [C.POINTER(AmpObsBuildParams), vp]
     lib.ase_gemm.argtypes = [C.POINTER(GemmParams), vp]
     lib.ase_gemm_tc_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.ase_gemm_tc_profile.argtypes = [i32]
+    lib.ase_gemm_tc_profile_read.argtypes = [C.POINTER(C.c_double), C.POINTER(i64), C.POINTER(C.c_double)]
     lib.ase_learner_num_params.argtypes = [C.POINTER(LearnerConfig)]
     lib.ase_learner_param_desc.argtypes = [C.POINTER(LearnerConfig), i32, C.POINTER(i64), C.POINTER(i32), C.POINTER(i32)]
     lib.ase_learner_arena_floats.argtypes = [C.POINTER(LearnerConfig)]

@@ -1,0 +1,256 @@
+#!/usr/bin/env python
+"""bench.py -- training env-steps/sec, HumanoidAMPGetup ASE pre-train, 4096 envs/GPU (BASELINE.json metric).
+
+One "step" = one training epoch of the hot path on one batch of synthetic input:
+  32-step rollout of 4096 envs (Isaac Gym bypassed with synthetic rigid-body-state tensors; observation build,
+  AMP history, actor / critic inference, disc + enc rewards, GAE all run) + 6 x 8 minibatch updates
+  (calc_gradients + Adam, B = 16384, B_amp = 4096)  = 131072 env-steps per GPU.
+
+  value : inputs (rigid-body states) already resident in HBM when the timed region starts
+  e2e   : same epoch through the public agent API with the rigid-body states arriving from PINNED HOST memory
+          every sim step (H2D inside the timed region) and the train_result scalars read back to the host (D2H)
+
+  python bench.py --gpus 1 --steps 3 --warmup 3
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+  python bench.py --impl reference ...     # the reference's own algorithm on the host CPU cores (oracle port)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "training env-steps/sec HumanoidAMPGetup 4096 envs/GPU"
+UNIT = "env-steps/s"
+NUM_ENVS, HORIZON, MINIBATCH, AMP_MINIBATCH, MINI_EPOCHS = 4096, 32, 16384, 4096, 6
+FLOP_PER_MINIBATCH = 0.9685e12      # algorithmic, fp32, fwd + bwd + gradient penalty
+FLOP_ROLLOUT_PER_EPOCH = 3.13e12
+
+
+def _workload_config(n_gpus):
+    return {"workload": "HumanoidAMPGetup ASE pre-train (disc+encoder+diversity), synthetic rigid-body states, Isaac Gym bypassed",
+            "num_envs_per_gpu": NUM_ENVS, "horizon": HORIZON, "minibatch": MINIBATCH, "amp_minibatch": AMP_MINIBATCH,
+            "mini_epochs": MINI_EPOCHS, "minibatches_per_step": MINI_EPOCHS * (NUM_ENVS * HORIZON // MINIBATCH),
+            "env_steps_per_step_per_gpu": NUM_ENVS * HORIZON, "parallelism": f"env-sharded dp{n_gpus}",
+            "l2_policy": "inputs larger than L2 (per-epoch working set ~3 GB: experience buffers, activations, 28 MB weights x4)"}
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._th = None
+
+    def _run(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(out[0])); self.max_mhz = float(out[1])
+                for n, v in zip(names, out[2:6]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._th = threading.Thread(target=self._run, daemon=True); self._th.start(); return self
+
+    def __exit__(self, *a):
+        self._stop.set(); self._th.join(timeout=6)
+
+    def summary(self):
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------ ours
+def _make_agent(torch, rank, world, state_source, seed):
+    from ase_b200 import configs
+    from ase_b200.agent import ASEAgent
+    from ase_b200.synthetic_env import SyntheticHumanoidEnv
+    dev = f"cuda:{torch.cuda.current_device()}"
+    env = SyntheticHumanoidEnv(NUM_ENVS, device=dev, seed=seed + rank, state_source=state_source)   # seed += rank (run.py:36-50)
+    cfg = configs.make('ase', device=dev, vec_env=env, num_actors=NUM_ENVS, multi_gpu=world > 1, print_stats=False,
+                       seed=seed, gemm_backend=1)
+    agent = ASEAgent('bench', cfg)
+    agent.init_tensors()
+    agent.obs = agent.env_reset()
+    if world > 1:
+        import torch.distributed as dist
+        dist.broadcast(agent.model.params, 0)
+    agent._init_train()
+    return agent, env
+
+
+def _timed_epochs(torch, agent, steps, world, d2h=False):
+    """barrier + synchronize on both sides, CUDA events on the launching (current) stream, max over ranks."""
+    import torch.distributed as dist
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    host = []
+    e0.record()
+    for _ in range(steps):
+        agent.update_epoch()
+        info = agent.train_epoch()
+        if d2h:
+            host.append(agent._tr_buf.cpu())           # the step's train_result series -> host (D2H inside the timed region)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    return float(ms) / 1e3, host
+
+
+def run_ours(args):
+    import torch
+    rank = int(os.environ.get("RANK", 0)); world = int(os.environ.get("WORLD_SIZE", 1)); local = int(os.environ.get("LOCAL_RANK", 0))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    from ase_b200 import lib as L
+    import ctypes as C
+    torch.manual_seed(1234 + rank)
+
+    agent, env = _make_agent(torch, rank, world, 'device', seed=0)
+    for _ in range(args.warmup):
+        agent.update_epoch(); agent.train_epoch()
+    torch.cuda.synchronize()
+    launches0 = L.launch_count()
+    L.lib.ase_gemm_tc_profile(1)
+    with ClockSampler(local) as clk:
+        secs, _ = _timed_epochs(torch, agent, args.steps, world)
+    tot_ms, nl, fl = C.c_double(), C.c_int64(), C.c_double()
+    L.check(L.lib.ase_gemm_tc_profile_read(C.byref(tot_ms), C.byref(nl), C.byref(fl)), 'profile_read')
+    L.lib.ase_gemm_tc_profile(0)
+    launches = L.launch_count() - launches0
+    play_t, upd_t, _ = agent.epoch_times()
+    tr = {k: float(v) for k, v in zip(L.TR_NAMES, agent._tr_buf[-1].tolist())}
+    env_steps = args.steps * NUM_ENVS * HORIZON * world
+    value = env_steps / secs
+    del agent, env
+    torch.cuda.empty_cache()
+
+    # e2e: host-resident simulator state, H2D every sim step, D2H of the step's train_result
+    agent, env = _make_agent(torch, rank, world, 'host', seed=0)
+    for _ in range(max(1, min(args.warmup, 2))):
+        agent.update_epoch(); agent.train_epoch()
+    e2e_secs, host = _timed_epochs(torch, agent, args.steps, world, d2h=True)
+    e2e_value = env_steps / e2e_secs
+    h2d = env.h2d_bytes_per_step * HORIZON
+    d2h = host[0].numel() * 4 if host else 0
+    del agent, env
+
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained")
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16, sustained: the kernel is timed inside a long step)"
+    if peak_tf is None:
+        peak_tf, peak_src = 1400.0, "fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)"
+    achieved_tf = (fl.value / 1e12) / (tot_ms.value / 1e3) if tot_ms.value > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    nmb = args.steps * MINI_EPOCHS * (NUM_ENVS * HORIZON // MINIBATCH)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": secs * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (3xTF32 tensor-core products, fp32 accumulate)", "data": "synthetic",
+        "config": _workload_config(world),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_secs * 1e3 / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc_kernel (tcgen05.mma kind::tf32, 3xTF32)", "achieved": achieved_tf,
+                     "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
+                     "peak_source": peak_src, "launches_timed": int(nl.value), "kernel_ms_per_step": tot_ms.value / args.steps,
+                     "kernel_share_of_step": (tot_ms.value / 1e3) / secs,
+                     "note": "achieved = algorithmic 2*M*N*K FLOPs of the timed launches / summed CUDA-event kernel time; fp32 parity "
+                             "forces 3 TF32 MMAs per product, so the ceiling against the bf16 peak is 1/6",
+                     "learner_tflops_algorithmic": nmb * FLOP_PER_MINIBATCH / 1e12 / (upd_t * args.steps) if upd_t > 0 else None},
+        "split": {"play_time_s_last_step": play_t, "update_time_s_last_step": upd_t},
+        "train_result_last": tr,
+    }
+    if world == 1:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs
+def cpu_baseline():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import cpu_bench
+    torch.set_num_threads(os.cpu_count() or 1)
+    r = cpu_bench.sample_epoch_seconds(NUM_ENVS, HORIZON, MINIBATCH, AMP_MINIBATCH, MINI_EPOCHS, warm=False)
+    return {"value": r["env_steps_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
+            "sample": r["sample"] + " (no warm-up)", "minibatch_s": r["minibatch_s"], "rollout_step_s": r["rollout_step_s"]}
+
+
+def run_reference(args):
+    """The reference's own algorithm (CPU torch fp32, all host threads) on the same workload: oracle port, since the
+    reference is Python and /root/reference does not exist on the GPU box.  Each step is a bounded sample."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch
+    import cpu_bench
+    torch.set_num_threads(os.cpu_count() or 1)
+    for _ in range(min(args.warmup, 1)):
+        cpu_bench.sample_epoch_seconds(NUM_ENVS, HORIZON, MINIBATCH, AMP_MINIBATCH, MINI_EPOCHS, warm=False)
+    vals, last = [], None
+    for _ in range(args.steps):
+        last = cpu_bench.sample_epoch_seconds(NUM_ENVS, HORIZON, MINIBATCH, AMP_MINIBATCH, MINI_EPOCHS, warm=False)
+        vals.append(last["env_steps_per_s"])
+    v = statistics.median(vals)
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * NUM_ENVS * HORIZON / v, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": _workload_config(args.gpus),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["threads"], "kind": "port", "sample": last["sample"]},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "CPU arm does not scale with --gpus: one host runs the reference algorithm for one env shard"}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

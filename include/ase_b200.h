@@ -145,6 +145,11 @@ typedef struct {
 } AseGemmParams;
 int ase_gemm(const AseGemmParams* p, void* stream);
 int64_t ase_gemm_tc_workspace_bytes(int M, int N, int K);
+/* Live timing of the tcgen05 main kernel (bench.py roofline): enable(1)/disable(0) resets the counters; while
+ * enabled every launch is bracketed by CUDA events on its stream.  _read synchronises those events and returns the
+ * summed kernel time, the launch count and the algorithmic FLOPs (2*M*N*Kpad per launch). */
+int ase_gemm_tc_profile(int enable);
+int ase_gemm_tc_profile_read(double* total_ms, int64_t* launches, double* flops);
 
 /* ------------------------------------------------------------------------------------------------
  * Learner: one PPO + adversarial minibatch update.  Replaces
