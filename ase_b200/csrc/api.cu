@@ -45,7 +45,7 @@ extern "C" int ase_gemm(const AseGemmParams* p, void* stream) {
   if (p->backend == 1) {
     int rc = check_gemm(*p);
     if (rc) return rc;
-    if (!gemm_tc_supported(*p)) { set_error("ase_gemm: shape/alignment not supported by the tcgen05 backend"); return ASE_ERR_UNSUPPORTED; }
+    if (!gemm_tc_supported(*p)) { set_error("ase_gemm: shape %dx%dx%d not supported by the tcgen05 backend (needs M>=128, N>=64, K>=32)", p->M, p->N, p->K); return ASE_ERR_UNSUPPORTED; }
     return gemm_tc(*p, (cudaStream_t)stream);
   }
   return gemm_dispatch(*p, (cudaStream_t)stream);

@@ -310,11 +310,18 @@ int64_t gemm_tc_workspace_bytes(int M, int N, int K) {
   return 2 * align_up((int64_t)M * Kp * 4, 1024) + 2 * align_up((int64_t)N * Kp * 4, 1024);
 }
 
-bool gemm_tc_supported(const AseGemmParams& p) {
-  if (p.M < 128 || p.N < 64 || p.K < 32) return false;
-  if (!p.workspace || p.workspace_bytes < gemm_tc_workspace_bytes(p.M, p.N, p.K)) return false;
-  if (reinterpret_cast<uintptr_t>(p.workspace) & 1023) return false;
-  return true;
+// shapes the tcgen05 kernel takes; everything else (tiny heads, K=1 outer products) goes to the SIMT kernel
+bool gemm_tc_supported(const AseGemmParams& p) { return p.M >= 128 && p.N >= 64 && p.K >= 32; }
+
+// a qualifying shape with a missing / small / misaligned workspace is an ERROR, never a silent fallback
+int gemm_tc_check_workspace(const AseGemmParams& p) {
+  if (!p.workspace || p.workspace_bytes < gemm_tc_workspace_bytes(p.M, p.N, p.K)) {
+    set_error("tcgen05 GEMM %dx%dx%d: workspace %lld bytes < required %lld", p.M, p.N, p.K, (long long)p.workspace_bytes,
+              (long long)gemm_tc_workspace_bytes(p.M, p.N, p.K));
+    return ASE_ERR_WORKSPACE;
+  }
+  if (reinterpret_cast<uintptr_t>(p.workspace) & 1023) { set_error("tcgen05 GEMM: workspace must be 1024-byte aligned"); return ASE_ERR_WORKSPACE; }
+  return ASE_OK;
 }
 
 static int prep_operand(const float* src, int64_t ld, int trans, int rows, int K, int Kp, float* hi, float* lo, cudaStream_t st) {
@@ -367,6 +374,8 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
 }
 
 int gemm_tc(const AseGemmParams& p, cudaStream_t st) {
+  int wrc = gemm_tc_check_workspace(p);
+  if (wrc) return wrc;
   const int Kp = kpad(p.K);
   char* ws = (char*)p.workspace;
   float* Ahi = (float*)ws; ws += align_up((int64_t)p.M * Kp * 4, 1024);

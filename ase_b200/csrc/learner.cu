@@ -154,6 +154,7 @@ static void carve(AseLearner& L, void* ws, int64_t* total) {
   L.rms_obs_scratch = cv.take<char>(rms_scratch_bytes(c.obs_dim, L.B, 1));
   L.rms_amp_scratch = L.amp ? cv.take<char>(rms_scratch_bytes(c.amp_dim, L.Ba, 3)) : nullptr;
   L.tc_ws_bytes = tc_ws_need(L);
+  cv.off = align_up(cv.off, 1024);
   L.tc_ws = L.tc_ws_bytes ? cv.take<char>(L.tc_ws_bytes) : nullptr;
   *total = cv.off;
 }
@@ -303,7 +304,7 @@ extern "C" int64_t ase_learner_workspace_bytes(const AseLearnerConfig* cfg) {
 }
 extern "C" int ase_learner_create(const AseLearnerConfig* cfg, void* workspace, int64_t workspace_bytes, AseLearner** out) {
   ASE_CHECK_ARG(cfg && workspace && out, "ase_learner_create: null pointer");
-  ASE_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "ase_learner_create: workspace must be 256-byte aligned");
+  ASE_CHECK_ARG((reinterpret_cast<uintptr_t>(workspace) & 1023) == 0, "ase_learner_create: workspace must be 1024-byte aligned");
   AseLearner* L = new (std::nothrow) AseLearner;
   ASE_CHECK_ARG(L != nullptr, "ase_learner_create: out of host memory");
   memset(L, 0, sizeof(*L));

@@ -207,10 +207,10 @@ def cpu_baseline():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
     import cpu_bench
-    torch.set_num_threads(os.cpu_count() or 1)
-    r = cpu_bench.sample_epoch_seconds(NUM_ENVS, HORIZON, MINIBATCH, AMP_MINIBATCH, MINI_EPOCHS, warm=False)
+    cpu_bench.pick_threads()
+    r = cpu_bench.sample_epoch_seconds(NUM_ENVS, HORIZON, MINIBATCH, AMP_MINIBATCH, MINI_EPOCHS, warm=True)
     return {"value": r["env_steps_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
-            "sample": r["sample"] + " (no warm-up)", "minibatch_s": r["minibatch_s"], "rollout_step_s": r["rollout_step_s"]}
+            "sample": r["sample"] + " (each call warmed once)", "minibatch_s": r["minibatch_s"], "rollout_step_s": r["rollout_step_s"]}
 
 
 def run_reference(args):
@@ -222,7 +222,7 @@ def run_reference(args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch
     import cpu_bench
-    torch.set_num_threads(os.cpu_count() or 1)
+    cpu_bench.pick_threads()
     for _ in range(min(args.warmup, 1)):
         cpu_bench.sample_epoch_seconds(NUM_ENVS, HORIZON, MINIBATCH, AMP_MINIBATCH, MINI_EPOCHS, warm=False)
     vals, last = [], None

@@ -16,6 +16,31 @@ import ase_oracle as O
 import synth
 
 
+def pick_threads():
+    """The GPU box advertises 128 logical CPUs but torch CPU kernels collapse when oversubscribed: probe a GEMM of the
+    learner's shape with a few thread counts (<= the affinity mask) and keep the fastest.  This is the core count the
+    CPU arm reports."""
+    import os
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    cands = sorted({c for c in (avail, 64, 32, 16, 8) if 1 <= c <= avail}, reverse=True)
+    a = torch.randn(4096, 1024); b = torch.randn(1024, 1024)
+    best, best_t = cands[-1], float('inf')
+    for c in cands:
+        torch.set_num_threads(c)
+        a @ b
+        t0 = time.perf_counter()
+        for _ in range(3):
+            a @ b
+        t = time.perf_counter() - t0
+        if t < best_t:
+            best, best_t = c, t
+    torch.set_num_threads(best)
+    return best
+
+
 def _t(fn, reps=1):
     t0 = time.perf_counter()
     for _ in range(reps):
