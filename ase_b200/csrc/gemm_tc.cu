@@ -107,18 +107,32 @@ struct TcSmem {
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// fp32-exact accumulation ("accumulate outside the tensor core", Ootomo & Yokota 2022, mapped to TMEM):
+// the tensor core adds into its accumulator with truncation (measured: one-sided drift of ~0.1 ulp per MMA), which
+// over K/8 x 3 sequential MMAs costs ~1e-5 absolute on O(1) sums -- enough to flip ReLU masks against the fp32
+// reference.  So the main term A_hi.B_hi is accumulated in TMEM only WITHIN one 32-wide k-block (4 MMAs, fresh
+// accumulator), double buffered; the epilogue warps drain each k-block's partial tile with tcgen05.ld and add it
+// into fp32 registers with round-to-nearest FADDs while the tensor core works on the next k-block.  The two
+// correction terms (2^-11 smaller) accumulate across all of K in a third TMEM tile: their truncation is negligible.
 template <int BN, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const TcEpi e) {
   using SM = TcSmem<BN, STAGES>;
+  constexpr uint32_t TMEM_COLS = (3 * BN <= 256) ? 256u : 512u;      // main[0], main[1], corr
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
-  uint64_t* tmem_full = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+  uint64_t* main_full = bars + 2 * STAGES;         // [2]
+  uint64_t* main_empty = bars + 2 * STAGES + 2;    // [2]
+  uint64_t* corr_full = bars + 2 * STAGES + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
@@ -127,17 +141,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(tmem_full, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&main_full[b], 1); mbar_init(&main_empty[b], 4); }   // 4 epilogue warps arrive
+    mbar_init(corr_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)BN));
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_corr = tmem_base + 2 * BN;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -162,70 +178,97 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
+        const int b = kb & 1;
+        const uint32_t bph = (kb >> 1) & 1;
         mbar_wait(&full[s], ph);
+        mbar_wait(&main_empty[b], bph ^ 1);       // the drain of the k-block that used this TMEM tile two steps ago
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
         const uint32_t a_hi = sa, a_lo = sa + SM::A_BYTES, b_hi = sa + 2 * SM::A_BYTES, b_lo = b_hi + SM::B_BYTES;
+        const uint32_t tmem_main = tmem_base + (uint32_t)b * BN;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k)     // 8 tf32 = 32 bytes along the swizzled row per MMA
+          tc_mma_tf32(tmem_main, make_smem_desc(a_hi + k * 32), make_smem_desc(b_hi + k * 32), idesc, k > 0 ? 1u : 0u);
+        tc_commit(&main_full[b]);              // this k-block's A_hi.B_hi partial tile is complete
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {
-          const uint32_t ko = k * 32;   // 8 tf32 = 32 bytes along the swizzled row
-          const uint64_t dah = make_smem_desc(a_hi + ko), dal = make_smem_desc(a_lo + ko);
-          const uint64_t dbh = make_smem_desc(b_hi + ko), dbl = make_smem_desc(b_lo + ko);
-          tc_mma_tf32(tmem_base, dal, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);   // small terms first
-          tc_mma_tf32(tmem_base, dah, dbl, idesc, 1u);
-          tc_mma_tf32(tmem_base, dah, dbh, idesc, 1u);
+          tc_mma_tf32(tmem_corr, make_smem_desc(a_lo + k * 32), make_smem_desc(b_hi + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_mma_tf32(tmem_corr, make_smem_desc(a_hi + k * 32), make_smem_desc(b_lo + k * 32), idesc, 1u);
         }
-        tc_commit(&empty[s]);          // frees this smem stage once the MMAs above have read it
+        tc_commit(&empty[s]);                  // all 12 MMAs have read this smem stage
       }
-      tc_commit(tmem_full);            // accumulator complete
+      tc_commit(corr_full);
     }
     __syncwarp();
   } else {
-    // epilogue warps 2..5 own TMEM lane groups (warp % 4)
+    // epilogue / drain warps 2..5 own TMEM lane groups (warp % 4); one output row per thread
     const int lg = warp & 3;
-    mbar_wait(tmem_full, 0);
+    const uint32_t lane_off = (uint32_t)(lg * 32) << 16;
+    float acc[BN];
+#pragma unroll
+    for (int j = 0; j < BN; ++j) acc[j] = 0.0f;
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int b = kb & 1;
+      const uint32_t bph = (kb >> 1) & 1;
+      mbar_wait(&main_full[b], bph);
+      tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tc_ld_32x32(tmem_base + lane_off + (uint32_t)(b * BN + c), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c + j] += v[j];      // round-to-nearest fp32 accumulation across k-blocks
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&main_empty[b]);
+    }
+    mbar_wait(corr_full, 0);
     tc_fence_after();
     const int m = m0 + lg * 32 + lane;
     const bool row_ok = m < e.M;
     const bool vec_ok = ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0);
-#pragma unroll 1
+#pragma unroll
     for (int c = 0; c < BN; c += 32) {
       float v[32];
-      tc_ld_32x32(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)c, v);
+      tc_ld_32x32(tmem_corr + lane_off + (uint32_t)c, v);
       const int nb = n0 + c;
-      if (!row_ok || nb >= e.N) continue;
-      float* crow = e.C + (int64_t)m * e.ldc + nb;
-      const int nvalid = min(32, e.N - nb);
+      if (row_ok && nb < e.N) {
+        float* crow = e.C + (int64_t)m * e.ldc + nb;
+        const int nvalid = min(32, e.N - nb);
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = e.alpha * v[j];
-        if (j < nvalid) {
-          if (e.accumulate) {
-            if (e.bias && blockIdx.z == 0) x += e.bias[nb + j];
-          } else {
-            if (e.bias) x += e.bias[nb + j];
-            if (e.act == 1) x = fmaxf(x, 0.0f);
-            else if (e.act == 2) x = tanhf(x);
-            if (e.mask_mode == 1) x = (e.mask_src[(int64_t)m * e.ldm + nb + j] > 0.0f) ? x : 0.0f;
-            else if (e.mask_mode == 2) { const float s = e.mask_src[(int64_t)m * e.ldm + nb + j]; x *= (1.0f - s * s); }
+        for (int j = 0; j < 32; ++j) {
+          float x = e.alpha * (acc[c + j] + v[j]);
+          if (j < nvalid) {
+            if (e.accumulate) {
+              if (e.bias && blockIdx.z == 0) x += e.bias[nb + j];
+            } else {
+              if (e.bias) x += e.bias[nb + j];
+              if (e.act == 1) x = fmaxf(x, 0.0f);
+              else if (e.act == 2) x = tanhf(x);
+              if (e.mask_mode == 1) x = (e.mask_src[(int64_t)m * e.ldm + nb + j] > 0.0f) ? x : 0.0f;
+              else if (e.mask_mode == 2) { const float sv = e.mask_src[(int64_t)m * e.ldm + nb + j]; x *= (1.0f - sv * sv); }
+            }
           }
+          v[j] = x;
         }
-        v[j] = x;
-      }
-      if (e.accumulate) {
-        for (int j = 0; j < nvalid; ++j) atomicAdd(crow + j, v[j]);
-      } else if (vec_ok && nvalid == 32) {
+        if (e.accumulate) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-      } else {
-        for (int j = 0; j < nvalid; ++j) crow[j] = v[j];
+          for (int j = 0; j < 32; ++j) if (j < nvalid) atomicAdd(crow + j, v[j]);
+        } else if (vec_ok && nvalid == 32) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (j < nvalid) crow[j] = v[j];
+        }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BN));
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
 }
 

@@ -96,6 +96,7 @@ def test_tc_accuracy_is_fp32_class_not_tf32():
     B = (1.0 + torch.rand(128, 1024, generator=g) * 1e-3).cuda()
     C = ops.gemm(A, B, backend=1)
     ref = A.double() @ B.double().t()
-    # single-pass TF32 rounds every operand to 10 mantissa bits: |err| ~ 0.25 on these sums of ~1025.
-    # 3xTF32 leaves only the tensor core's truncating fp32 accumulation (measured 0.006 = 5e-6 relative, one-sided).
-    assert float((C.double() - ref).abs().max()) < 0.03
+    # single-pass TF32 rounds every operand to 10 mantissa bits: |err| ~ 0.25 on these sums of ~1025.  3xTF32 with the
+    # tensor core accumulating across all of K left a one-sided 0.006 (truncating accumulator); with the k-block partials
+    # accumulated outside in fp32 RN the error is a few ulps of 1025 (1.2e-4 each).
+    assert float((C.double() - ref).abs().max()) < 1.5e-3
