@@ -102,7 +102,7 @@ def test_calc_gradients_vs_reference_golden_tcgen05(name):
     ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
     L.check(L.lib.ase_gemm_tc_profile_read(C.byref(ms), C.byref(n), C.byref(fl)), 'profile_read')
     L.lib.ase_gemm_tc_profile(0)
-    assert n.value >= 2 * 30, f"the tcgen05 kernel was launched only {n.value} times: the learner fell back to SIMT"
+    assert n.value >= 20, f"the tcgen05 kernel was launched only {n.value} times: the learner fell back to SIMT"
 
 
 def test_ppo_kind_vs_oracle():
