@@ -16,6 +16,7 @@
 // (cross-checked against cute/arch/mma_sm100_desc.hpp in the image's CUTLASS headers).
 #include <cuda.h>
 #include <vector>
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -97,6 +98,7 @@ struct TcEpi {
   int act;
   const float* mask_src; int64_t ldm; int mask_mode;
   int accumulate;
+  int debug;   // experiments only (env ASE_TC_DEBUG): 1 skip global stores, 2 skip TMEM drain loads, 4 skip correction MMAs, 8 skip bias/act
 };
 
 template <int BN, int STAGES>
@@ -190,6 +192,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         for (int k = 0; k < TC_BK / 8; ++k)     // 8 tf32 = 32 bytes along the swizzled row per MMA
           tc_mma_tf32(tmem_main, make_smem_desc(a_hi + k * 32), make_smem_desc(b_hi + k * 32), idesc, k > 0 ? 1u : 0u);
         tc_commit(&main_full[b]);              // this k-block's A_hi.B_hi partial tile is complete
+        if (!(e.debug & 4))
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {
           tc_mma_tf32(tmem_corr, make_smem_desc(a_lo + k * 32), make_smem_desc(b_hi + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
@@ -212,6 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
       const uint32_t bph = (kb >> 1) & 1;
       mbar_wait(&main_full[b], bph);
       tc_fence_after();
+      if (!(e.debug & 2))
 #pragma unroll
       for (int c = 0; c < BN; c += 32) {
         float v[32];
@@ -225,42 +229,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
     }
     mbar_wait(corr_full, 0);
     tc_fence_after();
-    const int m = m0 + lg * 32 + lane;
-    const bool row_ok = m < e.M;
-    const bool vec_ok = ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0);
+    // Phase 1: (main + correction) -> shared staging tile [128][BN+4].  The mainloop stages are free now: every MMA
+    // has completed (corr_full) and every TMA load was consumed.  One accumulator row per thread.
+    float* cs = reinterpret_cast<float*>(smem);
+    constexpr int CS_LD = BN + 4;
+    {
+      float* crow_s = cs + (lg * 32 + lane) * CS_LD;
 #pragma unroll
-    for (int c = 0; c < BN; c += 32) {
-      float v[32];
-      tc_ld_32x32(tmem_corr + lane_off + (uint32_t)c, v);
-      const int nb = n0 + c;
-      if (row_ok && nb < e.N) {
-        float* crow = e.C + (int64_t)m * e.ldc + nb;
-        const int nvalid = min(32, e.N - nb);
+      for (int c = 0; c < BN; c += 32) {
+        float v[32];
+        tc_ld_32x32(tmem_corr + lane_off + (uint32_t)c, v);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = e.alpha * (acc[c + j] + v[j]);
-          if (j < nvalid) {
-            if (e.accumulate) {
-              if (e.bias && blockIdx.z == 0) x += e.bias[nb + j];
-            } else {
-              if (e.bias) x += e.bias[nb + j];
-              if (e.act == 1) x = fmaxf(x, 0.0f);
-              else if (e.act == 2) x = tanhf(x);
-              if (e.mask_mode == 1) x = (e.mask_src[(int64_t)m * e.ldm + nb + j] > 0.0f) ? x : 0.0f;
-              else if (e.mask_mode == 2) { const float sv = e.mask_src[(int64_t)m * e.ldm + nb + j]; x *= (1.0f - sv * sv); }
-            }
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(crow_s + c + j) = make_float4(e.alpha * (acc[c + j] + v[j]), e.alpha * (acc[c + j + 1] + v[j + 1]),
+                                                                   e.alpha * (acc[c + j + 2] + v[j + 2]), e.alpha * (acc[c + j + 3] + v[j + 3]));
+      }
+    }
+    asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 epilogue warps only
+    // Phase 2: coalesced epilogue -- warp w owns rows [32w, 32w+32); a row is written as BN/4 float4 by consecutive lanes
+    // (full 128-byte lines); bias / activation / mask operands are read with the same coalesced mapping.
+    if (!(e.debug & 1)) {
+      const bool vec_ok = ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0) &&
+                          (!e.mask_mode || (((e.ldm & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.mask_src) & 15) == 0)));
+      const bool add_bias = e.bias && (!e.accumulate || blockIdx.z == 0);
+#pragma unroll 1
+      for (int cc = lane * 4; cc < BN; cc += 128) {
+        const int n = n0 + cc;
+        if (n >= e.N) break;
+        const int nvalid = min(4, e.N - n);
+        float bv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (add_bias) for (int j = 0; j < nvalid; ++j) bv[j] = e.bias[n + j];
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          const int row = lg * 32 + r, m = m0 + row;
+          if (m >= e.M) break;
+          const float4 t = *reinterpret_cast<const float4*>(cs + row * CS_LD + cc);
+          float x[4] = {t.x + bv[0], t.y + bv[1], t.z + bv[2], t.w + bv[3]};
+          float* cp = e.C + (int64_t)m * e.ldc + n;
+          if (e.accumulate) {
+            for (int j = 0; j < nvalid; ++j) atomicAdd(cp + j, x[j]);
+            continue;
           }
-          v[j] = x;
-        }
-        if (e.accumulate) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (j < nvalid) atomicAdd(crow + j, v[j]);
-        } else if (vec_ok && nvalid == 32) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(crow + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) if (j < nvalid) crow[j] = v[j];
+          if (e.act == 1) { for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.0f); }
+          else if (e.act == 2) { for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]); }
+          if (e.mask_mode) {
+            const float* mp = e.mask_src + (int64_t)m * e.ldm + n;
+            float mv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (vec_ok && nvalid == 4) { const float4 q = *reinterpret_cast<const float4*>(mp); mv[0] = q.x; mv[1] = q.y; mv[2] = q.z; mv[3] = q.w; }
+            else for (int j = 0; j < nvalid; ++j) mv[j] = mp[j];
+            if (e.mask_mode == 1) { for (int j = 0; j < 4; ++j) x[j] = (mv[j] > 0.0f) ? x[j] : 0.0f; }
+            else { for (int j = 0; j < 4; ++j) x[j] *= (1.0f - mv[j] * mv[j]); }
+          }
+          if (vec_ok && nvalid == 4) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+          else for (int j = 0; j < nvalid; ++j) cp[j] = x[j];
         }
       }
     }
@@ -440,6 +461,7 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st) {
   e.C = p.C; e.ldc = p.ldc; e.M = p.M; e.N = p.N; e.alpha = p.alpha; e.bias = p.bias; e.act = p.act;
   e.mask_src = p.mask_src; e.ldm = p.ldm; e.mask_mode = p.mask_src ? p.mask_mode : 0; e.accumulate = p.accumulate;
   e.kb_total = Kp / TC_BK;
+  { static int dbg = -1; if (dbg < 0) { const char* d = getenv("ASE_TC_DEBUG"); dbg = d ? atoi(d) : 0; } e.debug = dbg; }
   int splits = (p.accumulate && p.split_k > 1) ? p.split_k : 1;
   splits = min(splits, e.kb_total);
   e.kb_per_split = ceil_div(e.kb_total, splits);
