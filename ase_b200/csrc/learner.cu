@@ -206,10 +206,16 @@ struct G {
     AseGemmParams p = base();
     p.A = dZ; p.lda = ldz; p.a_trans = 1; p.B = X; p.ldb = ldx; p.b_trans = 1; p.C = GR + l.w; p.ldc = l.in;
     p.M = l.out; p.N = l.in; p.K = M; p.accumulate = 1;
+    // split-K so that tiles x splits fills whole waves of the 148 SMs; every extra split adds one RED pass over dW
     const int tiles = ceil_div(l.out, 128) * ceil_div(l.in, 128);
-    int s = ceil_div(2 * 148, tiles);
-    s = min(s, max(1, M / 512));
-    p.split_k = max(1, s);
+    const int smax = max(1, min(16, M / 1024));
+    int best = 1; double best_cost = 1e30;
+    for (int s = 1; s <= smax; ++s) {
+      const double waves = (double)ceil_div((int64_t)tiles * s, 148);
+      const double cost = waves / s * (1.0 + 0.03 * s);
+      if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+    }
+    p.split_k = best;
     return gemm_dispatch(p, st);
   }
   int db(const float* dZ, int64_t ldz, int M, const Layer& l) const { return launch_colsum(dZ, ldz, M, l.out, GR + l.b, st); }
