@@ -89,9 +89,17 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
+// MN-major, 128-byte swizzle (operand stored with the M/N index contiguous, reduction index strided): the tile is
+// (BM or BN)/32 boxes of [32 k-rows x 32 mn] = 4 KB each, box b at +4096*b; inside a box an 8-row group (one K=8
+// MMA slice) is a 1024-byte swizzle atom.  LBO = byte distance between 32-wide MN blocks (4096), SBO = distance
+// between 8-row k groups (1024).  (cute/atom/mma_traits_sm100.hpp, "make_umma_desc<Major::MN>" canonical B128 layout.)
+__device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
 struct TcEpi {
   float* C; int64_t ldc;
-  int M, N;
+  int M, N, K;
   int kb_total, kb_per_split;
   float alpha;
   const float* bias;
@@ -120,7 +128,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // accumulator), double buffered; the epilogue warps drain each k-block's partial tile with tcgen05.ld and add it
 // into fp32 registers with round-to-nearest FADDs while the tensor core works on the next k-block.  The two
 // correction terms (2^-11 smaller) accumulate across all of K in a third TMEM tile: their truncation is negligible.
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool AMN, bool BMN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const TcEpi e) {
@@ -166,17 +174,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         mbar_expect_tx(&full[s], SM::STAGE_BYTES);
         uint8_t* st = smem + s * SM::STAGE_BYTES;
         const int k0 = (kb_begin + kb) * TC_BK;
-        tma_load_2d(st, &tmAhi, &full[s], k0, m0);
-        tma_load_2d(st + SM::A_BYTES, &tmAlo, &full[s], k0, m0);
-        tma_load_2d(st + 2 * SM::A_BYTES, &tmBhi, &full[s], k0, n0);
-        tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmBlo, &full[s], k0, n0);
+        if (!AMN) {          // K-major planes [rows, K]: one box of 128 rows x 32 k
+          tma_load_2d(st, &tmAhi, &full[s], k0, m0);
+          tma_load_2d(st + SM::A_BYTES, &tmAlo, &full[s], k0, m0);
+        } else {             // MN-major planes [K, rows]: 4 boxes of 32 k-rows x 32 m
+#pragma unroll
+          for (int b = 0; b < TC_BM / 32; ++b) {
+            tma_load_2d(st + b * 4096, &tmAhi, &full[s], m0 + b * 32, k0);
+            tma_load_2d(st + SM::A_BYTES + b * 4096, &tmAlo, &full[s], m0 + b * 32, k0);
+          }
+        }
+        if (!BMN) {
+          tma_load_2d(st + 2 * SM::A_BYTES, &tmBhi, &full[s], k0, n0);
+          tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmBlo, &full[s], k0, n0);
+        } else {
+#pragma unroll
+          for (int b = 0; b < BN / 32; ++b) {
+            tma_load_2d(st + 2 * SM::A_BYTES + b * 4096, &tmBhi, &full[s], n0 + b * 32, k0);
+            tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES + b * 4096, &tmBlo, &full[s], n0 + b * 32, k0);
+          }
+        }
       }
     }
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
       // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2), K-major A/B, N>>3 at 17, M>>4 at 24
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((AMN ? 1u : 0u) << 15) | ((BMN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      // per K=8 MMA slice: K-major operands advance 32 bytes along the swizzled row, MN-major ones one 1024-byte atom
+      auto adesc = [](uint32_t base, int k) { return AMN ? make_smem_desc_mn(base + k * 1024) : make_smem_desc(base + k * 32); };
+      auto bdesc = [](uint32_t base, int k) { return BMN ? make_smem_desc_mn(base + k * 1024) : make_smem_desc(base + k * 32); };
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -190,13 +218,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         const uint32_t tmem_main = tmem_base + (uint32_t)b * BN;
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k)     // 8 tf32 = 32 bytes along the swizzled row per MMA
-          tc_mma_tf32(tmem_main, make_smem_desc(a_hi + k * 32), make_smem_desc(b_hi + k * 32), idesc, k > 0 ? 1u : 0u);
+          tc_mma_tf32(tmem_main, adesc(a_hi, k), bdesc(b_hi, k), idesc, k > 0 ? 1u : 0u);
         tc_commit(&main_full[b]);              // this k-block's A_hi.B_hi partial tile is complete
         if (!(e.debug & 4))
 #pragma unroll
         for (int k = 0; k < TC_BK / 8; ++k) {
-          tc_mma_tf32(tmem_corr, make_smem_desc(a_lo + k * 32), make_smem_desc(b_hi + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          tc_mma_tf32(tmem_corr, make_smem_desc(a_hi + k * 32), make_smem_desc(b_lo + k * 32), idesc, 1u);
+          tc_mma_tf32(tmem_corr, adesc(a_lo, k), bdesc(b_hi, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_mma_tf32(tmem_corr, adesc(a_hi, k), bdesc(b_lo, k), idesc, 1u);
         }
         tc_commit(&empty[s]);                  // all 12 MMAs have read this smem stage
       }
@@ -303,36 +331,16 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   lo = __uint_as_float(l);
 }
 
-// source is K-major: src[r*ld + k]
+// split src[rows, cols] (ld) into zero-padded hi/lo planes [rows_p, cols_p]
 __global__ void __launch_bounds__(256)
-tc_prep_plain_kernel(const float* __restrict__ src, int64_t ld, int rows, int K, int Kp, float* __restrict__ hi, float* __restrict__ lo) {
-  const int64_t total = (int64_t)rows * Kp;
+tc_prep_kernel(const float* __restrict__ src, int64_t ld, int rows, int cols, int rows_p, int cols_p, float* __restrict__ hi,
+               float* __restrict__ lo) {
+  const int64_t total = (int64_t)rows_p * cols_p;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / Kp), k = (int)(i - (int64_t)r * Kp);
+    const int r = (int)(i / cols_p), c = (int)(i - (int64_t)r * cols_p);
     float h = 0.0f, l = 0.0f;
-    if (k < K) split_tf32(src[(int64_t)r * ld + k], h, l);
+    if (r < rows && c < cols) split_tf32(src[(int64_t)r * ld + c], h, l);
     hi[i] = h; lo[i] = l;
-  }
-}
-
-// source is MN-major: src[k*ld + r]  ->  dst[r*Kp + k]   (32x32 tiles through shared memory)
-__global__ void __launch_bounds__(256)
-tc_prep_transpose_kernel(const float* __restrict__ src, int64_t ld, int rows, int K, int Kp, float* __restrict__ hi, float* __restrict__ lo) {
-  __shared__ float tile[32][33];
-  const int r0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
-  for (int i = ty; i < 32; i += 8) {
-    const int k = k0 + i, r = r0 + tx;
-    tile[i][tx] = (k < K && r < rows) ? src[(int64_t)k * ld + r] : 0.0f;
-  }
-  __syncthreads();
-  for (int i = ty; i < 32; i += 8) {
-    const int r = r0 + i, k = k0 + tx;
-    if (r < rows && k < Kp) {
-      float h, l;
-      split_tf32(tile[tx][i], h, l);
-      hi[(int64_t)r * Kp + k] = h; lo[(int64_t)r * Kp + k] = l;
-    }
   }
 }
 
@@ -354,30 +362,32 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-static int make_map(CUtensorMap* tm, const float* base, int rows, int Kp, int box_rows) {
+// 2D tensor map over a zero-padded plane [rows_p, cols_p] (cols contiguous); box = [box_rows x 32 cols], 128B swizzle
+static int make_map(CUtensorMap* tm, const float* base, int rows_p, int cols_p, int box_rows) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return ASE_ERR_UNSUPPORTED; }
-  cuuint64_t gdim[2] = {(cuuint64_t)Kp, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)Kp * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint64_t gdim[2] = {(cuuint64_t)cols_p, (cuuint64_t)rows_p};
+  cuuint64_t gstr[1] = {(cuuint64_t)cols_p * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (rows %d, Kp %d)", (int)r, rows, Kp); return ASE_ERR_CUDA; }
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (plane %d x %d)", (int)r, rows_p, cols_p); return ASE_ERR_CUDA; }
   return ASE_OK;
 }
 
-static inline int kpad(int K) { return (K + TC_BK - 1) / TC_BK * TC_BK; }
+static inline int pad_to(int x, int m) { return (x + m - 1) / m * m; }
 
+// planes are padded to whole tiles in both dimensions (zero filled by the prep kernel): no reliance on TMA OOB fill
 int64_t gemm_tc_workspace_bytes(int M, int N, int K) {
-  const int64_t Kp = kpad(K);
-  return 2 * align_up((int64_t)M * Kp * 4, 1024) + 2 * align_up((int64_t)N * Kp * 4, 1024);
+  const int64_t Mp = pad_to(M, 128), Np = pad_to(N, 128), Kp = pad_to(K, TC_BK);
+  return 2 * align_up(Mp * Kp * 4, 1024) + 2 * align_up(Np * Kp * 4, 1024);
 }
 
-// shapes the tcgen05 kernel takes; everything else (tiny heads, K=1 outer products) goes to the SIMT kernel
-bool gemm_tc_supported(const AseGemmParams& p) { return p.M >= 128 && p.N >= 64 && p.K >= 32; }
+// every shape runs on the tensor cores (small heads are padded up to one tile)
+bool gemm_tc_supported(const AseGemmParams& p) { return p.M >= 1 && p.N >= 1 && p.K >= 1; }
 
-// a qualifying shape with a missing / small / misaligned workspace is an ERROR, never a silent fallback
+// a missing / small / misaligned workspace is an ERROR, never a silent fallback
 int gemm_tc_check_workspace(const AseGemmParams& p) {
   if (!p.workspace || p.workspace_bytes < gemm_tc_workspace_bytes(p.M, p.N, p.K)) {
     set_error("tcgen05 GEMM %dx%dx%d: workspace %lld bytes < required %lld", p.M, p.N, p.K, (long long)p.workspace_bytes,
@@ -388,14 +398,13 @@ int gemm_tc_check_workspace(const AseGemmParams& p) {
   return ASE_OK;
 }
 
-static int prep_operand(const float* src, int64_t ld, int trans, int rows, int K, int Kp, float* hi, float* lo, cudaStream_t st) {
-  if (!trans) {
-    const int64_t total = (int64_t)rows * Kp;
-    tc_prep_plain_kernel<<<(int)imin64((total + 255) / 256, 148 * 16), 256, 0, st>>>(src, ld, rows, K, Kp, hi, lo);
-  } else {
-    dim3 grid(ceil_div(rows, 32), Kp / 32);
-    tc_prep_transpose_kernel<<<grid, 256, 0, st>>>(src, ld, rows, K, Kp, hi, lo);
-  }
+// operand with `rows` = its M/N extent and reduction length K.  trans == 0: stored [rows, K] (K-major planes
+// [rows_p, Kp]); trans == 1: stored [K, rows] (MN-major planes [Kp, rows_p]) -- no transposition anywhere.
+static int prep_operand(const float* src, int64_t ld, int trans, int rows, int K, int rows_p, int Kp, float* hi, float* lo, cudaStream_t st) {
+  const int pr = trans ? Kp : rows_p, pc = trans ? rows_p : Kp;
+  const int sr = trans ? K : rows, sc = trans ? rows : K;
+  const int64_t total = (int64_t)pr * pc;
+  tc_prep_kernel<<<(int)imin64((total + 255) / 256, 148 * 16), 256, 0, st>>>(src, ld, sr, sc, pr, pc, hi, lo);
   ASE_LAUNCH_OK();
   return ASE_OK;
 }
@@ -419,46 +428,55 @@ static void prof_mark(cudaStream_t st) {
   cudaEventRecord(g_prof.ev[g_prof.used++], st);
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool AMN, bool BMN>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcEpi& e,
                      int splits, cudaStream_t st) {
   using SM = TcSmem<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    ASE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    ASE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr_set = true;
   }
   dim3 grid(ceil_div(e.N, BN), ceil_div(e.M, TC_BM), splits);
   const bool prof = g_prof.on;
   if (prof) prof_mark(st);
-  gemm_tc_kernel<BN, STAGES><<<grid, TC_THREADS, SM::TOTAL, st>>>(ah, al, bh, bl, e);
-  if (prof) { prof_mark(st); g_prof.flops += 2.0 * (double)e.M * (double)e.N * (double)e.kb_total * TC_BK; }
+  gemm_tc_kernel<BN, STAGES, AMN, BMN><<<grid, TC_THREADS, SM::TOTAL, st>>>(ah, al, bh, bl, e);
+  if (prof) { prof_mark(st); g_prof.flops += 2.0 * (double)e.M * (double)e.N * (double)e.K; }
   ASE_LAUNCH_OK();
   return ASE_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_tc_major(bool amn, bool bmn, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                           const TcEpi& e, int splits, cudaStream_t st) {
+  if (!amn && !bmn) return launch_tc<BN, STAGES, false, false>(ah, al, bh, bl, e, splits, st);
+  if (!amn && bmn) return launch_tc<BN, STAGES, false, true>(ah, al, bh, bl, e, splits, st);
+  if (amn && !bmn) return launch_tc<BN, STAGES, true, false>(ah, al, bh, bl, e, splits, st);
+  return launch_tc<BN, STAGES, true, true>(ah, al, bh, bl, e, splits, st);
 }
 
 int gemm_tc(const AseGemmParams& p, cudaStream_t st) {
   int wrc = gemm_tc_check_workspace(p);
   if (wrc) return wrc;
-  const int Kp = kpad(p.K);
+  const int BN = (p.N > 64) ? 128 : 64;
+  const int Mp = pad_to(p.M, 128), Np = pad_to(p.N, 128), Kp = pad_to(p.K, TC_BK);
   char* ws = (char*)p.workspace;
-  float* Ahi = (float*)ws; ws += align_up((int64_t)p.M * Kp * 4, 1024);
-  float* Alo = (float*)ws; ws += align_up((int64_t)p.M * Kp * 4, 1024);
-  float* Bhi = (float*)ws; ws += align_up((int64_t)p.N * Kp * 4, 1024);
+  float* Ahi = (float*)ws; ws += align_up((int64_t)Mp * Kp * 4, 1024);
+  float* Alo = (float*)ws; ws += align_up((int64_t)Mp * Kp * 4, 1024);
+  float* Bhi = (float*)ws; ws += align_up((int64_t)Np * Kp * 4, 1024);
   float* Blo = (float*)ws;
-  // A operand: K-major already when a_trans == 0 ([M,K]); B operand: K-major when b_trans == 0 ([N,K])
-  int rc = prep_operand(p.A, p.lda, p.a_trans, p.M, p.K, Kp, Ahi, Alo, st);
+  int rc = prep_operand(p.A, p.lda, p.a_trans, p.M, p.K, Mp, Kp, Ahi, Alo, st);
   if (rc) return rc;
-  rc = prep_operand(p.B, p.ldb, p.b_trans, p.N, p.K, Kp, Bhi, Blo, st);
+  rc = prep_operand(p.B, p.ldb, p.b_trans, p.N, p.K, Np, Kp, Bhi, Blo, st);
   if (rc) return rc;
-  const int BN = (p.N >= 128) ? 128 : 64;
   CUtensorMap ah, al, bh, bl;
-  if ((rc = make_map(&ah, Ahi, p.M, Kp, TC_BM))) return rc;
-  if ((rc = make_map(&al, Alo, p.M, Kp, TC_BM))) return rc;
-  if ((rc = make_map(&bh, Bhi, p.N, Kp, BN))) return rc;
-  if ((rc = make_map(&bl, Blo, p.N, Kp, BN))) return rc;
+  // K-major plane [rows_p, Kp]: box = tile rows x 32 k;  MN-major plane [Kp, rows_p]: box = 32 k-rows x 32 mn
+  if (!p.a_trans) { if ((rc = make_map(&ah, Ahi, Mp, Kp, TC_BM)) || (rc = make_map(&al, Alo, Mp, Kp, TC_BM))) return rc; }
+  else            { if ((rc = make_map(&ah, Ahi, Kp, Mp, 32)) || (rc = make_map(&al, Alo, Kp, Mp, 32))) return rc; }
+  if (!p.b_trans) { if ((rc = make_map(&bh, Bhi, Np, Kp, BN)) || (rc = make_map(&bl, Blo, Np, Kp, BN))) return rc; }
+  else            { if ((rc = make_map(&bh, Bhi, Kp, Np, 32)) || (rc = make_map(&bl, Blo, Kp, Np, 32))) return rc; }
   TcEpi e;
-  e.C = p.C; e.ldc = p.ldc; e.M = p.M; e.N = p.N; e.alpha = p.alpha; e.bias = p.bias; e.act = p.act;
+  e.C = p.C; e.ldc = p.ldc; e.M = p.M; e.N = p.N; e.K = p.K; e.alpha = p.alpha; e.bias = p.bias; e.act = p.act;
   e.mask_src = p.mask_src; e.ldm = p.ldm; e.mask_mode = p.mask_src ? p.mask_mode : 0; e.accumulate = p.accumulate;
   e.kb_total = Kp / TC_BK;
   { static int dbg = -1; if (dbg < 0) { const char* d = getenv("ASE_TC_DEBUG"); dbg = d ? atoi(d) : 0; } e.debug = dbg; }
@@ -466,8 +484,8 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st) {
   splits = min(splits, e.kb_total);
   e.kb_per_split = ceil_div(e.kb_total, splits);
   splits = ceil_div(e.kb_total, e.kb_per_split);
-  if (BN == 128) return launch_tc<128, 3>(ah, al, bh, bl, e, splits, st);
-  return launch_tc<64, 4>(ah, al, bh, bl, e, splits, st);
+  if (BN == 128) return launch_tc_major<128, 3>(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
+  return launch_tc_major<64, 4>(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
 }
 
 }  // namespace ase

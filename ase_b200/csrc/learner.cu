@@ -108,6 +108,7 @@ static int64_t tc_ws_need(const AseLearner& L) {
   int in = L.in0;
   for (int k = 0; k < c.n_units; ++k) { upd(L.Ra, c.units[k], in); upd(L.Ra, in, c.units[k]); upd(c.units[k], in, L.Ra); in = c.units[k]; }
   upd(L.Ra, c.act_dim, in); upd(L.Ra, in, c.act_dim); upd(c.act_dim, in, L.Ra);
+  upd(L.B, 1, in); upd(L.B, in, 1); upd(1, in, L.B);
   if (L.ase) {
     in = c.latent_dim;
     for (int k = 0; k < c.n_style_units; ++k) { upd(L.Ra, c.style_units[k], in); upd(L.Ra, in, c.style_units[k]); upd(c.style_units[k], in, L.Ra); in = c.style_units[k]; }
@@ -116,7 +117,8 @@ static int64_t tc_ws_need(const AseLearner& L) {
   if (L.amp) {
     in = c.amp_dim;
     for (int k = 0; k < c.n_disc_units; ++k) { upd(3 * L.Ba, c.disc_units[k], in); upd(3 * L.Ba, in, c.disc_units[k]); upd(c.disc_units[k], in, 3 * L.Ba); in = c.disc_units[k]; }
-    upd(3 * L.Ba, c.latent_dim > 0 ? c.latent_dim : 1, in);
+    upd(3 * L.Ba, c.latent_dim > 0 ? c.latent_dim : 1, in); upd(3 * L.Ba, in, c.latent_dim > 0 ? c.latent_dim : 1);
+    upd(c.latent_dim > 0 ? c.latent_dim : 1, in, 3 * L.Ba); upd(L.Ba, c.amp_dim, c.disc_units[0]); upd(c.disc_units[0], c.amp_dim, L.Ba);
   }
   return need;
 }

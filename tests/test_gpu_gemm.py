@@ -72,15 +72,21 @@ def test_simt_learner_shapes():
     _run(1024, 317, 2048, True, True, 0, accumulate=True, split_k=4, tol=2e-5)
 
 
-@pytest.mark.parametrize('a_trans,b_trans', [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize('a_trans,b_trans', [(False, False), (False, True), (True, False), (True, True)])
 def test_tc_matches_fp64(a_trans, b_trans):
-    _run(256, 256, 64, a_trans, b_trans, 1, tol=2e-5)
-    _run(384, 192, 317, a_trans, b_trans, 1, lda_pad=3, tol=2e-5)     # ragged K (zero padded to 320), N tail with BN=128
-    _run(1000, 100, 96, a_trans, b_trans, 1, tol=2e-5)                # BN = 64 path, ragged M and N
+    # a_trans / b_trans operands are consumed MN-major by the tensor core (no transposition pass)
+    _run(256, 256, 64, a_trans, b_trans, 1, tol=1e-5)
+    _run(384, 192, 317, a_trans, b_trans, 1, lda_pad=3, tol=1e-5)     # ragged K (zero padded to 320), N tail with BN=128
+    _run(1000, 100, 96, a_trans, b_trans, 1, tol=1e-5)                # ragged M and N
+    _run(200, 40, 50, a_trans, b_trans, 1, tol=1e-5)                  # BN = 64 path
+    _run(31, 512, 700, a_trans, b_trans, 1, tol=1e-5)                 # M smaller than one tile (mu-head weight gradient)
+    _run(300, 1, 512, a_trans, b_trans, 1, tol=1e-5)                  # N = 1 (value / logit heads)
+    _run(512, 96, 1, a_trans, b_trans, 1, tol=1e-5)                   # K = 1 outer product
+    _run(1, 1, 1, a_trans, b_trans, 1, tol=1e-5)
 
 
 def test_tc_epilogues_and_split_k():
-    _run(512, 256, 512, False, False, 1, bias=True, act=1, tol=2e-5)
+    _run(512, 256, 512, False, False, 1, bias=True, act=1, tol=1e-5)
     _run(256, 128, 256, False, False, 1, bias=True, act=2, alpha=1.0 / 16, tol=3e-5)   # O(1) pre-activations
     _run(512, 320, 256, False, True, 1, mask_mode=1, tol=2e-5)
     _run(256, 64, 128, False, True, 1, mask_mode=2, tol=2e-5)
