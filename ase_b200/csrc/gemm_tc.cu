@@ -89,12 +89,15 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-// MN-major, 128-byte swizzle (operand stored with the M/N index contiguous, reduction index strided): the tile is
-// (BM or BN)/32 boxes of [32 k-rows x 32 mn] = 4 KB each, box b at +4096*b; inside a box an 8-row group (one K=8
-// MMA slice) is a 1024-byte swizzle atom.  LBO = byte distance between 32-wide MN blocks (4096), SBO = distance
-// between 8-row k groups (1024).  (cute/atom/mma_traits_sm100.hpp, "make_umma_desc<Major::MN>" canonical B128 layout.)
+// MN-major (operand stored with the M/N index contiguous, reduction index strided).  For 32-bit operands the only
+// MN-major layout the tensor core accepts is "128B swizzle with a 32-byte atom" (layout type 1, Swizzle<2,5,2>:
+// 32-byte chunks XORed with the row index mod 4; TMA mode CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B) -- see
+// cutlass/gemm/collective/builders/sm100_common.inl "for mn-major tf32 operands, SW128_32B is the only available smem
+// layout".  The tile is (BM or BN)/32 boxes of [32 k-rows x 32 mn] = 4 KB each, box b at +4096*b; a K=8 MMA slice is
+// 8 rows = two 4-row swizzle groups.  LBO = byte distance between 32-wide MN blocks (4096), SBO = distance between
+// 4-row k groups (512).
 __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
 }
 
 struct TcEpi {
@@ -363,7 +366,7 @@ static PFN_encodeTiled get_encode() {
 }
 
 // 2D tensor map over a zero-padded plane [rows_p, cols_p] (cols contiguous); box = [box_rows x 32 cols], 128B swizzle
-static int make_map(CUtensorMap* tm, const float* base, int rows_p, int cols_p, int box_rows) {
+static int make_map(CUtensorMap* tm, const float* base, int rows_p, int cols_p, int box_rows, bool mn_major = false) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return ASE_ERR_UNSUPPORTED; }
   cuuint64_t gdim[2] = {(cuuint64_t)cols_p, (cuuint64_t)rows_p};
@@ -371,7 +374,8 @@ static int make_map(CUtensorMap* tm, const float* base, int rows_p, int cols_p, 
   cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (plane %d x %d)", (int)r, rows_p, cols_p); return ASE_ERR_CUDA; }
   return ASE_OK;
 }
@@ -472,9 +476,9 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st) {
   CUtensorMap ah, al, bh, bl;
   // K-major plane [rows_p, Kp]: box = tile rows x 32 k;  MN-major plane [Kp, rows_p]: box = 32 k-rows x 32 mn
   if (!p.a_trans) { if ((rc = make_map(&ah, Ahi, Mp, Kp, TC_BM)) || (rc = make_map(&al, Alo, Mp, Kp, TC_BM))) return rc; }
-  else            { if ((rc = make_map(&ah, Ahi, Kp, Mp, 32)) || (rc = make_map(&al, Alo, Kp, Mp, 32))) return rc; }
+  else            { if ((rc = make_map(&ah, Ahi, Kp, Mp, 32, true)) || (rc = make_map(&al, Alo, Kp, Mp, 32, true))) return rc; }
   if (!p.b_trans) { if ((rc = make_map(&bh, Bhi, Np, Kp, BN)) || (rc = make_map(&bl, Blo, Np, Kp, BN))) return rc; }
-  else            { if ((rc = make_map(&bh, Bhi, Kp, Np, 32)) || (rc = make_map(&bl, Blo, Kp, Np, 32))) return rc; }
+  else            { if ((rc = make_map(&bh, Bhi, Kp, Np, 32, true)) || (rc = make_map(&bl, Blo, Kp, Np, 32, true))) return rc; }
   TcEpi e;
   e.C = p.C; e.ldc = p.ldc; e.M = p.M; e.N = p.N; e.K = p.K; e.alpha = p.alpha; e.bias = p.bias; e.act = p.act;
   e.mask_src = p.mask_src; e.ldm = p.ldm; e.mask_mode = p.mask_src ? p.mask_mode : 0; e.accumulate = p.accumulate;
