@@ -175,6 +175,7 @@ class CommonAgent:
         self.frame = w.get('frame', 0)
         if 'optimizer' in w:
             self._load_optimizer_state_dict(w['optimizer'])
+        self.model.params_changed()
 
     def _optimizer_state_dict(self):
         """torch.optim.Adam.state_dict() layout: param index 0 is the frozen sigma (no state), 1.. follow parameters()."""
@@ -402,6 +403,7 @@ class CommonAgent:
         if self.multi_gpu:
             from .dist_utils import broadcast_state
             broadcast_state([self.model.params, self.model.exp_avg, self.model.exp_avg_sq])
+            self.model.params_changed()
         self._init_train()
         total_time = 0.0
         while True:

@@ -25,10 +25,10 @@ static int check_gemm(const AseGemmParams& p) {
   return ASE_OK;
 }
 
-int gemm_dispatch(const AseGemmParams& p, cudaStream_t st) {
+int gemm_dispatch(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   int rc = check_gemm(p);
   if (rc) return rc;
-  if (p.backend == 1 && gemm_tc_supported(p)) return gemm_tc(p, st);
+  if (p.backend == 1 && gemm_tc_supported(p)) return gemm_tc(p, st, reg);
   return gemm_simt(p, st);
 }
 

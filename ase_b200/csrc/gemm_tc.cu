@@ -100,6 +100,15 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
 }
 
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  const float r = x - hi;                       // exact
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
+  lo = __uint_as_float(l);
+}
+
 struct TcEpi {
   float* C; int64_t ldc;
   int M, N, K;
@@ -109,6 +118,7 @@ struct TcEpi {
   int act;
   const float* mask_src; int64_t ldm; int mask_mode;
   int accumulate;
+  float* Chi; float* Clo; int64_t ldp;     // optional TF32 hi/lo planes of C (operand cache for the consumers of C)
   int debug;   // experiments only (env ASE_TC_DEBUG): 1 skip global stores, 2 skip TMEM drain loads, 4 skip correction MMAs, 8 skip bias/act
 };
 
@@ -313,6 +323,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
           }
           if (vec_ok && nvalid == 4) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
           else for (int j = 0; j < nvalid; ++j) cp[j] = x[j];
+          if (e.Chi) {       // the consumers of C read these planes directly through TMA: no separate split pass
+            float h[4], l[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split_tf32(x[j], h[j], l[j]);
+            float* hp = e.Chi + (int64_t)m * e.ldp + n; float* lp = e.Clo + (int64_t)m * e.ldp + n;
+            if (nvalid == 4) { *reinterpret_cast<float4*>(hp) = make_float4(h[0], h[1], h[2], h[3]); *reinterpret_cast<float4*>(lp) = make_float4(l[0], l[1], l[2], l[3]); }
+            else for (int j = 0; j < nvalid; ++j) { hp[j] = h[j]; lp[j] = l[j]; }
+          }
         }
       }
     }
@@ -325,14 +343,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------ operand prep
-__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  uint32_t h, l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  const float r = x - hi;                       // exact
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
-  lo = __uint_as_float(l);
-}
 
 // split src[rows, cols] (ld) into zero-padded hi/lo planes [rows_p, cols_p]
 __global__ void __launch_bounds__(256)
@@ -459,29 +469,121 @@ static int launch_tc_major(bool amn, bool bmn, const CUtensorMap& ah, const CUte
   return launch_tc<BN, STAGES, true, true>(ah, al, bh, bl, e, splits, st);
 }
 
-int gemm_tc(const AseGemmParams& p, cudaStream_t st) {
-  int wrc = gemm_tc_check_workspace(p);
-  if (wrc) return wrc;
+// ---------------------------------------------------------------------------------------------------------
+// Operand-plane registry: fp32 buffers whose TF32 hi/lo planes are kept next to them so that a tensor is split at
+// most once (by the epilogue of the GEMM that produced it, or by one prep pass on first use) no matter how many
+// GEMMs consume it, in either major-ness.  Host-side bookkeeping in stream-issue order (single stream).
+// ---------------------------------------------------------------------------------------------------------
+PlaneBuf* PlaneRegistry::find(const float* p) {
+  for (int i = 0; i < n; ++i)
+    if (p >= b[i].base && p < b[i].base + b[i].capacity) return &b[i];
+  return nullptr;
+}
+void PlaneRegistry::add(const float* base, int64_t capacity, float* hi, float* lo, int64_t plane_capacity) {
+  if (n >= MAX) return;
+  PlaneBuf& x = b[n++];
+  x.base = base; x.capacity = capacity; x.hi = hi; x.lo = lo; x.plane_capacity = plane_capacity;
+  x.ld = 0; x.rows = x.cols = 0; x.ldp = 0; x.valid = false;
+}
+void PlaneRegistry::invalidate(const float* p) { if (PlaneBuf* x = find(p)) x->valid = false; }
+void PlaneRegistry::invalidate_range(const float* lo_, const float* hi_) {
+  for (int i = 0; i < n; ++i) if (b[i].base >= lo_ && b[i].base < hi_) b[i].valid = false;
+}
+
+struct OpView { const float* hi; const float* lo; int64_t ldp; bool ok; };
+
+// View [nat_rows, nat_cols] (ld) at `ptr` as planes.  Geometry of a registered buffer is whatever its last full
+// writer declared; a first read of a buffer without valid planes splits the WHOLE declared buffer once.
+static int resolve_operand(PlaneRegistry* reg, const float* ptr, int64_t ld, int nat_rows, int nat_cols, OpView* v, cudaStream_t st) {
+  v->ok = false;
+  if (!reg) return ASE_OK;
+  PlaneBuf* x = reg->find(ptr);
+  if (!x) return ASE_OK;
+  if (!x->valid) {
+    // adopt the reader's geometry if it starts at the buffer base (inputs written by non-GEMM kernels, weights)
+    if (ptr != x->base) return ASE_OK;
+    const int64_t ldp = pad_to(nat_cols, 4);
+    if ((int64_t)nat_rows * ldp > x->plane_capacity || (int64_t)(nat_rows - 1) * ld + nat_cols > x->capacity) return ASE_OK;
+    x->ld = ld; x->rows = nat_rows; x->cols = nat_cols; x->ldp = ldp;
+    const int64_t total = (int64_t)nat_rows * ldp;
+    tc_prep_kernel<<<(int)imin64((total + 255) / 256, 148 * 16), 256, 0, st>>>(ptr, ld, nat_rows, nat_cols, nat_rows, (int)ldp, x->hi, x->lo);
+    ASE_LAUNCH_OK();
+    x->valid = true;
+  }
+  if (ld != x->ld) return ASE_OK;
+  const int64_t off = ptr - x->base;
+  const int64_t r0 = off / x->ld, c0 = off - r0 * x->ld;
+  if ((c0 & 3) || r0 + nat_rows > x->rows || c0 + nat_cols > x->cols) return ASE_OK;
+  v->hi = x->hi + r0 * x->ldp + c0; v->lo = x->lo + r0 * x->ldp + c0; v->ldp = x->ldp; v->ok = true;
+  return ASE_OK;
+}
+
+// tensor map over a (sub-)view of a plane with TRUE extents: TMA zero-fills everything outside [rows, cols]
+static int make_view_map(CUtensorMap* tm, const float* base, int rows, int cols, int64_t ldp, int box_rows, bool mn_major) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return ASE_ERR_UNSUPPORTED; }
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ldp * sizeof(float)};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(view %d x %d, ld %lld) failed with CUresult %d", rows, cols, (long long)ldp, (int)r); return ASE_ERR_CUDA; }
+  return ASE_OK;
+}
+
+int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   const int BN = (p.N > 64) ? 128 : 64;
   const int Mp = pad_to(p.M, 128), Np = pad_to(p.N, 128), Kp = pad_to(p.K, TC_BK);
-  char* ws = (char*)p.workspace;
-  float* Ahi = (float*)ws; ws += align_up((int64_t)Mp * Kp * 4, 1024);
-  float* Alo = (float*)ws; ws += align_up((int64_t)Mp * Kp * 4, 1024);
-  float* Bhi = (float*)ws; ws += align_up((int64_t)Np * Kp * 4, 1024);
-  float* Blo = (float*)ws;
-  int rc = prep_operand(p.A, p.lda, p.a_trans, p.M, p.K, Mp, Kp, Ahi, Alo, st);
-  if (rc) return rc;
-  rc = prep_operand(p.B, p.ldb, p.b_trans, p.N, p.K, Np, Kp, Bhi, Blo, st);
-  if (rc) return rc;
+  int rc;
+  // ---- operands: cached planes when the buffer is registered, else a split pass into the shared workspace
+  OpView va, vb;
+  const int a_rows = p.a_trans ? p.K : p.M, a_cols = p.a_trans ? p.M : p.K;
+  const int b_rows = p.b_trans ? p.K : p.N, b_cols = p.b_trans ? p.N : p.K;
+  if ((rc = resolve_operand(reg, p.A, p.lda, a_rows, a_cols, &va, st))) return rc;
+  if ((rc = resolve_operand(reg, p.B, p.ldb, b_rows, b_cols, &vb, st))) return rc;
   CUtensorMap ah, al, bh, bl;
-  // K-major plane [rows_p, Kp]: box = tile rows x 32 k;  MN-major plane [Kp, rows_p]: box = 32 k-rows x 32 mn
-  if (!p.a_trans) { if ((rc = make_map(&ah, Ahi, Mp, Kp, TC_BM)) || (rc = make_map(&al, Alo, Mp, Kp, TC_BM))) return rc; }
-  else            { if ((rc = make_map(&ah, Ahi, Kp, Mp, 32, true)) || (rc = make_map(&al, Alo, Kp, Mp, 32, true))) return rc; }
-  if (!p.b_trans) { if ((rc = make_map(&bh, Bhi, Np, Kp, BN)) || (rc = make_map(&bl, Blo, Np, Kp, BN))) return rc; }
-  else            { if ((rc = make_map(&bh, Bhi, Kp, Np, 32, true)) || (rc = make_map(&bl, Blo, Kp, Np, 32, true))) return rc; }
+  char* ws = (char*)p.workspace;
+  if (!va.ok || !vb.ok) { if ((rc = gemm_tc_check_workspace(p))) return rc; }
+  if (va.ok) {
+    if ((rc = make_view_map(&ah, va.hi, a_rows, a_cols, va.ldp, p.a_trans ? 32 : TC_BM, p.a_trans != 0)) ||
+        (rc = make_view_map(&al, va.lo, a_rows, a_cols, va.ldp, p.a_trans ? 32 : TC_BM, p.a_trans != 0))) return rc;
+  } else {
+    float* Ahi = (float*)ws; float* Alo = (float*)(ws + align_up((int64_t)Mp * Kp * 4, 1024));
+    if ((rc = prep_operand(p.A, p.lda, p.a_trans, p.M, p.K, Mp, Kp, Ahi, Alo, st))) return rc;
+    if (!p.a_trans) { if ((rc = make_map(&ah, Ahi, Mp, Kp, TC_BM)) || (rc = make_map(&al, Alo, Mp, Kp, TC_BM))) return rc; }
+    else            { if ((rc = make_map(&ah, Ahi, Kp, Mp, 32, true)) || (rc = make_map(&al, Alo, Kp, Mp, 32, true))) return rc; }
+  }
+  if (vb.ok) {
+    if ((rc = make_view_map(&bh, vb.hi, b_rows, b_cols, vb.ldp, p.b_trans ? 32 : BN, p.b_trans != 0)) ||
+        (rc = make_view_map(&bl, vb.lo, b_rows, b_cols, vb.ldp, p.b_trans ? 32 : BN, p.b_trans != 0))) return rc;
+  } else {
+    char* wb = ws + 2 * align_up((int64_t)Mp * Kp * 4, 1024);
+    float* Bhi = (float*)wb; float* Blo = (float*)(wb + align_up((int64_t)Np * Kp * 4, 1024));
+    if ((rc = prep_operand(p.B, p.ldb, p.b_trans, p.N, p.K, Np, Kp, Bhi, Blo, st))) return rc;
+    if (!p.b_trans) { if ((rc = make_map(&bh, Bhi, Np, Kp, BN)) || (rc = make_map(&bl, Blo, Np, Kp, BN))) return rc; }
+    else            { if ((rc = make_map(&bh, Bhi, Kp, Np, 32, true)) || (rc = make_map(&bl, Blo, Kp, Np, 32, true))) return rc; }
+  }
   TcEpi e;
   e.C = p.C; e.ldc = p.ldc; e.M = p.M; e.N = p.N; e.K = p.K; e.alpha = p.alpha; e.bias = p.bias; e.act = p.act;
   e.mask_src = p.mask_src; e.ldm = p.ldm; e.mask_mode = p.mask_src ? p.mask_mode : 0; e.accumulate = p.accumulate;
+  e.Chi = e.Clo = nullptr; e.ldp = 0;
+  // ---- output planes: a full write at the base of a registered buffer (re)declares its geometry; a partial write
+  // keeps planes in sync only if they are currently valid with the same leading dimension; accumulation invalidates
+  if (reg) {
+    if (PlaneBuf* x = reg->find(p.C)) {
+      if (p.accumulate) x->valid = false;
+      else if (p.C == x->base && (int64_t)p.M * pad_to(p.N, 4) <= x->plane_capacity && !(x->valid && x->ld == p.ldc && (x->rows > p.M || x->cols > p.N))) {
+        x->ld = p.ldc; x->rows = p.M; x->cols = p.N; x->ldp = pad_to(p.N, 4); x->valid = true;
+        e.Chi = x->hi; e.Clo = x->lo; e.ldp = x->ldp;
+      } else if (x->valid && x->ld == p.ldc) {
+        const int64_t off = p.C - x->base, r0 = off / x->ld, c0 = off - r0 * x->ld;
+        if (!(c0 & 3) && r0 + p.M <= x->rows && c0 + p.N <= x->cols) { e.Chi = x->hi + r0 * x->ldp + c0; e.Clo = x->lo + r0 * x->ldp + c0; e.ldp = x->ldp; }
+        else x->valid = false;
+      } else x->valid = false;
+    }
+  }
   e.kb_total = Kp / TC_BK;
   { static int dbg = -1; if (dbg < 0) { const char* d = getenv("ASE_TC_DEBUG"); dbg = d ? atoi(d) : 0; } e.debug = dbg; }
   int splits = (p.accumulate && p.split_k > 1) ? p.split_k : 1;

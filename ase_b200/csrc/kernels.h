@@ -20,10 +20,25 @@ int copy_cols(const float* x, int64_t ldx, int rows, int cols, float* y, int64_t
 
 // ------------------------------------------------------------------ GEMM backends
 int gemm_simt(const AseGemmParams& p, cudaStream_t st);
-int gemm_tc(const AseGemmParams& p, cudaStream_t st);          // tcgen05 3xTF32 (gemm_tc.cu)
+// TF32 hi/lo operand planes kept next to registered fp32 buffers (gemm_tc.cu)
+struct PlaneBuf {
+  const float* base; int64_t capacity;          // fp32 buffer (floats)
+  float* hi; float* lo; int64_t plane_capacity; // planes (floats each)
+  int64_t ld; int rows, cols; int64_t ldp;      // geometry declared by the last full writer / first reader
+  bool valid;
+};
+struct PlaneRegistry {
+  static constexpr int MAX = 160;
+  PlaneBuf b[MAX]; int n = 0;
+  PlaneBuf* find(const float* p);
+  void add(const float* base, int64_t capacity, float* hi, float* lo, int64_t plane_capacity);
+  void invalidate(const float* p);
+  void invalidate_range(const float* lo_, const float* hi_);
+};
+int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg = nullptr);   // tcgen05 3xTF32 (gemm_tc.cu)
 bool gemm_tc_supported(const AseGemmParams& p);
 int64_t gemm_tc_workspace_bytes(int M, int N, int K);
-int gemm_dispatch(const AseGemmParams& p, cudaStream_t st);    // picks the backend named in p.backend (falls back to SIMT for shapes tc rejects)
+int gemm_dispatch(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg = nullptr);    // picks the backend named in p.backend (falls back to SIMT for shapes tc rejects)
 
 // ------------------------------------------------------------------ loss-side accumulators (doubles)
 enum {

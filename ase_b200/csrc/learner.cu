@@ -86,6 +86,11 @@ struct AseLearner {
   double* acc;
   void *rms_obs_scratch, *rms_amp_scratch;
   void* tc_ws; int64_t tc_ws_bytes;
+  // TF32 operand planes (tcgen05 backend): one hi/lo pair per registered activation buffer + one pair per weight
+  PlaneRegistry* reg;
+  float* act_planes; int64_t act_plane_floats;     // carved region for activation planes
+  float* w_planes; int64_t w_plane_floats;         // carved region for weight planes
+  const float* reg_params;                         // parameter arena the weight entries currently point at
 };
 
 namespace ase {
@@ -158,7 +163,65 @@ static void carve(AseLearner& L, void* ws, int64_t* total) {
   L.tc_ws_bytes = tc_ws_need(L);
   cv.off = align_up(cv.off, 1024);
   L.tc_ws = L.tc_ws_bytes ? cv.take<char>(L.tc_ws_bytes) : nullptr;
+  if (c.gemm_backend == 1) {
+    // activation planes: registered lazily in register_planes(); size = 2 x (sum of registered fp32 buffers, ld padded to 4)
+    int64_t act = 0;
+    auto add = [&](int64_t rows, int64_t cols) { act += rows * align_up(cols, 4); };
+    add(Ra, L.ldx); if (L.ase) { add(B, L.ldx); add(Ra, c.latent_dim); for (int k = 0; k < c.n_style_units; ++k) add(Ra, c.style_units[k]); }
+    for (int k = 0; k < c.n_units; ++k) { add(Ra, c.units[k]); add(B, c.units[k]); }
+    if (L.amp) {
+      add(3 * Ba, L.amp_ld);
+      for (int k = 0; k < c.n_disc_units; ++k) { add(3 * Ba, c.disc_units[k]); add(Ba, c.disc_units[k]); }
+      add(Ba, L.amp_ld);
+    }
+    add(1, gsz); add(1, gsz);
+    L.act_plane_floats = act;
+    L.act_planes = cv.take<float>(2 * act);
+    int64_t wf = 0;
+    for (int i = 0; i < L.net.n_tensors; ++i) wf += (int64_t)L.net.desc[i].rows * align_up(L.net.desc[i].cols, 4);
+    L.w_plane_floats = wf;
+    L.w_planes = cv.take<float>(2 * wf);
+  }
   *total = cv.off;
+}
+
+// (Re)build the plane registry: activation buffers once, weight entries whenever the parameter arena pointer changes.
+static void register_planes(AseLearner& L, const float* params) {
+  if (L.cfg.gemm_backend != 1) return;
+  const AseLearnerConfig& c = L.cfg;
+  if (!L.reg) L.reg = new PlaneRegistry;
+  if (L.reg->n > 0 && L.reg_params == params) return;
+  PlaneRegistry& R = *L.reg;
+  R.n = 0;
+  float* hp = L.act_planes; float* lp = L.act_planes + L.act_plane_floats;
+  int64_t off = 0;
+  auto add = [&](const float* base, int64_t rows, int64_t cols) {
+    const int64_t cap = rows * align_up(cols, 4);
+    R.add(base, rows * cols, hp + off, lp + off, cap);
+    off += cap;
+  };
+  const int64_t Ra = L.Ra, B = L.B, Ba = L.Ba;
+  add(L.Xa, Ra, L.ldx);
+  if (L.ase) { add(L.Xc, B, L.ldx); add(L.Zc, Ra, c.latent_dim); for (int k = 0; k < c.n_style_units; ++k) add(L.S[k], Ra, c.style_units[k]); }
+  for (int k = 0; k < c.n_units; ++k) { add(L.H[k], Ra, c.units[k]); add(L.C[k], B, c.units[k]); }
+  int64_t gsz = Ra * (int64_t)L.maxw;
+  if (L.amp) {
+    add(L.Xd, 3 * Ba, L.amp_ld);
+    int dmax = 0;
+    for (int k = 0; k < c.n_disc_units; ++k) { add(L.D[k], 3 * Ba, c.disc_units[k]); add(L.U[k], Ba, c.disc_units[k]); dmax = max(dmax, c.disc_units[k]); }
+    add(L.Gx, Ba, L.amp_ld);
+    gsz = imax64(gsz, 3 * Ba * (int64_t)dmax);
+  }
+  add(L.G0, 1, gsz); add(L.G1, 1, gsz);
+  float* wh = L.w_planes; float* wl = L.w_planes + L.w_plane_floats;
+  int64_t woff = 0;
+  for (int i = 0; i < L.net.n_tensors; ++i) {
+    const TensorDesc& d = L.net.desc[i];
+    const int64_t cap = (int64_t)d.rows * align_up(d.cols, 4);
+    if (d.rows > 1 || true) R.add(params + d.off, (int64_t)d.rows * d.cols, wh + woff, wl + woff, cap);
+    woff += cap;
+  }
+  L.reg_params = params;
 }
 
 static int init_learner(AseLearner& L, const AseLearnerConfig& cfg) {
@@ -183,6 +246,8 @@ static int init_learner(AseLearner& L, const AseLearnerConfig& cfg) {
 
 struct G {
   AseLearner& L; cudaStream_t st; const float* P; float* GR;   // P = parameter arena, GR = gradient arena
+  PlaneRegistry* reg() const { return L.reg; }
+  void inval(const float* p) const { if (L.reg) L.reg->invalidate(p); }
   AseGemmParams base() const {
     AseGemmParams p; memset(&p, 0, sizeof(p));
     p.alpha = 1.0f; p.backend = L.cfg.gemm_backend; p.workspace = L.tc_ws; p.workspace_bytes = L.tc_ws_bytes;
@@ -193,7 +258,7 @@ struct G {
     AseGemmParams p = base();
     p.A = X; p.lda = lda; p.B = P + l.w; p.ldb = l.in; p.C = Y; p.ldc = ldc; p.M = M; p.N = l.out; p.K = l.in;
     p.bias = P + l.b; p.act = act;
-    return gemm_dispatch(p, st);
+    return gemm_dispatch(p, st, reg());
   }
   // dX[M,ncols] (ldc) = (dZ[M,l.out] . W[:, col0:col0+ncols]) (*) mask
   int dx(const float* dZ, int64_t ldz, int M, const Layer& l, int col0, int ncols, float* dX, int64_t ldc,
@@ -201,7 +266,7 @@ struct G {
     AseGemmParams p = base();
     p.A = dZ; p.lda = ldz; p.B = P + l.w + col0; p.ldb = l.in; p.b_trans = 1; p.C = dX; p.ldc = ldc; p.M = M; p.N = ncols; p.K = l.out;
     p.mask_src = mask_src; p.ldm = ldm; p.mask_mode = mask_src ? mask_mode : 0;
-    return gemm_dispatch(p, st);
+    return gemm_dispatch(p, st, reg());
   }
   // dW[l.out, l.in] += dZ[M,l.out]^T . X[M,l.in]
   int dw(const float* dZ, int64_t ldz, int M, const Layer& l, const float* X, int64_t ldx) const {
@@ -218,7 +283,7 @@ struct G {
       if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
     }
     p.split_k = best;
-    return gemm_dispatch(p, st);
+    return gemm_dispatch(p, st, reg());
   }
   int db(const float* dZ, int64_t ldz, int M, const Layer& l) const { return launch_colsum(dZ, ldz, M, l.out, GR + l.b, st); }
   // Y = X . W^T (no bias), masked: used by the gradient-penalty backward chain
@@ -226,7 +291,7 @@ struct G {
     AseGemmParams p = base();
     p.A = X; p.lda = lda; p.B = P + l.w; p.ldb = l.in; p.C = Y; p.ldc = l.out; p.M = M; p.N = l.out; p.K = l.in;
     p.mask_src = mask_src; p.ldm = ldm; p.mask_mode = 1;
-    return gemm_dispatch(p, st);
+    return gemm_dispatch(p, st, reg());
   }
 };
 
@@ -330,7 +395,13 @@ extern "C" int ase_learner_create(const AseLearnerConfig* cfg, void* workspace, 
   *out = L;
   return ASE_OK;
 }
-extern "C" void ase_learner_destroy(AseLearner* l) { delete l; }
+extern "C" void ase_learner_destroy(AseLearner* l) { if (l) { delete l->reg; delete l; } }
+
+extern "C" int ase_learner_params_changed(AseLearner* l) {
+  ASE_CHECK_ARG(l != nullptr, "ase_learner_params_changed: null learner");
+  if (l->reg && l->reg_params) l->reg->invalidate_range(l->reg_params, l->reg_params + l->net.arena);
+  return ASE_OK;
+}
 
 extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState* s, const AseMinibatch* mb, const AseTrainResult* out,
                                           void* stream) {
@@ -345,6 +416,7 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
   if (L.ase) ASE_CHECK_ARG(mb->ase_latents && (!L.has_div || mb->new_latents), "calc_gradients: ASE latents");
   ASE_CHECK_ARG(out->scalars, "calc_gradients: scalars output");
   const int B = L.B, Ba = L.Ba, Ra = L.Ra, Z = c.latent_dim, A = c.act_dim;
+  register_planes(L, s->params);
   G g{L, st, s->params, s->grads};
 
   ASE_CUDA_OK(cudaMemsetAsync(L.acc, 0, ACC_COUNT * sizeof(double), st));
@@ -360,11 +432,13 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
     if (L.has_div) { d.y[1] = L.Xa + (int64_t)B * L.ldx; d.ld[1] = L.ldx; }
     if (L.ase) { d.y[2] = L.Xc; d.ld[2] = L.ldx; }
     RC(rms_normalize(mb->obs, c.obs_dim, B, c.obs_dim, mf, sf, 0, d, st));
+    g.inval(L.Xa); g.inval(L.Xc);
   }
   if (L.ase) {
     RC(copy_cols(mb->ase_latents, Z, B, Z, L.Xc + c.obs_dim, L.ldx, st));
     RC(copy_cols(mb->ase_latents, Z, B, Z, L.Zc, Z, st));
     if (L.has_div) RC(copy_cols(mb->new_latents, Z, B, Z, L.Zc + (int64_t)B * Z, Z, st));
+    g.inval(L.Xc); g.inval(L.Zc);
   }
   if (L.amp) {
     // three sequential updates: agent, replay, demo -- each batch normalised with the stats after ITS update
@@ -376,6 +450,7 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
       RmsDst d = {}; d.y[0] = L.Xd + (int64_t)b * Ba * L.amp_ld; d.ld[0] = L.amp_ld;
       RC(rms_normalize(bl.x[b], c.amp_dim, Ba, c.amp_dim, mf + (int64_t)b * c.amp_dim, sf + (int64_t)b * c.amp_dim, 0, d, st));
     }
+    g.inval(L.Xd);
   }
 
   // ---- forward ------------------------------------------------------------------------------------------
@@ -438,11 +513,12 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
         AseGemmParams p = g.base();
         p.A = L.dE; p.lda = Z; p.B = s->params + n.enc.w; p.ldb = last.out; p.b_trans = 1; p.C = cur; p.ldc = last.out;
         p.M = Ba; p.N = last.out; p.K = Z; p.accumulate = 1; p.split_k = 1;
-        RC(gemm_dispatch(p, st));
+        RC(gemm_dispatch(p, st, g.reg()));
       }
       const int64_t tot = (int64_t)R3 * last.out;
       relu_mask_inplace_kernel<<<(int)imin64((tot + 255) / 256, 148 * 16), 256, 0, st>>>(cur, L.D[nd - 1], tot);
       ASE_LAUNCH_OK();
+      g.inval(cur);
     } else {
       RC(g.dx(L.dLOGIT, 1, R3, n.logit, 0, last.out, cur, last.out, L.D[nd - 1], last.out, 1));
     }
@@ -452,12 +528,14 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
     const int64_t demo = (int64_t)2 * Ba;
     const float* wl = s->params + n.logit.w;
     RC(launch_gp_u_last(L.D[nd - 1] + demo * last.out, last.out, Ba, last.out, wl, L.U[nd - 1], st));
+    g.inval(L.U[nd - 1]);
     for (int k = nd - 1; k >= 1; --k)   // U_{k-1} = D_{k-1} (*) (U_k . W_k)
       RC(g.dx(L.U[k], n.disc[k].out, Ba, n.disc[k], 0, n.disc[k].in, L.U[k - 1], n.disc[k].in,
               L.D[k - 1] + demo * n.disc[k - 1].out, n.disc[k - 1].out, 1));
     RC(g.dx(L.U[0], n.disc[0].out, Ba, n.disc[0], 0, c.amp_dim, L.Gx, L.amp_ld, nullptr, 0, 0));     // G = U_0 . W_0
     // (padding columns of Gx are zero: they are never written)
     RC(launch_gp_scale(L.Gx, (int64_t)Ba * L.amp_ld, c.disc_coef * c.disc_grad_penalty * 2.0f / (float)Ba, L.acc, st));
+    g.inval(L.Gx);
     RC(g.dw(L.U[0], n.disc[0].out, Ba, n.disc[0], L.Gx, L.amp_ld));                                   // dW_0 += U_0^T Gbar
     RC(g.nt_masked(L.Gx, L.amp_ld, Ba, n.disc[0], cur, L.D[0] + demo * n.disc[0].out, n.disc[0].out)); // Ubar_0
     for (int k = 1; k < nd; ++k) {
@@ -492,6 +570,7 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
 extern "C" int ase_learner_adam_step(AseLearner* lp, const AseLearnerState* s, int64_t step, float grad_scale, void* stream) {
   ASE_CHECK_ARG(lp && s && s->params && s->grads && s->exp_avg && s->exp_avg_sq && step >= 1, "adam_step: bad argument");
   const AseLearnerConfig& c = lp->cfg;
+  if (lp->reg) lp->reg->invalidate_range(s->params, s->params + lp->net.arena);   // weight planes are stale after the update
   return launch_adam(s->params, s->grads, s->exp_avg, s->exp_avg_sq, lp->net.arena, grad_scale, c.beta1, c.beta2, c.lr, c.adam_eps, step,
                      (cudaStream_t)stream);
 }
@@ -503,8 +582,10 @@ extern "C" int ase_learner_eval_actor_critic(AseLearner* lp, const AseLearnerSta
   ASE_CHECK_ARG(rows > 0 && rows <= L.B, "eval_actor_critic: rows %d > minibatch %d", rows, L.B);
   ASE_CHECK_ARG(!L.ase || latents, "eval_actor_critic: latents required");
   cudaStream_t st = (cudaStream_t)stream;
+  register_planes(L, s->params);
   G g{L, st, s->params, s->grads};
   RC(rms_apply(obs, c.obs_dim, rows, c.obs_dim, s->obs_mean, s->obs_var, c.rms_eps, 0, L.Xa, L.ldx, st));
+  g.inval(L.Xa); g.inval(L.Xc); g.inval(L.Zc);
   if (L.ase) {
     RC(copy_cols(L.Xa, L.ldx, rows, c.obs_dim, L.Xc, L.ldx, st));
     RC(copy_cols(latents, c.latent_dim, rows, c.latent_dim, L.Xc + c.obs_dim, L.ldx, st));
@@ -524,8 +605,10 @@ extern "C" int ase_learner_eval_disc_enc(AseLearner* lp, const AseLearnerState* 
   ASE_CHECK_ARG(rows > 0 && rows <= 3 * L.Ba, "eval_disc_enc: rows %d > 3*amp_batch %d", rows, 3 * L.Ba);
   ASE_CHECK_ARG(!enc_pred || L.ase, "eval_disc_enc: enc_pred needs an ASE learner");
   cudaStream_t st = (cudaStream_t)stream;
+  register_planes(L, s->params);
   G g{L, st, s->params, s->grads};
   RC(rms_apply(amp_obs, c.amp_dim, rows, c.amp_dim, s->amp_mean, s->amp_var, c.rms_eps, 0, L.Xd, L.amp_ld, st));
+  g.inval(L.Xd);
   RC(forward_disc(g, rows, enc_pred ? rows : 0));
   if (disc_logits) ASE_CUDA_OK(cudaMemcpyAsync(disc_logits, L.LOGIT, (size_t)rows * sizeof(float), cudaMemcpyDeviceToDevice, st));
   if (enc_pred) RC(launch_enc_head(L.E, rows, c.latent_dim, nullptr, 0.0f, nullptr, enc_pred, nullptr, st));

@@ -154,6 +154,11 @@ class Learner:
             elif name.startswith('_enc.'):
                 bound = 0.1
             v.copy_(((torch.rand(v.shape, generator=g) * 2 - 1) * bound).to(v.device))
+        self.params_changed()
+
+    def params_changed(self):
+        """Tell the library the parameter arena was written from outside (the tcgen05 backend caches weight planes)."""
+        check(lib.ase_learner_params_changed(self._h), 'ase_learner_params_changed')
 
     def load_named(self, named):
         """named: {reference name without the 'a2c_network.' prefix: tensor}"""
@@ -161,6 +166,7 @@ class Learner:
             v.copy_(named[k].to(v.device).reshape(v.shape))
         if 'sigma' in named:
             self.sigma.copy_(named['sigma'].to(self.device))
+        self.params_changed()
 
     def state_dict(self):
         sd = OrderedDict()

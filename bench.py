@@ -91,6 +91,7 @@ def _make_agent(torch, rank, world, state_source, seed):
     if world > 1:
         import torch.distributed as dist
         dist.broadcast(agent.model.params, 0)
+        agent.model.params_changed()
     agent._init_train()
     return agent, env
 

@@ -232,6 +232,10 @@ typedef struct {
   float* values;             /* optional [B] */
 } AseTrainResult;
 
+/* Must be called after the parameter arena was modified by anything other than ase_learner_adam_step (checkpoint load,
+ * initialisation, broadcast): the tcgen05 backend caches TF32 hi/lo planes of the weights between calls. */
+int ase_learner_params_changed(AseLearner* l);
+
 /* forward + losses + backward: fills state->grads (sum over local rows; no Adam) */
 int ase_learner_calc_gradients(AseLearner* l, const AseLearnerState* st, const AseMinibatch* mb,
                                const AseTrainResult* out, void* stream);
