@@ -21,6 +21,7 @@ static int check_gemm(const AseGemmParams& p) {
   ASE_CHECK_ARG(p.M > 0 && p.N > 0 && p.K > 0, "gemm: non-positive dimension %d %d %d", p.M, p.N, p.K);
   ASE_CHECK_ARG(p.lda >= (p.a_trans ? p.M : p.K) && p.ldb >= (p.b_trans ? p.N : p.K) && p.ldc >= p.N, "gemm: leading dimension too small");
   ASE_CHECK_ARG(!(p.accumulate && (p.act || (p.mask_src && p.mask_mode))), "gemm: accumulate cannot be combined with act/mask");
+  ASE_CHECK_ARG(!(p.accumulate && p.colsum_out), "gemm: colsum_out cannot be combined with accumulate");
   ASE_CHECK_ARG(p.act >= 0 && p.act <= 2 && p.mask_mode >= 0 && p.mask_mode <= 2, "gemm: bad act/mask mode");
   return ASE_OK;
 }

@@ -20,6 +20,7 @@ struct SimtArgs {
   int act;
   const float* mask_src; int64_t ldm; int mask_mode;
   int accumulate;
+  float* colsum;
   int k_per_split;
   int vecA, vecB;    // 16-byte vector loads allowed (alignment of base + leading dimension)
 };
@@ -144,6 +145,7 @@ gemm_simt_kernel(SimtArgs g) {
         if (g.mask_mode == 1) v = (g.mask_src[(int64_t)m * g.ldm + n] > 0.0f) ? v : 0.0f;
         else if (g.mask_mode == 2) { const float s = g.mask_src[(int64_t)m * g.ldm + n]; v *= (1.0f - s * s); }
         g.C[(int64_t)m * g.ldc + n] = v;
+        if (g.colsum) atomicAdd(&g.colsum[n], v);
       }
     }
   }
@@ -153,7 +155,7 @@ int gemm_simt(const AseGemmParams& p, cudaStream_t st) {
   SimtArgs g;
   g.A = p.A; g.lda = p.lda; g.B = p.B; g.ldb = p.ldb; g.C = p.C; g.ldc = p.ldc;
   g.M = p.M; g.N = p.N; g.K = p.K; g.alpha = p.alpha; g.bias = p.bias; g.act = p.act;
-  g.mask_src = p.mask_src; g.ldm = p.ldm; g.mask_mode = p.mask_src ? p.mask_mode : 0; g.accumulate = p.accumulate;
+  g.mask_src = p.mask_src; g.ldm = p.ldm; g.mask_mode = p.mask_src ? p.mask_mode : 0; g.accumulate = p.accumulate; g.colsum = p.colsum_out;
   int splits = p.split_k > 1 ? p.split_k : 1;
   if (!p.accumulate) splits = 1;
   int kps = (p.K + splits - 1) / splits;

@@ -118,6 +118,7 @@ struct TcEpi {
   int act;
   const float* mask_src; int64_t ldm; int mask_mode;
   int accumulate;
+  float* colsum;                           // optional: colsum[n] += sum_m C[m,n] (bias gradient of the layer whose dZ this GEMM produces)
   float* Chi; float* Clo; int64_t ldp;     // optional TF32 hi/lo planes of C (operand cache for the consumers of C)
   int debug;   // experiments only (env ASE_TC_DEBUG): 1 skip global stores, 2 skip TMEM drain loads, 4 skip correction MMAs, 8 skip bias/act
 };
@@ -300,6 +301,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         const int nvalid = min(4, e.N - n);
         float bv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         if (add_bias) for (int j = 0; j < nvalid; ++j) bv[j] = e.bias[n + j];
+        float cs4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 4
         for (int r = 0; r < 32; ++r) {
           const int row = lg * 32 + r, m = m0 + row;
@@ -323,6 +325,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
           }
           if (vec_ok && nvalid == 4) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
           else for (int j = 0; j < nvalid; ++j) cp[j] = x[j];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cs4[j] += x[j];
           if (e.Chi) {       // the consumers of C read these planes directly through TMA: no separate split pass
             float h[4], l[4];
 #pragma unroll
@@ -332,6 +336,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
             else for (int j = 0; j < nvalid; ++j) { hp[j] = h[j]; lp[j] = l[j]; }
           }
         }
+        if (e.colsum && !e.accumulate) for (int j = 0; j < nvalid; ++j) atomicAdd(e.colsum + n + j, cs4[j]);
       }
     }
   }
@@ -568,7 +573,7 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   TcEpi e;
   e.C = p.C; e.ldc = p.ldc; e.M = p.M; e.N = p.N; e.K = p.K; e.alpha = p.alpha; e.bias = p.bias; e.act = p.act;
   e.mask_src = p.mask_src; e.ldm = p.ldm; e.mask_mode = p.mask_src ? p.mask_mode : 0; e.accumulate = p.accumulate;
-  e.Chi = e.Clo = nullptr; e.ldp = 0;
+  e.Chi = e.Clo = nullptr; e.ldp = 0; e.colsum = p.colsum_out;
   // ---- output planes: a full write at the base of a registered buffer (re)declares its geometry; a partial write
   // keeps planes in sync only if they are currently valid with the same leading dimension; accumulation invalidates
   if (reg) {

@@ -262,8 +262,9 @@ struct G {
   }
   // dX[M,ncols] (ldc) = (dZ[M,l.out] . W[:, col0:col0+ncols]) (*) mask
   int dx(const float* dZ, int64_t ldz, int M, const Layer& l, int col0, int ncols, float* dX, int64_t ldc,
-         const float* mask_src, int64_t ldm, int mask_mode) const {
+         const float* mask_src, int64_t ldm, int mask_mode, float* colsum = nullptr) const {
     AseGemmParams p = base();
+    p.colsum_out = colsum;
     p.A = dZ; p.lda = ldz; p.B = P + l.w + col0; p.ldb = l.in; p.b_trans = 1; p.C = dX; p.ldc = ldc; p.M = M; p.N = ncols; p.K = l.out;
     p.mask_src = mask_src; p.ldm = ldm; p.mask_mode = mask_src ? mask_mode : 0;
     return gemm_dispatch(p, st, reg());
@@ -298,15 +299,17 @@ struct G {
 // Backward through a ReLU MLP trunk.  On entry *cur holds dZ of the LAST layer (already masked), [M, out_last].
 // acts[k] = stored post-activation outputs, X0 (ld ldx0) = trunk input.  On exit *cur holds dZ of layer 0.
 static int trunk_backward(const G& g, const Layer* layers, int n, float* const* acts, const float* X0, int64_t ldx0, int M,
-                          float** cur, float** other) {
+                          float** cur, float** other, bool have_db = false) {
   for (int k = n - 1; k >= 0; --k) {
     const Layer& l = layers[k];
     const float* Xin = (k == 0) ? X0 : acts[k - 1];
     const int64_t ldin = (k == 0) ? ldx0 : layers[k - 1].out;
     RC(g.dw(*cur, l.out, M, l, Xin, ldin));
-    RC(g.db(*cur, l.out, M, l));
+    if (!have_db) RC(g.db(*cur, l.out, M, l));
     if (k > 0) {
-      RC(g.dx(*cur, l.out, M, l, 0, l.in, *other, l.in, acts[k - 1], layers[k - 1].out, 1));
+      // the dX GEMM that produces dZ of layer k-1 also column-sums it into that layer's bias gradient
+      RC(g.dx(*cur, l.out, M, l, 0, l.in, *other, l.in, acts[k - 1], layers[k - 1].out, 1, g.GR + layers[k - 1].b));
+      have_db = true;
       float* t = *cur; *cur = *other; *other = t;
     }
   }
@@ -476,19 +479,18 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
     const Layer& last = n.actor[n.n_actor - 1];
     RC(g.dw(L.dMU, A, Ra, n.mu, L.H[n.n_actor - 1], last.out));
     RC(g.db(L.dMU, A, Ra, n.mu));
-    RC(g.dx(L.dMU, A, Ra, n.mu, 0, last.out, cur, last.out, L.H[n.n_actor - 1], last.out, 1));
-    RC(trunk_backward(g, n.actor, n.n_actor, L.H, L.Xa, L.ldx, Ra, &cur, &oth));
+    RC(g.dx(L.dMU, A, Ra, n.mu, 0, last.out, cur, last.out, L.H[n.n_actor - 1], last.out, 1, s->grads + last.b));
+    RC(trunk_backward(g, n.actor, n.n_actor, L.H, L.Xa, L.ldx, Ra, &cur, &oth, true));
     if (L.ase) {
       // d(style pre-activation) = (dZ0 . W0[:, obs:obs+Z]) * (1 - style^2)
       const Layer& l0 = n.actor[0];
-      RC(g.dx(cur, l0.out, Ra, l0, c.obs_dim, Z, oth, Z, L.Xa + c.obs_dim, L.ldx, 2));
+      RC(g.dx(cur, l0.out, Ra, l0, c.obs_dim, Z, oth, Z, L.Xa + c.obs_dim, L.ldx, 2, s->grads + n.style_dense.b));
       { float* t = cur; cur = oth; oth = t; }
       const Layer& sd = n.style_dense; const Layer& sl = n.style[n.n_style - 1];
       RC(g.dw(cur, Z, Ra, sd, L.S[n.n_style - 1], sl.out));
-      RC(g.db(cur, Z, Ra, sd));
-      RC(g.dx(cur, Z, Ra, sd, 0, sl.out, oth, sl.out, L.S[n.n_style - 1], sl.out, 1));
+      RC(g.dx(cur, Z, Ra, sd, 0, sl.out, oth, sl.out, L.S[n.n_style - 1], sl.out, 1, s->grads + sl.b));
       { float* t = cur; cur = oth; oth = t; }
-      RC(trunk_backward(g, n.style, n.n_style, L.S, L.Zc, Z, Ra, &cur, &oth));
+      RC(trunk_backward(g, n.style, n.n_style, L.S, L.Zc, Z, Ra, &cur, &oth, true));
     }
   }
   // ---- backward: critic ---------------------------------------------------------------------------------
@@ -496,8 +498,8 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
     const Layer& last = n.critic[n.n_critic - 1];
     RC(g.dw(L.dV, 1, B, n.value, L.C[n.n_critic - 1], last.out));
     RC(g.db(L.dV, 1, B, n.value));
-    RC(g.dx(L.dV, 1, B, n.value, 0, last.out, cur, last.out, L.C[n.n_critic - 1], last.out, 1));
-    RC(trunk_backward(g, n.critic, n.n_critic, L.C, L.Xc, L.ldx, B, &cur, &oth));
+    RC(g.dx(L.dV, 1, B, n.value, 0, last.out, cur, last.out, L.C[n.n_critic - 1], last.out, 1, s->grads + last.b));
+    RC(trunk_backward(g, n.critic, n.n_critic, L.C, L.Xc, L.ldx, B, &cur, &oth, true));
   }
   // ---- backward: discriminator (+ encoder through the shared trunk) -------------------------------------
   if (L.amp) {
@@ -520,9 +522,9 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
       ASE_LAUNCH_OK();
       g.inval(cur);
     } else {
-      RC(g.dx(L.dLOGIT, 1, R3, n.logit, 0, last.out, cur, last.out, L.D[nd - 1], last.out, 1));
+      RC(g.dx(L.dLOGIT, 1, R3, n.logit, 0, last.out, cur, last.out, L.D[nd - 1], last.out, 1, s->grads + last.b));
     }
-    RC(trunk_backward(g, n.disc, nd, L.D, L.Xd, L.amp_ld, R3, &cur, &oth));
+    RC(trunk_backward(g, n.disc, nd, L.D, L.Xd, L.amp_ld, R3, &cur, &oth, !L.ase));
 
     // ---- gradient penalty on the demo rows: analytic double backward (amp_agent.py:454-459) -------------
     const int64_t demo = (int64_t)2 * Ba;

@@ -142,6 +142,7 @@ typedef struct {
   int split_k;              /* 0/1 = none */
   int backend;
   void* workspace; int64_t workspace_bytes;   /* backend 1 only: >= ase_gemm_tc_workspace_bytes() */
+  float* colsum_out;        /* optional [N]: colsum_out[n] += sum_m C[m,n] (not with accumulate) */
 } AseGemmParams;
 int ase_gemm(const AseGemmParams* p, void* stream);
 int64_t ase_gemm_tc_workspace_bytes(int M, int N, int K);
