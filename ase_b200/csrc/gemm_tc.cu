@@ -52,6 +52,19 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, ui
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -142,7 +155,10 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // accumulator), double buffered; the epilogue warps drain each k-block's partial tile with tcgen05.ld and add it
 // into fp32 registers with round-to-nearest FADDs while the tensor core works on the next k-block.  The two
 // correction terms (2^-11 smaller) accumulate across all of K in a third TMEM tile: their truncation is negligible.
-template <int BN, int STAGES, bool AMN, bool BMN>
+// CL = cluster size along N (1 or 2).  With CL = 2 the two CTAs of a cluster work on the same 128 rows of A: each
+// loads HALF of the A planes and multicasts it into both CTAs' shared memory, halving the A traffic out of L2
+// (the mainloop is operand-feed bound: 64 KB per k-block per CTA against ~768 MMA cycles).
+template <int BN, int STAGES, bool AMN, bool BMN, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const TcEpi e) {
@@ -164,7 +180,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
   const int nkb = min(e.kb_per_split, e.kb_total - kb_begin);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }   // every CTA of the cluster releases a stage
     for (int b = 0; b < 2; ++b) { mbar_init(&main_full[b], 1); mbar_init(&main_empty[b], 4); }   // 4 epilogue warps arrive
     mbar_init(corr_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -176,8 +192,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (CL > 1) cluster_sync_all();        // peers' barriers are initialised before any multicast / remote arrive
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_corr = tmem_base + 2 * BN;
+  const uint32_t crank = (CL > 1) ? cluster_rank() : 0u;
+  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -188,14 +207,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         mbar_expect_tx(&full[s], SM::STAGE_BYTES);
         uint8_t* st = smem + s * SM::STAGE_BYTES;
         const int k0 = (kb_begin + kb) * TC_BK;
-        if (!AMN) {          // K-major planes [rows, K]: one box of 128 rows x 32 k
-          tma_load_2d(st, &tmAhi, &full[s], k0, m0);
-          tma_load_2d(st + SM::A_BYTES, &tmAlo, &full[s], k0, m0);
-        } else {             // MN-major planes [K, rows]: 4 boxes of 32 k-rows x 32 m
+        if (CL == 1) {
+          if (!AMN) {          // K-major planes [rows, K]: one box of 128 rows x 32 k
+            tma_load_2d(st, &tmAhi, &full[s], k0, m0);
+            tma_load_2d(st + SM::A_BYTES, &tmAlo, &full[s], k0, m0);
+          } else {             // MN-major planes [K, rows]: 4 boxes of 32 k-rows x 32 m
 #pragma unroll
-          for (int b = 0; b < TC_BM / 32; ++b) {
-            tma_load_2d(st + b * 4096, &tmAhi, &full[s], m0 + b * 32, k0);
-            tma_load_2d(st + SM::A_BYTES + b * 4096, &tmAlo, &full[s], m0 + b * 32, k0);
+            for (int b = 0; b < TC_BM / 32; ++b) {
+              tma_load_2d(st + b * 4096, &tmAhi, &full[s], m0 + b * 32, k0);
+              tma_load_2d(st + SM::A_BYTES + b * 4096, &tmAlo, &full[s], m0 + b * 32, k0);
+            }
+          }
+        } else {               // this CTA's half of A, multicast to the whole cluster (the A maps have 128/CL-row boxes)
+          constexpr int HALF = TC_BM / CL;
+          if (!AMN) {
+            tma_load_2d_mc(st + crank * HALF * 128, &tmAhi, &full[s], k0, m0 + crank * HALF, MC_MASK);
+            tma_load_2d_mc(st + SM::A_BYTES + crank * HALF * 128, &tmAlo, &full[s], k0, m0 + crank * HALF, MC_MASK);
+          } else {
+#pragma unroll
+            for (int bb = 0; bb < HALF / 32; ++bb) {
+              const int b = crank * (HALF / 32) + bb;
+              tma_load_2d_mc(st + b * 4096, &tmAhi, &full[s], m0 + b * 32, k0, MC_MASK);
+              tma_load_2d_mc(st + SM::A_BYTES + b * 4096, &tmAlo, &full[s], m0 + b * 32, k0, MC_MASK);
+            }
           }
         }
         if (!BMN) {
@@ -240,7 +274,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
           tc_mma_tf32(tmem_corr, adesc(a_lo, k), bdesc(b_hi, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           tc_mma_tf32(tmem_corr, adesc(a_hi, k), bdesc(b_lo, k), idesc, 1u);
         }
-        tc_commit(&empty[s]);                  // all 12 MMAs have read this smem stage
+        if (CL == 1) tc_commit(&empty[s]);     // all 12 MMAs have read this smem stage
+        else tc_commit_mc(&empty[s], MC_MASK); // ... and tell every CTA that multicasts into it
       }
       tc_commit(corr_full);
     }
@@ -342,6 +377,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();        // nobody exits while a peer may still multicast into / arrive on this CTA
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
@@ -447,31 +483,44 @@ static void prof_mark(cudaStream_t st) {
   cudaEventRecord(g_prof.ev[g_prof.used++], st);
 }
 
-template <int BN, int STAGES, bool AMN, bool BMN>
+template <int BN, int STAGES, bool AMN, bool BMN, int CL>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcEpi& e,
                      int splits, cudaStream_t st) {
   using SM = TcSmem<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    ASE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    ASE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, AMN, BMN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr_set = true;
   }
   dim3 grid(ceil_div(e.N, BN), ceil_div(e.M, TC_BM), splits);
+  grid.x = (grid.x + CL - 1) / CL * CL;       // whole clusters; a padding CTA computes an all-out-of-range tile and stores nothing
   const bool prof = g_prof.on;
   if (prof) prof_mark(st);
-  gemm_tc_kernel<BN, STAGES, AMN, BMN><<<grid, TC_THREADS, SM::TOTAL, st>>>(ah, al, bh, bl, e);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  ASE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, AMN, BMN, CL>, ah, al, bh, bl, e));
   if (prof) { prof_mark(st); g_prof.flops += 2.0 * (double)e.M * (double)e.N * (double)e.K; }
   ASE_LAUNCH_OK();
   return ASE_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int CL>
 static int launch_tc_major(bool amn, bool bmn, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                            const TcEpi& e, int splits, cudaStream_t st) {
-  if (!amn && !bmn) return launch_tc<BN, STAGES, false, false>(ah, al, bh, bl, e, splits, st);
-  if (!amn && bmn) return launch_tc<BN, STAGES, false, true>(ah, al, bh, bl, e, splits, st);
-  if (amn && !bmn) return launch_tc<BN, STAGES, true, false>(ah, al, bh, bl, e, splits, st);
-  return launch_tc<BN, STAGES, true, true>(ah, al, bh, bl, e, splits, st);
+  if (!amn && !bmn) return launch_tc<BN, STAGES, false, false, CL>(ah, al, bh, bl, e, splits, st);
+  if (!amn && bmn) return launch_tc<BN, STAGES, false, true, CL>(ah, al, bh, bl, e, splits, st);
+  if (amn && !bmn) return launch_tc<BN, STAGES, true, false, CL>(ah, al, bh, bl, e, splits, st);
+  return launch_tc<BN, STAGES, true, true, CL>(ah, al, bh, bl, e, splits, st);
+}
+
+static int tc_cluster() {   // env ASE_TC_CLUSTER=1 disables the A-multicast pairs (debugging / A-B comparisons)
+  static int v = -1;
+  if (v < 0) { const char* d = getenv("ASE_TC_CLUSTER"); v = d ? atoi(d) : 2; if (v != 1 && v != 2) v = 2; }
+  return v;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -540,6 +589,8 @@ static int make_view_map(CUtensorMap* tm, const float* base, int rows, int cols,
 
 int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   const int BN = (p.N > 64) ? 128 : 64;
+  const int CL = (BN == 128 && p.N > 128) ? tc_cluster() : 1;       // A-multicast pairs need >= 2 N tiles
+  const int a_box = TC_BM / CL;
   const int Mp = pad_to(p.M, 128), Np = pad_to(p.N, 128), Kp = pad_to(p.K, TC_BK);
   int rc;
   // ---- operands: cached planes when the buffer is registered, else a split pass into the shared workspace
@@ -552,12 +603,12 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   char* ws = (char*)p.workspace;
   if (!va.ok || !vb.ok) { if ((rc = gemm_tc_check_workspace(p))) return rc; }
   if (va.ok) {
-    if ((rc = make_view_map(&ah, va.hi, a_rows, a_cols, va.ldp, p.a_trans ? 32 : TC_BM, p.a_trans != 0)) ||
-        (rc = make_view_map(&al, va.lo, a_rows, a_cols, va.ldp, p.a_trans ? 32 : TC_BM, p.a_trans != 0))) return rc;
+    if ((rc = make_view_map(&ah, va.hi, a_rows, a_cols, va.ldp, p.a_trans ? 32 : a_box, p.a_trans != 0)) ||
+        (rc = make_view_map(&al, va.lo, a_rows, a_cols, va.ldp, p.a_trans ? 32 : a_box, p.a_trans != 0))) return rc;
   } else {
     float* Ahi = (float*)ws; float* Alo = (float*)(ws + align_up((int64_t)Mp * Kp * 4, 1024));
     if ((rc = prep_operand(p.A, p.lda, p.a_trans, p.M, p.K, Mp, Kp, Ahi, Alo, st))) return rc;
-    if (!p.a_trans) { if ((rc = make_map(&ah, Ahi, Mp, Kp, TC_BM)) || (rc = make_map(&al, Alo, Mp, Kp, TC_BM))) return rc; }
+    if (!p.a_trans) { if ((rc = make_map(&ah, Ahi, Mp, Kp, a_box)) || (rc = make_map(&al, Alo, Mp, Kp, a_box))) return rc; }
     else            { if ((rc = make_map(&ah, Ahi, Kp, Mp, 32, true)) || (rc = make_map(&al, Alo, Kp, Mp, 32, true))) return rc; }
   }
   if (vb.ok) {
@@ -595,8 +646,9 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   splits = min(splits, e.kb_total);
   e.kb_per_split = ceil_div(e.kb_total, splits);
   splits = ceil_div(e.kb_total, e.kb_per_split);
-  if (BN == 128) return launch_tc_major<128, 3>(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
-  return launch_tc_major<64, 4>(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
+  if (BN == 128 && CL == 2) return launch_tc_major<128, 3, 2>(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
+  if (BN == 128) return launch_tc_major<128, 3, 1>(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
+  return launch_tc_major<64, 4, 1>(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
 }
 
 }  // namespace ase
