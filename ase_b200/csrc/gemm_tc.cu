@@ -517,9 +517,11 @@ static int launch_tc_major(bool amn, bool bmn, const CUtensorMap& ah, const CUte
   return launch_tc<BN, STAGES, true, true, CL>(ah, al, bh, bl, e, splits, st);
 }
 
-static int tc_cluster() {   // env ASE_TC_CLUSTER=1 disables the A-multicast pairs (debugging / A-B comparisons)
+// A-multicast clusters are OFF by default: measured on B200 (profiles/experiments_r01.md) they do not help -- the
+// mainloop is bound by the per-SM ingest port (~64 B/clk), which multicast does not relieve.  ASE_TC_CLUSTER=2|4 enables them.
+static int tc_cluster() {
   static int v = -1;
-  if (v < 0) { const char* d = getenv("ASE_TC_CLUSTER"); v = d ? atoi(d) : 2; if (v != 1 && v != 2) v = 2; }
+  if (v < 0) { const char* d = getenv("ASE_TC_CLUSTER"); v = d ? atoi(d) : 1; if (v != 1 && v != 2 && v != 4) v = 1; }
   return v;
 }
 
@@ -589,7 +591,8 @@ static int make_view_map(CUtensorMap* tm, const float* base, int rows, int cols,
 
 int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   const int BN = (p.N > 64) ? 128 : 64;
-  const int CL = (BN == 128 && p.N > 128) ? tc_cluster() : 1;       // A-multicast pairs need >= 2 N tiles
+  int CL = (BN == 128 && p.N > 128) ? tc_cluster() : 1;       // A-multicast groups need >= 2 N tiles
+  if (CL == 4 && p.N <= 384) CL = 2;
   const int a_box = TC_BM / CL;
   const int Mp = pad_to(p.M, 128), Np = pad_to(p.N, 128), Kp = pad_to(p.K, TC_BK);
   int rc;
@@ -646,6 +649,7 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   splits = min(splits, e.kb_total);
   e.kb_per_split = ceil_div(e.kb_total, splits);
   splits = ceil_div(e.kb_total, e.kb_per_split);
+  if (BN == 128 && CL == 4) return launch_tc_major<128, 3, 4>(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
   if (BN == 128 && CL == 2) return launch_tc_major<128, 3, 2>(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
   if (BN == 128) return launch_tc_major<128, 3, 1>(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
   return launch_tc_major<64, 4, 1>(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
