@@ -203,6 +203,15 @@ def run_ours(args):
     print(json.dumps(line))
 
 
+def _shutdown():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
 # ------------------------------------------------------------------------------------------------ CPU legs
 def cpu_baseline():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -251,6 +260,7 @@ def main():
         run_reference(args)
     else:
         run_ours(args)
+        _shutdown()
 
 
 if __name__ == "__main__":
