@@ -16,6 +16,8 @@
 // (cross-checked against cute/arch/mma_sm100_desc.hpp in the image's CUTLASS headers).
 #include <cuda.h>
 #include <vector>
+#include <unordered_map>
+#include <string.h>
 #include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
@@ -135,6 +137,59 @@ struct TcEpi {
   float* Chi; float* Clo; int64_t ldp;     // optional TF32 hi/lo planes of C (operand cache for the consumers of C)
   int debug;   // experiments only (env ASE_TC_DEBUG): 1 skip global stores, 2 skip TMEM drain loads, 4 skip correction MMAs, 8 skip bias/act
 };
+
+// Phase 2 of the epilogue, shared by the tile shapes: a warp writes rows [row0, row0+nrows) of the staged tile; a row is
+// written as BNT/4 float4 by consecutive lanes (full 128-byte lines); bias / activation / mask operands are read with the
+// same coalesced mapping; optional TF32 planes of C and the fused column sums (bias gradient) ride along.
+__device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* cs, int cs_ld, int row0, int nrows, int BNT, int m0, int n0, int lane) {
+  const bool vec_ok = ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0) &&
+                      (!e.mask_mode || (((e.ldm & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.mask_src) & 15) == 0)));
+  const bool add_bias = e.bias && (!e.accumulate || blockIdx.z == 0);
+#pragma unroll 1
+  for (int cc = lane * 4; cc < BNT; cc += 128) {
+    const int n = n0 + cc;
+    if (n >= e.N) break;
+    const int nvalid = min(4, e.N - n);
+    float bv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (add_bias) for (int j = 0; j < nvalid; ++j) bv[j] = e.bias[n + j];
+    float cs4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll 4
+    for (int r = 0; r < nrows; ++r) {
+      const int row = row0 + r, m = m0 + row;
+      if (m >= e.M) break;
+      const float4 t = *reinterpret_cast<const float4*>(cs + row * cs_ld + cc);
+      float x[4] = {t.x + bv[0], t.y + bv[1], t.z + bv[2], t.w + bv[3]};
+      float* cp = e.C + (int64_t)m * e.ldc + n;
+      if (e.accumulate) {
+        for (int j = 0; j < nvalid; ++j) atomicAdd(cp + j, x[j]);
+        continue;
+      }
+      if (e.act == 1) { for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.0f); }
+      else if (e.act == 2) { for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]); }
+      if (e.mask_mode) {
+        const float* mp = e.mask_src + (int64_t)m * e.ldm + n;
+        float mv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+        if (vec_ok && nvalid == 4) { const float4 q = *reinterpret_cast<const float4*>(mp); mv[0] = q.x; mv[1] = q.y; mv[2] = q.z; mv[3] = q.w; }
+        else for (int j = 0; j < nvalid; ++j) mv[j] = mp[j];
+        if (e.mask_mode == 1) { for (int j = 0; j < 4; ++j) x[j] = (mv[j] > 0.0f) ? x[j] : 0.0f; }
+        else { for (int j = 0; j < 4; ++j) x[j] *= (1.0f - mv[j] * mv[j]); }
+      }
+      if (vec_ok && nvalid == 4) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+      else for (int j = 0; j < nvalid; ++j) cp[j] = x[j];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cs4[j] += x[j];
+      if (e.Chi) {       // the consumers of C read these planes directly through TMA: no separate split pass
+        float h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) split_tf32(x[j], h[j], l[j]);
+        float* hp = e.Chi + (int64_t)m * e.ldp + n; float* lp = e.Clo + (int64_t)m * e.ldp + n;
+        if (nvalid == 4) { *reinterpret_cast<float4*>(hp) = make_float4(h[0], h[1], h[2], h[3]); *reinterpret_cast<float4*>(lp) = make_float4(l[0], l[1], l[2], l[3]); }
+        else for (int j = 0; j < nvalid; ++j) { hp[j] = h[j]; lp[j] = l[j]; }
+      }
+    }
+    if (e.colsum && !e.accumulate) for (int j = 0; j < nvalid; ++j) atomicAdd(e.colsum + n + j, cs4[j]);
+  }
+}
 
 template <int BN, int STAGES>
 struct TcSmem {
@@ -323,63 +378,174 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
       }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 epilogue warps only
-    // Phase 2: coalesced epilogue -- warp w owns rows [32w, 32w+32); a row is written as BN/4 float4 by consecutive lanes
-    // (full 128-byte lines); bias / activation / mask operands are read with the same coalesced mapping.
-    if (!(e.debug & 1)) {
-      const bool vec_ok = ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0) &&
-                          (!e.mask_mode || (((e.ldm & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.mask_src) & 15) == 0)));
-      const bool add_bias = e.bias && (!e.accumulate || blockIdx.z == 0);
-#pragma unroll 1
-      for (int cc = lane * 4; cc < BN; cc += 128) {
-        const int n = n0 + cc;
-        if (n >= e.N) break;
-        const int nvalid = min(4, e.N - n);
-        float bv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-        if (add_bias) for (int j = 0; j < nvalid; ++j) bv[j] = e.bias[n + j];
-        float cs4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-          const int row = lg * 32 + r, m = m0 + row;
-          if (m >= e.M) break;
-          const float4 t = *reinterpret_cast<const float4*>(cs + row * CS_LD + cc);
-          float x[4] = {t.x + bv[0], t.y + bv[1], t.z + bv[2], t.w + bv[3]};
-          float* cp = e.C + (int64_t)m * e.ldc + n;
-          if (e.accumulate) {
-            for (int j = 0; j < nvalid; ++j) atomicAdd(cp + j, x[j]);
-            continue;
-          }
-          if (e.act == 1) { for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.0f); }
-          else if (e.act == 2) { for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]); }
-          if (e.mask_mode) {
-            const float* mp = e.mask_src + (int64_t)m * e.ldm + n;
-            float mv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            if (vec_ok && nvalid == 4) { const float4 q = *reinterpret_cast<const float4*>(mp); mv[0] = q.x; mv[1] = q.y; mv[2] = q.z; mv[3] = q.w; }
-            else for (int j = 0; j < nvalid; ++j) mv[j] = mp[j];
-            if (e.mask_mode == 1) { for (int j = 0; j < 4; ++j) x[j] = (mv[j] > 0.0f) ? x[j] : 0.0f; }
-            else { for (int j = 0; j < 4; ++j) x[j] *= (1.0f - mv[j] * mv[j]); }
-          }
-          if (vec_ok && nvalid == 4) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
-          else for (int j = 0; j < nvalid; ++j) cp[j] = x[j];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) cs4[j] += x[j];
-          if (e.Chi) {       // the consumers of C read these planes directly through TMA: no separate split pass
-            float h[4], l[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) split_tf32(x[j], h[j], l[j]);
-            float* hp = e.Chi + (int64_t)m * e.ldp + n; float* lp = e.Clo + (int64_t)m * e.ldp + n;
-            if (nvalid == 4) { *reinterpret_cast<float4*>(hp) = make_float4(h[0], h[1], h[2], h[3]); *reinterpret_cast<float4*>(lp) = make_float4(l[0], l[1], l[2], l[3]); }
-            else for (int j = 0; j < nvalid; ++j) { hp[j] = h[j]; lp[j] = l[j]; }
-          }
-        }
-        if (e.colsum && !e.accumulate) for (int j = 0; j < nvalid; ++j) atomicAdd(e.colsum + n + j, cs4[j]);
-      }
-    }
+    // Phase 2: coalesced epilogue -- warp w owns rows [32w, 32w+32)
+    if (!(e.debug & 1)) epilogue_rows(e, cs, CS_LD, lg * 32, 32, BN, m0, n0, lane);
   }
   tc_fence_before();
   __syncthreads();
   if (CL > 1) cluster_sync_all();        // nobody exits while a peer may still multicast into / arrive on this CTA
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------
+// 128 x 256 tile variant.  A 128x128 tile needs 64 KB of operand planes per 768 MMA clocks = 85 B/clk, above the
+// ~64 B/clk a B200 SM can ingest (profiles/experiments_r01.md), and its MMAs read shared memory at the full
+// 128 B/clk.  Doubling N amortises the A planes: 96 KB per 1536 clocks = 62 B/clk ingest, 96 B/clk smem reads.
+// TMEM: main (256 cols, single buffered) + corr (256 cols) = all 512 columns.  8 drain/epilogue warps (two per TMEM lane
+// quadrant, 128 columns each) keep the per-thread accumulator at 128 registers; setmaxnreg moves registers from the
+// producer / MMA warpgroup to them.  The drain of k-block kb runs under the 8 correction MMAs of kb (1024 clocks).
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TC256_THREADS = 384;       // WG0: warp 0 TMA, warp 1 MMA (+2 idle); WG1, WG2: drain / epilogue
+constexpr int TC256_BN = 256;
+constexpr int TC256_STAGES = 2;
+
+template <bool AMN, bool BMN>
+__global__ void __launch_bounds__(TC256_THREADS, 1)
+gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+                  const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const TcEpi e) {
+  constexpr int BN = TC256_BN, STAGES = TC256_STAGES;
+  using SM = TcSmem<BN, STAGES>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* main_full = bars + 2 * STAGES;
+  uint64_t* main_empty = bars + 2 * STAGES + 1;
+  uint64_t* corr_full = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 3);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * TC_BM, n0 = blockIdx.x * BN;
+  const int kb_begin = blockIdx.z * e.kb_per_split;
+  const int nkb = min(e.kb_per_split, e.kb_total - kb_begin);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(main_full, 1); mbar_init(main_empty, 8); mbar_init(corr_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_corr = tmem_base + BN;
+
+  if (warp < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    if (warp == 0 && lane == 0) {
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        mbar_expect_tx(&full[s], SM::STAGE_BYTES);
+        uint8_t* st = smem + s * SM::STAGE_BYTES;
+        const int k0 = (kb_begin + kb) * TC_BK;
+        if (!AMN) {
+          tma_load_2d(st, &tmAhi, &full[s], k0, m0);
+          tma_load_2d(st + SM::A_BYTES, &tmAlo, &full[s], k0, m0);
+        } else {
+#pragma unroll
+          for (int b = 0; b < TC_BM / 32; ++b) {
+            tma_load_2d(st + b * 4096, &tmAhi, &full[s], m0 + b * 32, k0);
+            tma_load_2d(st + SM::A_BYTES + b * 4096, &tmAlo, &full[s], m0 + b * 32, k0);
+          }
+        }
+        if (!BMN) {        // the B maps have 128-row boxes: two per plane
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            tma_load_2d(st + 2 * SM::A_BYTES + h * 16384, &tmBhi, &full[s], k0, n0 + h * 128);
+            tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES + h * 16384, &tmBlo, &full[s], k0, n0 + h * 128);
+          }
+        } else {
+#pragma unroll
+          for (int b = 0; b < BN / 32; ++b) {
+            tma_load_2d(st + 2 * SM::A_BYTES + b * 4096, &tmBhi, &full[s], n0 + b * 32, k0);
+            tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES + b * 4096, &tmBlo, &full[s], n0 + b * 32, k0);
+          }
+        }
+      }
+    } else if (warp == 1 && lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((AMN ? 1u : 0u) << 15) | ((BMN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      auto adesc = [](uint32_t base, int k) { return AMN ? make_smem_desc_mn(base + k * 1024) : make_smem_desc(base + k * 32); };
+      auto bdesc = [](uint32_t base, int k) { return BMN ? make_smem_desc_mn(base + k * 1024) : make_smem_desc(base + k * 32); };
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        mbar_wait(main_empty, (uint32_t)((kb & 1) ^ 1));       // drain of k-block kb-1 (runs under its correction MMAs)
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
+        const uint32_t a_hi = sa, a_lo = sa + SM::A_BYTES, b_hi = sa + 2 * SM::A_BYTES, b_lo = b_hi + SM::B_BYTES;
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k)
+          tc_mma_tf32(tmem_base, adesc(a_hi, k), bdesc(b_hi, k), idesc, k > 0 ? 1u : 0u);
+        tc_commit(main_full);
+        if (!(e.debug & 4))
+#pragma unroll
+        for (int k = 0; k < TC_BK / 8; ++k) {
+          tc_mma_tf32(tmem_corr, adesc(a_lo, k), bdesc(b_hi, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_mma_tf32(tmem_corr, adesc(a_hi, k), bdesc(b_lo, k), idesc, 1u);
+        }
+        tc_commit(&empty[s]);
+      }
+      tc_commit(corr_full);
+    }
+    __syncwarp();
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int lg = warp & 3;                 // TMEM lane quadrant
+    const int half = (warp - 4) >> 2;        // which 128 columns of the 256
+    const uint32_t lane_off = (uint32_t)(lg * 32) << 16;
+    float acc[128];
+#pragma unroll
+    for (int j = 0; j < 128; ++j) acc[j] = 0.0f;
+    for (int kb = 0; kb < nkb; ++kb) {
+      mbar_wait(main_full, (uint32_t)(kb & 1));
+      tc_fence_after();
+      if (!(e.debug & 2))
+#pragma unroll
+      for (int c = 0; c < 128; c += 32) {
+        float v[32];
+        tc_ld_32x32(tmem_base + lane_off + (uint32_t)(half * 128 + c), v);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[c + j] += v[j];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(main_empty);
+    }
+    mbar_wait(corr_full, 0);
+    tc_fence_after();
+    float* cs = reinterpret_cast<float*>(smem);
+    constexpr int CS_LD = BN + 4;
+    {
+      float* crow_s = cs + (lg * 32 + lane) * CS_LD + half * 128;
+#pragma unroll
+      for (int c = 0; c < 128; c += 32) {
+        float v[32];
+        tc_ld_32x32(tmem_corr + lane_off + (uint32_t)(half * 128 + c), v);
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(crow_s + c + j) = make_float4(e.alpha * (acc[c + j] + v[j]), e.alpha * (acc[c + j + 1] + v[j + 1]),
+                                                                   e.alpha * (acc[c + j + 2] + v[j + 2]), e.alpha * (acc[c + j + 3] + v[j + 3]));
+      }
+    }
+    asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps only
+    if (!(e.debug & 1)) epilogue_rows(e, cs, CS_LD, (warp - 4) * 16, 16, BN, m0, n0, lane);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
   }
 }
 
@@ -416,19 +582,45 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
-// 2D tensor map over a zero-padded plane [rows_p, cols_p] (cols contiguous); box = [box_rows x 32 cols], 128B swizzle
-static int make_map(CUtensorMap* tm, const float* base, int rows_p, int cols_p, int box_rows, bool mn_major = false) {
+// cuTensorMapEncodeTiled costs microseconds and the learner re-issues the same ~230 maps every minibatch: memoise.
+struct MapKey {
+  const void* base; int rows, cols; int64_t ld; int box_rows; int mn;
+  bool operator==(const MapKey& o) const { return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && mn == o.mn; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = (size_t)k.base;
+    h ^= (size_t)k.rows * 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    h ^= (size_t)k.cols * 0xC2B2AE3D27D4EB4Full + (h << 6) + (h >> 2);
+    h ^= (size_t)k.ld * 0x165667B19E3779F9ull + (size_t)k.box_rows * 31 + (size_t)k.mn;
+    return h;
+  }
+};
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash>& map_cache() { static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> c; return c; }
+
+static int encode_cached(CUtensorMap* tm, const float* base, int rows, int cols, int64_t ld, int box_rows, bool mn_major) {
+  MapKey k{base, rows, cols, ld, box_rows, mn_major ? 1 : 0};
+  auto& c = map_cache();
+  auto it = c.find(k);
+  if (it != c.end()) { memcpy(tm, &it->second, sizeof(CUtensorMap)); return ASE_OK; }
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return ASE_ERR_UNSUPPORTED; }
-  cuuint64_t gdim[2] = {(cuuint64_t)cols_p, (cuuint64_t)rows_p};
-  cuuint64_t gstr[1] = {(cuuint64_t)cols_p * sizeof(float)};
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
   cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d (plane %d x %d)", (int)r, rows_p, cols_p); return ASE_ERR_CUDA; }
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(%d x %d, ld %lld, box %d) failed with CUresult %d", rows, cols, (long long)ld, box_rows, (int)r); return ASE_ERR_CUDA; }
+  if (c.size() > 8192) c.clear();
+  c.emplace(k, *tm);
   return ASE_OK;
+}
+
+// 2D tensor map over a zero-padded plane [rows_p, cols_p] (cols contiguous); box = [box_rows x 32 cols], 128B swizzle
+static int make_map(CUtensorMap* tm, const float* base, int rows_p, int cols_p, int box_rows, bool mn_major = false) {
+  return encode_cached(tm, base, rows_p, cols_p, cols_p, box_rows, mn_major);
 }
 
 static inline int pad_to(int x, int m) { return (x + m - 1) / m * m; }
@@ -519,6 +711,36 @@ static int launch_tc_major(bool amn, bool bmn, const CUtensorMap& ah, const CUte
 
 // A-multicast clusters are OFF by default: measured on B200 (profiles/experiments_r01.md) they do not help -- the
 // mainloop is bound by the per-SM ingest port (~64 B/clk), which multicast does not relieve.  ASE_TC_CLUSTER=2|4 enables them.
+template <bool AMN, bool BMN>
+static int launch_tc256(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcEpi& e,
+                        int splits, cudaStream_t st) {
+  using SM = TcSmem<TC256_BN, TC256_STAGES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ASE_CUDA_OK(cudaFuncSetAttribute(gemm_tc256_kernel<AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(e.N, TC256_BN), ceil_div(e.M, TC_BM), splits);
+  const bool prof = g_prof.on;
+  if (prof) prof_mark(st);
+  gemm_tc256_kernel<AMN, BMN><<<grid, TC256_THREADS, SM::TOTAL, st>>>(ah, al, bh, bl, e);
+  if (prof) { prof_mark(st); g_prof.flops += 2.0 * (double)e.M * (double)e.N * (double)e.K; }
+  ASE_LAUNCH_OK();
+  return ASE_OK;
+}
+static int launch_tc256_major(bool amn, bool bmn, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
+                              const TcEpi& e, int splits, cudaStream_t st) {
+  if (!amn && !bmn) return launch_tc256<false, false>(ah, al, bh, bl, e, splits, st);
+  if (!amn && bmn) return launch_tc256<false, true>(ah, al, bh, bl, e, splits, st);
+  if (amn && !bmn) return launch_tc256<true, false>(ah, al, bh, bl, e, splits, st);
+  return launch_tc256<true, true>(ah, al, bh, bl, e, splits, st);
+}
+static int tc_tile256() {   // env ASE_TC_TILE256=0 keeps every GEMM on the 128x128 kernel
+  static int v = -1;
+  if (v < 0) { const char* d = getenv("ASE_TC_TILE256"); v = d ? atoi(d) : 1; }
+  return v;
+}
+
 static int tc_cluster() {
   static int v = -1;
   if (v < 0) { const char* d = getenv("ASE_TC_CLUSTER"); v = d ? atoi(d) : 1; if (v != 1 && v != 2 && v != 4) v = 1; }
@@ -576,22 +798,13 @@ static int resolve_operand(PlaneRegistry* reg, const float* ptr, int64_t ld, int
 
 // tensor map over a (sub-)view of a plane with TRUE extents: TMA zero-fills everything outside [rows, cols]
 static int make_view_map(CUtensorMap* tm, const float* base, int rows, int cols, int64_t ldp, int box_rows, bool mn_major) {
-  PFN_encodeTiled enc = get_encode();
-  if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return ASE_ERR_UNSUPPORTED; }
-  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ldp * sizeof(float)};
-  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(view %d x %d, ld %lld) failed with CUresult %d", rows, cols, (long long)ldp, (int)r); return ASE_ERR_CUDA; }
-  return ASE_OK;
+  return encode_cached(tm, base, rows, cols, ldp, box_rows, mn_major);
 }
 
 int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   const int BN = (p.N > 64) ? 128 : 64;
-  int CL = (BN == 128 && p.N > 128) ? tc_cluster() : 1;       // A-multicast groups need >= 2 N tiles
+  const bool use256 = tc_tile256() && p.N >= 384;               // 128x256 tiles (B maps keep 128-row boxes: two per stage)
+  int CL = (BN == 128 && p.N > 128 && !use256) ? tc_cluster() : 1;       // A-multicast groups need >= 2 N tiles
   if (CL == 4 && p.N <= 384) CL = 2;
   const int a_box = TC_BM / CL;
   const int Mp = pad_to(p.M, 128), Np = pad_to(p.N, 128), Kp = pad_to(p.K, TC_BK);
@@ -649,6 +862,7 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   splits = min(splits, e.kb_total);
   e.kb_per_split = ceil_div(e.kb_total, splits);
   splits = ceil_div(e.kb_total, e.kb_per_split);
+  if (use256) return launch_tc256_major(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
   if (BN == 128 && CL == 4) return launch_tc_major<128, 3, 4>(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
   if (BN == 128 && CL == 2) return launch_tc_major<128, 3, 2>(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
   if (BN == 128) return launch_tc_major<128, 3, 1>(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);

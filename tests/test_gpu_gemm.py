@@ -85,6 +85,27 @@ def test_tc_matches_fp64(a_trans, b_trans):
     _run(1, 1, 1, a_trans, b_trans, 1, tol=1e-5)
 
 
+@pytest.mark.parametrize('a_trans,b_trans', [(False, False), (False, True), (True, False), (True, True)])
+def test_tc_wide_tiles_128x256(a_trans, b_trans):
+    """N >= 384 runs on the 128x256-tile kernel (8 drain warps, single-buffered main accumulator)."""
+    _run(256, 512, 96, a_trans, b_trans, 1, tol=1e-5)
+    _run(300, 1400, 317, a_trans, b_trans, 1, lda_pad=3, tol=1e-5)      # ragged everything, 6 N tiles with a tail
+    _run(1000, 384, 1024, a_trans, b_trans, 1, bias=True, act=1, tol=1e-5)
+    _run(512, 1024, 2048, a_trans, b_trans, 1, mask_mode=1, tol=1e-5)    # long K: many main/corr hand-offs
+
+
+def test_tc_wide_tiles_split_k_and_colsum():
+    from ase_b200 import ops
+    _run(1024, 1024, 8192, True, True, 1, accumulate=True, split_k=3, tol=2e-5)
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn(700, 256, generator=g).cuda(); B = torch.randn(512, 256, generator=g).cuda()
+    cs = torch.zeros(512, device='cuda')
+    C = ops.gemm(A, B, backend=1, colsum_out=cs)
+    ref = A.double() @ B.double().t()
+    assert float((C.double() - ref).abs().max() / ref.abs().max()) < 1e-5
+    assert float((cs.double() - ref.sum(0)).abs().max() / ref.sum(0).abs().max()) < 1e-5
+
+
 def test_tc_epilogues_and_split_k():
     _run(512, 256, 512, False, False, 1, bias=True, act=1, tol=1e-5)
     _run(256, 128, 256, False, False, 1, bias=True, act=2, alpha=1.0 / 16, tol=3e-5)   # O(1) pre-activations
