@@ -735,6 +735,7 @@ static int launch_tc256_major(bool amn, bool bmn, const CUtensorMap& ah, const C
   if (amn && !bmn) return launch_tc256<true, false>(ah, al, bh, bl, e, splits, st);
   return launch_tc256<true, true>(ah, al, bh, bl, e, splits, st);
 }
+int gemm_tc_tile_n(int N);
 static int tc_tile256() {   // env ASE_TC_TILE256=0 keeps every GEMM on the 128x128 kernel
   static int v = -1;
   if (v < 0) { const char* d = getenv("ASE_TC_TILE256"); v = d ? atoi(d) : 1; }
@@ -746,6 +747,8 @@ static int tc_cluster() {
   if (v < 0) { const char* d = getenv("ASE_TC_CLUSTER"); v = d ? atoi(d) : 1; if (v != 1 && v != 2 && v != 4) v = 1; }
   return v;
 }
+
+int gemm_tc_tile_n(int N) { return (tc_tile256() && N >= 384) ? 256 : (N > 64 ? 128 : 64); }
 
 // ---------------------------------------------------------------------------------------------------------
 // Operand-plane registry: fp32 buffers whose TF32 hi/lo planes are kept next to them so that a tensor is split at

@@ -38,6 +38,7 @@ struct PlaneRegistry {
 int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg = nullptr);   // tcgen05 3xTF32 (gemm_tc.cu)
 bool gemm_tc_supported(const AseGemmParams& p);
 int64_t gemm_tc_workspace_bytes(int M, int N, int K);
+int gemm_tc_tile_n(int N);      // N extent of the output tile the tcgen05 backend will use for this N
 int gemm_dispatch(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg = nullptr);    // picks the backend named in p.backend (falls back to SIMT for shapes tc rejects)
 
 // ------------------------------------------------------------------ loss-side accumulators (doubles)

@@ -275,7 +275,7 @@ struct G {
     p.A = dZ; p.lda = ldz; p.a_trans = 1; p.B = X; p.ldb = ldx; p.b_trans = 1; p.C = GR + l.w; p.ldc = l.in;
     p.M = l.out; p.N = l.in; p.K = M; p.accumulate = 1;
     // split-K so that tiles x splits fills whole waves of the 148 SMs; every extra split adds one RED pass over dW
-    const int tiles = ceil_div(l.out, 128) * ceil_div(l.in, 128);
+    const int tiles = ceil_div(l.out, 128) * ceil_div(l.in, L.cfg.gemm_backend == 1 ? gemm_tc_tile_n(l.in) : 128);
     const int smax = max(1, min(16, M / 1024));
     int best = 1; double best_cost = 1e30;
     for (int s = 1; s <= smax; ++s) {
