@@ -145,6 +145,7 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* cs, i
   const bool vec_ok = ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0) &&
                       (!e.mask_mode || (((e.ldm & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.mask_src) & 15) == 0)));
   const bool add_bias = e.bias && (!e.accumulate || blockIdx.z == 0);
+  const bool pvec = e.Chi && ((e.ldp & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.Chi) & 15) == 0) && ((reinterpret_cast<uintptr_t>(e.Clo) & 15) == 0);
 #pragma unroll 1
   for (int cc = lane * 4; cc < BNT; cc += 128) {
     const int n = n0 + cc;
@@ -183,7 +184,7 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* cs, i
 #pragma unroll
         for (int j = 0; j < 4; ++j) split_tf32(x[j], h[j], l[j]);
         float* hp = e.Chi + (int64_t)m * e.ldp + n; float* lp = e.Clo + (int64_t)m * e.ldp + n;
-        if (nvalid == 4) { *reinterpret_cast<float4*>(hp) = make_float4(h[0], h[1], h[2], h[3]); *reinterpret_cast<float4*>(lp) = make_float4(l[0], l[1], l[2], l[3]); }
+        if (pvec && nvalid == 4) { *reinterpret_cast<float4*>(hp) = make_float4(h[0], h[1], h[2], h[3]); *reinterpret_cast<float4*>(lp) = make_float4(l[0], l[1], l[2], l[3]); }
         else for (int j = 0; j < nvalid; ++j) { hp[j] = h[j]; lp[j] = l[j]; }
       }
     }
@@ -766,6 +767,14 @@ void PlaneRegistry::add(const float* base, int64_t capacity, float* hi, float* l
   x.base = base; x.capacity = capacity; x.hi = hi; x.lo = lo; x.plane_capacity = plane_capacity;
   x.ld = 0; x.rows = x.cols = 0; x.ldp = 0; x.valid = false;
 }
+PlaneBuf* PlaneRegistry::declare(const float* base, int64_t ld, int rows, int cols) {
+  PlaneBuf* x = find(base);
+  if (!x || x->base != base) return nullptr;
+  const int64_t ldp = (cols + 3) / 4 * 4;
+  if ((int64_t)rows * ldp > x->plane_capacity) { x->valid = false; return nullptr; }
+  x->ld = ld; x->rows = rows; x->cols = cols; x->ldp = ldp; x->valid = true;
+  return x;
+}
 void PlaneRegistry::invalidate(const float* p) { if (PlaneBuf* x = find(p)) x->valid = false; }
 void PlaneRegistry::invalidate_range(const float* lo_, const float* hi_) {
   for (int i = 0; i < n; ++i) if (b[i].base >= lo_ && b[i].base < hi_) b[i].valid = false;
@@ -854,7 +863,7 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
         e.Chi = x->hi; e.Clo = x->lo; e.ldp = x->ldp;
       } else if (x->valid && x->ld == p.ldc) {
         const int64_t off = p.C - x->base, r0 = off / x->ld, c0 = off - r0 * x->ld;
-        if (!(c0 & 3) && r0 + p.M <= x->rows && c0 + p.N <= x->cols) { e.Chi = x->hi + r0 * x->ldp + c0; e.Clo = x->lo + r0 * x->ldp + c0; e.ldp = x->ldp; }
+        if (r0 + p.M <= x->rows && c0 + p.N <= x->cols) { e.Chi = x->hi + r0 * x->ldp + c0; e.Clo = x->lo + r0 * x->ldp + c0; e.ldp = x->ldp; }
         else x->valid = false;
       } else x->valid = false;
     }

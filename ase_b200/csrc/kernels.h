@@ -8,7 +8,7 @@ namespace ase {
 
 // ------------------------------------------------------------------ RunningMeanStd
 struct RmsBatchList { const float* x[3]; int64_t ld[3]; int rows; };
-struct RmsDst { float* y[3]; int64_t ld[3]; };
+struct RmsDst { float* y[3]; int64_t ld[3]; float* hi[3]; float* lo[3]; int64_t ldp[3]; };   // optional TF32 planes per destination
 int64_t rms_scratch_bytes(int cols, int rows, int nbatch);
 int rms_update_batches(const RmsBatchList& bl, int nbatch, int cols, double* mean, double* var, double* count, float eps,
                        int update, void* scratch, float** meanf_out, float** stdf_out, cudaStream_t st);
@@ -16,7 +16,8 @@ int rms_normalize(const float* x, int64_t ldx, int rows, int cols, const float* 
                   const RmsDst& dst, cudaStream_t st);
 int rms_apply(const float* x, int64_t ldx, int rows, int cols, const double* mean, const double* var, float eps, int unnorm,
               float* y, int64_t ldy, cudaStream_t st);
-int copy_cols(const float* x, int64_t ldx, int rows, int cols, float* y, int64_t ldy, cudaStream_t st);
+int copy_cols(const float* x, int64_t ldx, int rows, int cols, float* y, int64_t ldy, cudaStream_t st, float* hi = nullptr, float* lo = nullptr,
+              int64_t ldp = 0);
 
 // ------------------------------------------------------------------ GEMM backends
 int gemm_simt(const AseGemmParams& p, cudaStream_t st);
@@ -31,6 +32,8 @@ struct PlaneRegistry {
   static constexpr int MAX = 160;
   PlaneBuf b[MAX]; int n = 0;
   PlaneBuf* find(const float* p);
+  // a non-GEMM kernel is about to write the whole buffer [rows, cols] (ld) INCLUDING its planes: returns the entry (valid) or null
+  PlaneBuf* declare(const float* base, int64_t ld, int rows, int cols);
   void add(const float* base, int64_t capacity, float* hi, float* lo, int64_t plane_capacity);
   void invalidate(const float* p);
   void invalidate_range(const float* lo_, const float* hi_);

@@ -434,14 +434,25 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
     RmsDst d = {}; d.y[0] = L.Xa; d.ld[0] = L.ldx;
     if (L.has_div) { d.y[1] = L.Xa + (int64_t)B * L.ldx; d.ld[1] = L.ldx; }
     if (L.ase) { d.y[2] = L.Xc; d.ld[2] = L.ldx; }
+    // the normalise pass also writes the TF32 operand planes of the network inputs (the style / latent columns follow below)
+    PlaneBuf* pa = L.reg ? L.reg->declare(L.Xa, L.ldx, Ra, L.in0) : nullptr;
+    PlaneBuf* pc = (L.reg && L.ase) ? L.reg->declare(L.Xc, L.ldx, B, L.in0) : nullptr;
+    if (pa) { d.hi[0] = pa->hi; d.lo[0] = pa->lo; d.ldp[0] = pa->ldp; if (L.has_div) { d.hi[1] = pa->hi + (int64_t)B * pa->ldp; d.lo[1] = pa->lo + (int64_t)B * pa->ldp; d.ldp[1] = pa->ldp; } }
+    if (pc) { d.hi[2] = pc->hi; d.lo[2] = pc->lo; d.ldp[2] = pc->ldp; }
     RC(rms_normalize(mb->obs, c.obs_dim, B, c.obs_dim, mf, sf, 0, d, st));
-    g.inval(L.Xa); g.inval(L.Xc);
+    if (!pa) g.inval(L.Xa);
+    if (!pc) g.inval(L.Xc);
   }
   if (L.ase) {
-    RC(copy_cols(mb->ase_latents, Z, B, Z, L.Xc + c.obs_dim, L.ldx, st));
-    RC(copy_cols(mb->ase_latents, Z, B, Z, L.Zc, Z, st));
-    if (L.has_div) RC(copy_cols(mb->new_latents, Z, B, Z, L.Zc + (int64_t)B * Z, Z, st));
-    g.inval(L.Xc); g.inval(L.Zc);
+    PlaneBuf* pc = L.reg ? L.reg->find(L.Xc) : nullptr;
+    if (pc && !pc->valid) pc = nullptr;
+    RC(copy_cols(mb->ase_latents, Z, B, Z, L.Xc + c.obs_dim, L.ldx, st, pc ? pc->hi + c.obs_dim : nullptr, pc ? pc->lo + c.obs_dim : nullptr, pc ? pc->ldp : 0));
+    if (!pc) g.inval(L.Xc);
+    PlaneBuf* pz = L.reg ? L.reg->declare(L.Zc, Z, Ra, Z) : nullptr;
+    RC(copy_cols(mb->ase_latents, Z, B, Z, L.Zc, Z, st, pz ? pz->hi : nullptr, pz ? pz->lo : nullptr, pz ? pz->ldp : 0));
+    if (L.has_div) RC(copy_cols(mb->new_latents, Z, B, Z, L.Zc + (int64_t)B * Z, Z, st, pz ? pz->hi + (int64_t)B * pz->ldp : nullptr,
+                                pz ? pz->lo + (int64_t)B * pz->ldp : nullptr, pz ? pz->ldp : 0));
+    if (!pz) g.inval(L.Zc);
   }
   if (L.amp) {
     // three sequential updates: agent, replay, demo -- each batch normalised with the stats after ITS update
@@ -449,11 +460,13 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
     bl.ld[0] = bl.ld[1] = bl.ld[2] = c.amp_dim; bl.rows = Ba;
     float *mf, *sf;
     RC(rms_update_batches(bl, 3, c.amp_dim, s->amp_mean, s->amp_var, s->amp_count, c.rms_eps, mb->update_rms, L.rms_amp_scratch, &mf, &sf, st));
+    PlaneBuf* pd = L.reg ? L.reg->declare(L.Xd, L.amp_ld, 3 * Ba, c.amp_dim) : nullptr;
     for (int b = 0; b < 3; ++b) {
       RmsDst d = {}; d.y[0] = L.Xd + (int64_t)b * Ba * L.amp_ld; d.ld[0] = L.amp_ld;
+      if (pd) { d.hi[0] = pd->hi + (int64_t)b * Ba * pd->ldp; d.lo[0] = pd->lo + (int64_t)b * Ba * pd->ldp; d.ldp[0] = pd->ldp; }
       RC(rms_normalize(bl.x[b], c.amp_dim, Ba, c.amp_dim, mf + (int64_t)b * c.amp_dim, sf + (int64_t)b * c.amp_dim, 0, d, st));
     }
-    g.inval(L.Xd);
+    if (!pd) g.inval(L.Xd);
   }
 
   // ---- forward ------------------------------------------------------------------------------------------

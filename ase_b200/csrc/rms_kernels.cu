@@ -64,6 +64,15 @@ __global__ void rms_finalize_kernel(const double2* __restrict__ partial, int col
 
 __global__ void rms_count_add_kernel(double* count, double inc) { count[0] += inc; }
 
+__device__ __forceinline__ void split_tf32_rms(float x, float& hi, float& lo) {   // same split as gemm_tc.cu (operand planes)
+  uint32_t h, l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  const float rr = x - hi;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(rr));
+  lo = __uint_as_float(l);
+}
+
 // y = clamp((x-mean)/std, -5, 5) written to up to 3 destinations (unnorm: std*clamp(x,+-5)+mean)
 __global__ void __launch_bounds__(256)
 rms_normalize_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols,
@@ -75,19 +84,26 @@ rms_normalize_kernel(const float* __restrict__ x, int64_t ldx, int rows, int col
     float y;
     if (unnorm) y = stdf[c] * fminf(fmaxf(v, -5.0f), 5.0f) + meanf[c];
     else y = fminf(fmaxf((v - meanf[c]) / stdf[c], -5.0f), 5.0f);
+    float h = 0.0f, l = 0.0f;
+    if (dst.hi[0] || dst.hi[1] || dst.hi[2]) split_tf32_rms(y, h, l);
 #pragma unroll
-    for (int d = 0; d < 3; ++d)
+    for (int d = 0; d < 3; ++d) {
       if (dst.y[d]) dst.y[d][(int64_t)r * dst.ld[d] + c] = y;
+      if (dst.hi[d]) { dst.hi[d][(int64_t)r * dst.ldp[d] + c] = h; dst.lo[d][(int64_t)r * dst.ldp[d] + c] = l; }
+    }
   }
 }
 
 // just copy columns (used to place latents next to the normalised observations)
 __global__ void __launch_bounds__(256)
-copy_cols_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, float* __restrict__ y, int64_t ldy) {
+copy_cols_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, float* __restrict__ y, int64_t ldy,
+                 float* __restrict__ hi, float* __restrict__ lo, int64_t ldp) {
   const int64_t total = (int64_t)rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
-    y[(int64_t)r * ldy + c] = x[(int64_t)r * ldx + c];
+    const float v = x[(int64_t)r * ldx + c];
+    y[(int64_t)r * ldy + c] = v;
+    if (hi) { float h, l; split_tf32_rms(v, h, l); hi[(int64_t)r * ldp + c] = h; lo[(int64_t)r * ldp + c] = l; }
   }
 }
 
@@ -129,10 +145,10 @@ int rms_normalize(const float* x, int64_t ldx, int rows, int cols, const float* 
   return ASE_OK;
 }
 
-int copy_cols(const float* x, int64_t ldx, int rows, int cols, float* y, int64_t ldy, cudaStream_t st) {
+int copy_cols(const float* x, int64_t ldx, int rows, int cols, float* y, int64_t ldy, cudaStream_t st, float* hi, float* lo, int64_t ldp) {
   const int64_t total = (int64_t)rows * cols;
   const int blocks = (int)imin64((total + 255) / 256, 148 * 16);
-  copy_cols_kernel<<<blocks, 256, 0, st>>>(x, ldx, rows, cols, y, ldy);
+  copy_cols_kernel<<<blocks, 256, 0, st>>>(x, ldx, rows, cols, y, ldy, hi, lo, ldp);
   ASE_LAUNCH_OK();
   return ASE_OK;
 }
