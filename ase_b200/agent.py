@@ -3,6 +3,7 @@
     CommonAgent  learning/common_agent.py:25-564   (plain PPO; HRL high-level policy learner)
     AMPAgent     learning/amp_agent.py:21-628
     ASEAgent     learning/ase_agent.py:12-538
+    HRLAgent     learning/hrl_agent.py:24-268      (task training over a frozen ASE low-level controller)
 
 Same public surface (`play_steps`, `prepare_dataset`, `train_actor_critic` / `calc_gradients`, `train_epoch`,
 `train`, `get_full_state_weights` / `set_full_state_weights`, `train_result` keys) and the same config keys
@@ -125,7 +126,8 @@ class CommonAgent:
         hp = {k: config[k] for k in ('e_clip', 'critic_coef', 'entropy_coef', 'bounds_loss_coef', 'learning_rate') if k in config}
         sigma = np_['space']['continuous']['sigma_init'].get('val', 0.0)
         return dict(obs_dim=self.obs_shape[0], act_dim=self.actions_num, batch=self.minibatch_size, units=tuple(np_['mlp']['units']),
-                    hparams=hp, device=self.ppo_device, gemm_backend=config.get('gemm_backend', 1), sigma_init=sigma)
+                    hparams=hp, device=self.ppo_device, gemm_backend=config.get('gemm_backend', 1), sigma_init=sigma,
+                    mu_activation=getattr(self, '_mu_activation', 'None'))
 
     def _build_learner(self, config):
         kw = self._learner_kwargs(config)
@@ -605,3 +607,87 @@ class ASEAgent(AMPAgent):
     def prepare_dataset(self, batch_dict):
         super().prepare_dataset(batch_dict)
         self.dataset.values_dict['ase_latents'] = batch_dict['ase_latents']
+
+
+class HRLAgent(CommonAgent):
+    """learning/hrl_agent.py: a PPO high-level controller whose 64-d action is the latent of a FROZEN ASE low-level
+    controller, stepped `llc_steps` times per high-level step; reward = task_w * task + disc_w * LLC discriminator reward.
+    The HLC network applies tanh to mu (hrl_network_builder.py:26-29).  The LLC comes either as a ready ase_b200.Learner
+    (config['llc_learner']) or from the reference's pieces: config['llc_net_params'] (+ config['llc_checkpoint'], an
+    rl_games .pth such as ase/data/models/ase_llc_reallusion_sword_shield.pth)."""
+    kind = 'ppo'
+    _mu_activation = 'tanh'
+
+    def __init__(self, base_name, config):
+        self._latent_dim = int(config.get('latent_dim', config.get('llc_latent_dim', 64)))
+        super().__init__(base_name, config)
+        self._task_size = self.vec_env.env.task.get_task_obs_size()
+        self._llc_steps = config['llc_steps']
+        self._llc_disc_reward_scale = config.get('llc_disc_reward_scale', 2.0)
+        self._build_llc(config)
+
+    def _load_config_params(self, config):
+        self._task_reward_w = config['task_reward_w']
+        self._disc_reward_w = config['disc_reward_w']
+        self.actions_num = self._latent_dim            # hrl_agent.py:171-174 _setup_action_space
+
+    def _build_llc(self, config):
+        ln = config.get('llc_learner')
+        if ln is None:
+            np_ = config['llc_net_params']
+            amp_dim = self.env_info['amp_observation_space'].shape[0]
+            act = self.env_info['action_space'].shape[0]
+            ln = Learner('ase', self.obs_shape[0] - self._task_size, act, self.num_actors, amp_dim=amp_dim, latent_dim=self._latent_dim,
+                         amp_batch=max(2, self.num_actors), units=tuple(np_['mlp']['units']), disc_units=tuple(np_['disc']['units']),
+                         device=self.ppo_device, gemm_backend=config.get('gemm_backend', 1))
+            ckpt = config.get('llc_checkpoint')
+            if ckpt:
+                w = torch.load(ckpt, map_location='cpu', weights_only=True)
+                ln.load_state_dict(w['model'])
+                ln.set_stats_weights(w)
+            else:
+                ln.init_reference(seed=1)
+        for r in (ln.running_mean_std, ln.value_mean_std, ln.amp_input_mean_std):
+            r.eval()
+        self._llc = ln
+
+    def init_tensors(self):
+        super().init_tensors()
+        self.experience_buffer['disc_rewards'] = torch.zeros_like(self.experience_buffer['rewards'])
+        self.tensor_list += ['disc_rewards']
+
+    def _compute_llc_action(self, obs, actions):
+        """hrl_agent.py:231-240: z = normalize(HLC action); LLC actor mean on the humanoid part of the observation."""
+        llc_obs = obs[..., :obs.shape[-1] - self._task_size].contiguous()
+        z = torch.nn.functional.normalize(actions, dim=-1)
+        mu, _ = self._llc.eval_actor_critic(llc_obs, z, want_value=False)
+        return torch.clamp(mu, -1.0, 1.0)
+
+    def env_step(self, actions):
+        """hrl_agent.py:45-82."""
+        actions = torch.clamp(actions, -1.0, 1.0)
+        obs = self.obs['obs']
+        rewards = disc_rewards = done_count = terminate_count = 0.0
+        for _ in range(self._llc_steps):
+            llc_actions = self._compute_llc_action(obs, actions)
+            obs, curr_rewards, curr_dones, infos = self.vec_env.step(llc_actions)
+            rewards = rewards + curr_rewards
+            done_count = done_count + curr_dones.float()
+            terminate_count = terminate_count + infos['terminate'].float()
+            logits, _ = self._llc.eval_disc_enc(infos['amp_obs'], want_enc=False)
+            dr, _, _ = ops.amp_rewards(logits, None, None, self._llc_disc_reward_scale)
+            disc_rewards = disc_rewards + dr
+        rewards = rewards / self._llc_steps
+        disc_rewards = disc_rewards / self._llc_steps
+        infos = dict(infos)
+        infos['terminate'] = (terminate_count > 0).to(torch.uint8)
+        infos['disc_rewards'] = disc_rewards
+        return {'obs': obs}, rewards.unsqueeze(1), (done_count > 0).to(torch.uint8), infos
+
+    def _extra_buffer_writes(self, n, res, infos):
+        self.experience_buffer['disc_rewards'][n] = infos['disc_rewards']
+
+    def _final_rewards(self):
+        """hrl_agent.py:150-152,243-249 _combine_rewards."""
+        eb = self.experience_buffer
+        return self._task_reward_w * eb['rewards'] + self._disc_reward_w * eb['disc_rewards'], {}

@@ -45,7 +45,24 @@ AMP_HUMANOID = {   # amp_humanoid.yaml
 }
 
 
+HRL_HUMANOID = {   # hrl_humanoid.yaml (HumanoidHeading / Location / Reach / Strike task training over a frozen LLC)
+    'net_params': {
+        'separate': True,
+        'space': {'continuous': {'mu_activation': 'None', 'sigma_activation': 'None', 'mu_init': {'name': 'default'},
+                                 'sigma_init': {'name': 'const_initializer', 'val': -2.9}, 'fixed_sigma': True, 'learn_sigma': False}},
+        'mlp': {'units': [1024, 512], 'activation': 'relu'},
+    },
+    'llc_net_params': ASE_HUMANOID['net_params'], 'latent_dim': 64,
+    'name': 'Humanoid', 'env_name': 'rlgpu', 'multi_gpu': False, 'ppo': True, 'mixed_precision': False,
+    'normalize_input': True, 'normalize_value': True, 'reward_shaper': {'scale_value': 1}, 'normalize_advantage': True,
+    'gamma': 0.99, 'tau': 0.95, 'learning_rate': 2e-5, 'lr_schedule': 'constant', 'max_epochs': 100000,
+    'save_frequency': 50, 'print_stats': True, 'grad_norm': 1.0, 'entropy_coef': 0.0, 'truncate_grads': False,
+    'e_clip': 0.2, 'horizon_length': 32, 'minibatch_size': 16384, 'mini_epochs': 6, 'critic_coef': 5, 'clip_value': False,
+    'bounds_loss_coef': 10, 'task_reward_w': 0.9, 'disc_reward_w': 0.1, 'llc_steps': 5,
+}
+
+
 def make(name, **overrides):
-    cfg = copy.deepcopy({'ase': ASE_HUMANOID, 'amp': AMP_HUMANOID}[name])
+    cfg = copy.deepcopy({'ase': ASE_HUMANOID, 'amp': AMP_HUMANOID, 'hrl': HRL_HUMANOID}[name])
     cfg.update(overrides)
     return cfg

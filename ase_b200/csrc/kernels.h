@@ -59,6 +59,7 @@ struct PpoHeadArgs {
   const float* z; const float* z2; int Z;
   int B, A;
   int has_div;
+  int mu_tanh;                         // mu = tanh(raw): gradients are taken to the pre-activation
   float e_clip, critic_coef, bounds_coef, div_bonus, div_tar;
   float* dmu;                          // same layout as mu
   float* dv;                           // [B]

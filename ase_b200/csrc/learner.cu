@@ -332,7 +332,7 @@ static int forward_actor_critic(const G& g, int rows_a, int rows_c) {
   if (rows_a > 0) {
     const float* x = L.Xa; int64_t ld = L.ldx;
     for (int k = 0; k < n.n_actor; ++k) { RC(g.fwd(x, ld, rows_a, n.actor[k], L.H[k], n.actor[k].out, 1)); x = L.H[k]; ld = n.actor[k].out; }
-    RC(g.fwd(x, ld, rows_a, n.mu, L.MU, c.act_dim, 0));
+    RC(g.fwd(x, ld, rows_a, n.mu, L.MU, c.act_dim, c.mu_activation == 2 ? 2 : 0));
   }
   if (rows_c > 0) {
     const float* x = L.Xc; int64_t ld = L.ldx;
@@ -480,7 +480,7 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
     a.old_mu = mb->old_mu; a.old_sigma = mb->old_sigma; a.returns = mb->returns; a.mask = L.amp ? mb->rand_action_mask : nullptr;
     a.logstd = s->logstd; a.z = mb->ase_latents; a.z2 = mb->new_latents; a.Z = Z; a.B = B; a.A = A; a.has_div = L.has_div ? 1 : 0;
     a.e_clip = c.e_clip; a.critic_coef = c.critic_coef; a.bounds_coef = c.bounds_loss_coef; a.div_bonus = c.amp_diversity_bonus;
-    a.div_tar = c.amp_diversity_tar; a.dmu = L.dMU; a.dv = L.dV; a.acc = L.acc;
+    a.div_tar = c.amp_diversity_tar; a.dmu = L.dMU; a.dv = L.dV; a.acc = L.acc; a.mu_tanh = c.mu_activation == 2 ? 1 : 0;
     RC(launch_ppo_head(a, st));
   }
   if (L.amp) RC(launch_disc_head(L.LOGIT, Ba, c.disc_coef, L.dLOGIT, L.acc, out->disc_agent_logit, out->disc_demo_logit, st));

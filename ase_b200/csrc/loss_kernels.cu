@@ -92,6 +92,7 @@ ppo_head_kernel(PpoHeadArgs a) {
         if (mu[j] >= -1.0f && mu[j] <= 1.0f) g += coef_div * d;
         dmu2[j] = (mu2[j] >= -1.0f && mu2[j] <= 1.0f) ? -coef_div * d : 0.0f;
       }
+      if (a.mu_tanh) g *= (1.0f - mu[j] * mu[j]);
       dmu[j] = g;
     }
     if (lane == 0) {

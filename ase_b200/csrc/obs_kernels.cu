@@ -156,9 +156,78 @@ amp_obs_build_kernel(AseAmpObsBuildParams p, AmpTables tb) {
   }
 }
 
+// utils/torch_utils.py:130-141 heading quaternion (not inverted)
+__device__ __forceinline__ Quat calc_heading_quat(const Quat q) {
+  const Vec3 ex = {1.0f, 0.0f, 0.0f};
+  const Vec3 d = quat_rotate(q, ex);
+  const float heading = atan2f(d.y, d.x);
+  const Vec3 ez = {0.0f, 0.0f, 1.0f};
+  return quat_from_angle_axis(heading, ez);
+}
+
+// env/tasks/humanoid_heading.py:232-248
+__global__ void __launch_bounds__(128)
+heading_obs_kernel(const float* __restrict__ root, int64_t rs, const float* __restrict__ tar_dir, const float* __restrict__ tar_speed,
+                   const float* __restrict__ face, int n, float* __restrict__ obs, int64_t ld, int col0) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const float* r = root + (int64_t)e * rs;
+  const Quat q = {r[3], r[4], r[5], r[6]};
+  const Quat hq = calc_heading_quat_inv(q);
+  const Vec3 td = {tar_dir[2 * e], tar_dir[2 * e + 1], 0.0f}, fd = {face[2 * e], face[2 * e + 1], 0.0f};
+  const Vec3 ltd = quat_rotate(hq, td), lfd = quat_rotate(hq, fd);
+  float* o = obs + (int64_t)e * ld + col0;
+  o[0] = ltd.x; o[1] = ltd.y; o[2] = tar_speed[e]; o[3] = lfd.x; o[4] = lfd.y;
+}
+
+// env/tasks/humanoid_heading.py:250-285
+__global__ void __launch_bounds__(128)
+heading_reward_kernel(const float* __restrict__ pos, int64_t ps, const float* __restrict__ prev, int64_t pps, const float* __restrict__ rot,
+                      int64_t rs, const float* __restrict__ tar_dir, const float* __restrict__ tar_speed, const float* __restrict__ face,
+                      float dt, int n, float* __restrict__ reward) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n) return;
+  const float* p = pos + (int64_t)e * ps; const float* pp = prev + (int64_t)e * pps; const float* r = rot + (int64_t)e * rs;
+  const float vx = (p[0] - pp[0]) / dt, vy = (p[1] - pp[1]) / dt;
+  const float tx = tar_dir[2 * e], ty = tar_dir[2 * e + 1];
+  const float tar_dir_speed = tx * vx + ty * vy;
+  const float tangent_speed = (vx - tar_dir_speed * tx) + (vy - tar_dir_speed * ty);
+  const float verr = tar_speed[e] - tar_dir_speed;
+  float dir_reward = expf(-0.25f * (verr * verr + 0.1f * tangent_speed * tangent_speed));
+  if (tar_dir_speed <= 0.0f) dir_reward = 0.0f;
+  const Quat q = {r[0], r[1], r[2], r[3]};
+  const Quat hq = calc_heading_quat(q);
+  const Vec3 ex = {1.0f, 0.0f, 0.0f};
+  const Vec3 fdir = quat_rotate(hq, ex);
+  const float facing = fmaxf(face[2 * e] * fdir.x + face[2 * e + 1] * fdir.y, 0.0f);
+  reward[e] = 0.7f * dir_reward + 0.3f * facing;
+}
+
 }  // namespace ase
 
 using namespace ase;
+
+extern "C" int ase_heading_obs(const float* root_states, int64_t root_stride, const float* tar_dir, const float* tar_speed,
+                               const float* tar_face_dir, int num_envs, float* obs, int64_t obs_ld, int obs_col0, void* stream) {
+  ASE_CHECK_ARG(root_states && tar_dir && tar_speed && tar_face_dir && obs, "ase_heading_obs: null pointer");
+  if (num_envs <= 0) return ASE_OK;
+  heading_obs_kernel<<<ceil_div(num_envs, 128), 128, 0, (cudaStream_t)stream>>>(root_states, root_stride, tar_dir, tar_speed, tar_face_dir,
+                                                                                 num_envs, obs, obs_ld, obs_col0);
+  ASE_LAUNCH_OK();
+  return ASE_OK;
+}
+
+extern "C" int ase_heading_reward(const float* root_pos, int64_t root_pos_stride, const float* prev_root_pos, int64_t prev_stride,
+                                  const float* root_rot, int64_t rot_stride, const float* tar_dir, const float* tar_speed,
+                                  const float* tar_face_dir, float dt, int num_envs, float* reward, void* stream) {
+  ASE_CHECK_ARG(root_pos && prev_root_pos && root_rot && tar_dir && tar_speed && tar_face_dir && reward, "ase_heading_reward: null pointer");
+  if (num_envs <= 0) return ASE_OK;
+  heading_reward_kernel<<<ceil_div(num_envs, 128), 128, 0, (cudaStream_t)stream>>>(root_pos, root_pos_stride, prev_root_pos, prev_stride,
+                                                                                    root_rot, rot_stride, tar_dir, tar_speed, tar_face_dir, dt,
+                                                                                    num_envs, reward);
+  ASE_LAUNCH_OK();
+  return ASE_OK;
+}
 
 extern "C" int ase_obs_build(const AseObsBuildParams* p, void* stream) {
   ASE_CHECK_ARG(p && p->body_state && p->obs, "ase_obs_build: null pointer");

@@ -58,7 +58,7 @@ def _aligned_bytes(nbytes, device, align=1024):
 class Learner:
     def __init__(self, kind, obs_dim, act_dim, batch, amp_dim=0, latent_dim=0, amp_batch=0, units=(1024, 1024, 512),
                  disc_units=(1024, 1024, 512), style_units=(512, 256), hparams=None, device='cuda', gemm_backend=0,
-                 sigma_init=-2.9):
+                 sigma_init=-2.9, mu_activation='None'):
         assert kind in KINDS
         self.kind = kind
         self.device = torch.device(device)
@@ -83,6 +83,7 @@ class Learner:
             cfg.amp_diversity_bonus = 0.0
         cfg.lr = float(hp['learning_rate'])
         cfg.gemm_backend = int(gemm_backend)
+        cfg.mu_activation = 2 if mu_activation == 'tanh' else 0     # HRLBuilder.Network.forward: norm_mu = tanh(mu)
         self.cfg = cfg
         self.batch, self.amp_batch = batch, cfg.amp_batch
         self.obs_dim, self.act_dim, self.amp_dim, self.latent_dim = obs_dim, act_dim, cfg.amp_dim, cfg.latent_dim

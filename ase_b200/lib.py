@@ -47,7 +47,7 @@ class LearnerConfig(C.Structure):
                 ('e_clip', f32), ('critic_coef', f32), ('entropy_coef', f32), ('bounds_loss_coef', f32),
                 ('disc_coef', f32), ('disc_logit_reg', f32), ('disc_grad_penalty', f32), ('disc_weight_decay', f32),
                 ('enc_coef', f32), ('amp_diversity_bonus', f32), ('amp_diversity_tar', f32),
-                ('lr', f32), ('beta1', f32), ('beta2', f32), ('adam_eps', f32), ('rms_eps', f32), ('gemm_backend', i32)]
+                ('lr', f32), ('beta1', f32), ('beta2', f32), ('adam_eps', f32), ('rms_eps', f32), ('gemm_backend', i32), ('mu_activation', i32)]
 
 
 class LearnerState(C.Structure):
@@ -67,7 +67,7 @@ class TrainResult(C.Structure):
 
 # every symbol declared in include/ase_b200.h (tests/test_abi.py checks the two lists agree)
 EXPORTS = ['ase_abi_version', 'ase_last_error', 'ase_launch_count', 'ase_obs_build', 'ase_amp_obs_build',
-           'ase_rms_scratch_bytes', 'ase_rms_update', 'ase_rms_apply', 'ase_gae', 'ase_amp_rewards', 'ase_policy_sample', 'ase_adv_normalize',
+           'ase_rms_scratch_bytes', 'ase_rms_update', 'ase_rms_apply', 'ase_gae', 'ase_amp_rewards', 'ase_heading_obs', 'ase_heading_reward', 'ase_policy_sample', 'ase_adv_normalize',
            'ase_gemm', 'ase_gemm_tc_workspace_bytes', 'ase_gemm_tc_profile', 'ase_gemm_tc_profile_read', 'ase_learner_num_params', 'ase_learner_param_desc',
            'ase_learner_arena_floats', 'ase_learner_workspace_bytes', 'ase_learner_create', 'ase_learner_destroy', 'ase_learner_params_changed',
            'ase_learner_calc_gradients', 'ase_learner_adam_step', 'ase_learner_eval_actor_critic',
@@ -93,6 +93,8 @@ def _load():
     lib.ase_rms_apply.argtypes = [vp, i64, i32, i32, vp, vp, f32, i32, vp, i64, vp]
     lib.ase_gae.argtypes = [vp, vp, vp, vp, i32, i32, f32, f32, vp, vp, vp]
     lib.ase_amp_rewards.argtypes = [vp, vp, vp, i32, i32, f32, f32, vp, f32, f32, f32, vp, vp, vp, vp]
+    lib.ase_heading_obs.argtypes = [vp, i64, vp, vp, vp, i32, vp, i64, i32, vp]
+    lib.ase_heading_reward.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, vp, f32, i32, vp, vp]
     lib.ase_policy_sample.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
     lib.ase_adv_normalize.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     lib.ase_obs_build.argtypes = [C.POINTER(ObsBuildParams), vp]

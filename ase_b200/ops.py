@@ -138,6 +138,29 @@ def amp_rewards(disc_logits, enc_pred=None, latents=None, disc_scale=2.0, enc_sc
     return dr, er, comb
 
 
+def compute_heading_observations(root_states, tar_dir, tar_speed, tar_face_dir, out=None, col0=0):
+    """env/tasks/humanoid_heading.py:232-248 -> [N,5] (or written into out[:, col0:col0+5])."""
+    n = root_states.shape[0]
+    assert root_states.stride(1) == 1
+    tar_dir = _f32c(tar_dir, 'tar_dir'); tar_speed = _f32c(tar_speed, 'tar_speed'); tar_face_dir = _f32c(tar_face_dir, 'tar_face_dir')
+    if out is None:
+        out = torch.empty(n, 5, device=root_states.device, dtype=torch.float32)
+    check(lib.ase_heading_obs(_p(root_states), root_states.stride(0), _p(tar_dir), _p(tar_speed), _p(tar_face_dir), n, _p(out),
+                              out.stride(0), col0, _stream()), 'ase_heading_obs')
+    return out
+
+
+def compute_heading_reward(root_pos, prev_root_pos, root_rot, tar_dir, tar_speed, tar_face_dir, dt):
+    """env/tasks/humanoid_heading.py:250-285 -> [N]."""
+    n = root_pos.shape[0]
+    assert root_pos.stride(1) == 1 and prev_root_pos.stride(1) == 1 and root_rot.stride(1) == 1
+    tar_dir = _f32c(tar_dir, 'tar_dir'); tar_speed = _f32c(tar_speed, 'tar_speed'); tar_face_dir = _f32c(tar_face_dir, 'tar_face_dir')
+    r = torch.empty(n, device=root_pos.device, dtype=torch.float32)
+    check(lib.ase_heading_reward(_p(root_pos), root_pos.stride(0), _p(prev_root_pos), prev_root_pos.stride(0), _p(root_rot), root_rot.stride(0),
+                                 _p(tar_dir), _p(tar_speed), _p(tar_face_dir), float(dt), n, _p(r), _stream()), 'ase_heading_reward')
+    return r
+
+
 def policy_sample(mu, logstd, noise, rand_mask=None):
     """Eval-mode Gaussian head + eps-greedy override (amp_agent.py:139-169) -> (actions, neglogpacs, sigmas)."""
     rows, a = mu.shape

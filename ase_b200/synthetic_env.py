@@ -19,25 +19,31 @@ class _Box:
 
 
 class _Task:
-    def __init__(self, n, device):
+    def __init__(self, n, device, task_obs_size=0):
         self.num_envs = n
         self.progress_buf = torch.zeros(n, dtype=torch.long, device=device)
         self.viewer = None
+        self._task_obs_size = task_obs_size
+
+    def get_task_obs_size(self):
+        return self._task_obs_size
 
 
 class SyntheticHumanoidEnv:
     NUM_BODIES, NUM_DOFS, AMP_STEPS, AMP_STEP_DIM = 17, 31, 10, 140
 
     def __init__(self, num_envs, device='cuda', seed=0, pool=8, state_source='device', done_prob=1.0 / 300.0,
-                 local_root_obs=True, root_height_obs=True, demo_pool=8192):
+                 local_root_obs=True, root_height_obs=True, demo_pool=8192, heading_task=False, dt=1.0 / 30.0):
         self.device = torch.device(device)
         self.num_envs = num_envs
         self.local_root_obs, self.root_height_obs = local_root_obs, root_height_obs
         self.state_source = state_source
         self.done_prob = done_prob
-        self.task = _Task(num_envs, self.device)
+        self.heading_task, self.dt = heading_task, dt
+        self.task = _Task(num_envs, self.device, 5 if heading_task else 0)     # HumanoidHeading: 5 task-obs floats
         self.env = self                      # agents reach vec_env.env.task / vec_env.env.fetch_amp_obs_demo
-        self.num_obs = 1 + 16 * 3 + 17 * 6 + 17 * 3 + 17 * 3
+        self.num_humanoid_obs = 1 + 16 * 3 + 17 * 6 + 17 * 3 + 17 * 3
+        self.num_obs = self.num_humanoid_obs + (5 if heading_task else 0)
         self.num_amp_obs = self.AMP_STEPS * self.AMP_STEP_DIM
         self.observation_space = _Box(-np.inf * np.ones(self.num_obs), np.inf * np.ones(self.num_obs))
         self.amp_observation_space = _Box(-np.inf * np.ones(self.num_amp_obs), np.inf * np.ones(self.num_amp_obs))
@@ -78,7 +84,15 @@ class SyntheticHumanoidEnv:
             dbody = dbody + 0.01 * torch.randn(dbody.shape, device=self.device, generator=self._gen)
             dbody[:, :, 3:7] = torch.nn.functional.normalize(dbody[:, :, 3:7], dim=-1)
         self._demo_pool = self._demo_pool.view(dn, -1)
+        if heading_task:     # humanoid_heading.py:60-76 target direction / speed / facing direction per env
+            th = torch.rand(num_envs, generator=g) * 6.2831853; fh = torch.rand(num_envs, generator=g) * 6.2831853
+            self._tar_dir = torch.stack([torch.cos(th), torch.sin(th)], dim=-1).to(self.device)
+            self._tar_face_dir = torch.stack([torch.cos(fh), torch.sin(fh)], dim=-1).to(self.device)
+            self._tar_speed = (1.0 + 4.0 * torch.rand(num_envs, generator=g)).to(self.device)
+            self._prev_root_pos = torch.zeros(num_envs, 3, device=self.device)
         self._load_state()
+        if heading_task:
+            self._prev_root_pos.copy_(self._body[:, 0, 0:3])
         self._compute_observations(shift=False)
         self._amp_obs_buf[:, 1:] = self._amp_obs_buf[:, 0:1]
 
@@ -100,14 +114,22 @@ class SyntheticHumanoidEnv:
     def _compute_observations(self, shift, env_ids=None):
         D = self.NUM_DOFS
         ops.compute_humanoid_observations_max(self._body, self.local_root_obs, self.root_height_obs, out=self.obs_buf, env_ids=env_ids)
+        if self.heading_task:      # humanoid_amp_task.py:51-64: task obs appended behind the humanoid features
+            ops.compute_heading_observations(self._body[:, 0], self._tar_dir, self._tar_speed, self._tar_face_dir, out=self.obs_buf,
+                                             col0=self.num_humanoid_obs)
         ops.build_amp_observations(self._body, self._dof[:, :D], self._dof[:, D:], self._amp_obs_buf, self.local_root_obs,
                                    self.root_height_obs, shift_history=shift, env_ids=env_ids)
 
     def step(self, actions):
         """base_task.py:119-137: physics (bypassed: next synthetic state) then post_physics_step."""
+        if self.heading_task:
+            self._prev_root_pos.copy_(self._body[:, 0, 0:3])
         self._load_state()
         self.task.progress_buf += 1
         self._compute_observations(shift=True)
+        if self.heading_task:
+            self.rew_buf = ops.compute_heading_reward(self._body[:, 0, 0:3], self._prev_root_pos, self._body[:, 0, 3:7], self._tar_dir,
+                                                      self._tar_speed, self._tar_face_dir, self.dt)
         r = torch.rand(self.num_envs, device=self.device, generator=self._gen)
         self.reset_buf = (r < self.done_prob).to(torch.uint8)
         self._terminate_buf = (r < 0.5 * self.done_prob).to(torch.uint8)        # terminate is a subset of dones

@@ -108,6 +108,15 @@ int ase_amp_rewards(const float* disc_logits, const float* enc_pred, const float
                     int rows, float disc_scale, float enc_scale,
                     const float* task_rewards, float task_w, float disc_w, float enc_w,
                     float* disc_r, float* enc_r, float* combined, void* stream);
+/* HRL heading task (config 5): compute_heading_observations / compute_heading_reward, env/tasks/humanoid_heading.py:232-285.
+ * root_states [N, 13] rows with stride root_stride; tar_dir / tar_face_dir [N,2]; tar_speed [N]; task_obs [N, 5] written at
+ * obs + obs_col0 with row stride obs_ld (so it can land behind the 253 humanoid features, humanoid_amp_task.py:51-64). */
+int ase_heading_obs(const float* root_states, int64_t root_stride, const float* tar_dir, const float* tar_speed,
+                    const float* tar_face_dir, int num_envs, float* obs, int64_t obs_ld, int obs_col0, void* stream);
+int ase_heading_reward(const float* root_pos, int64_t root_pos_stride, const float* prev_root_pos, int64_t prev_stride,
+                       const float* root_rot, int64_t rot_stride, const float* tar_dir, const float* tar_speed,
+                       const float* tar_face_dir, float dt, int num_envs, float* reward, void* stream);
+
 /* Gaussian head in eval mode (rl_games ModelA2CContinuousLogStd.forward, is_train False) + the eps-greedy
  * override of get_action_values (amp_agent.py:164-167): a = mu + exp(logstd)*noise, neglogp(a); rows whose
  * rand_mask is 0 act deterministically (a := mu) but keep the sampled action's neglogp, as the reference does.
@@ -178,6 +187,7 @@ typedef struct {
   float lr, beta1, beta2, adam_eps;
   float rms_eps;      /* 1e-5 */
   int gemm_backend;   /* 0 SIMT, 1 tcgen05 3xTF32 */
+  int mu_activation;  /* 0 none (AMP/ASE), 2 tanh (HRL high-level policy, hrl_network_builder.py:26-29) */
 } AseLearnerConfig;
 
 /* Parameter arena: one flat fp32 buffer; tensor i (in the reference's model.parameters() order without

@@ -149,6 +149,38 @@ def build_amp_observations(root_pos, root_rot, root_vel, root_ang_vel, dof_pos, 
     return torch.cat([h, rr, lv, lw, dof_to_obs(dof_pos, dof_offsets), dof_vel, lk], dim=-1)
 
 
+def calc_heading_quat(q):
+    """utils/torch_utils.py:130-141."""
+    ex = torch.zeros_like(q[..., :3]); ex[..., 0] = 1
+    d = quat_rotate(q, ex)
+    heading = torch.atan2(d[..., 1], d[..., 0])
+    ez = torch.zeros_like(q[..., :3]); ez[..., 2] = 1
+    return quat_from_angle_axis(heading, ez)
+
+
+def compute_heading_observations(root_states, tar_dir, tar_speed, tar_face_dir):
+    """env/tasks/humanoid_heading.py:232-248 -> [N,5]."""
+    hq = calc_heading_quat_inv(root_states[:, 3:7])
+    z = torch.zeros_like(tar_dir[..., 0:1])
+    ltd = quat_rotate(hq, torch.cat([tar_dir, z], dim=-1))[..., 0:2]
+    lfd = quat_rotate(hq, torch.cat([tar_face_dir, z], dim=-1))[..., 0:2]
+    return torch.cat([ltd, tar_speed.unsqueeze(-1), lfd], dim=-1)
+
+
+def compute_heading_reward(root_pos, prev_root_pos, root_rot, tar_dir, tar_speed, tar_face_dir, dt):
+    """env/tasks/humanoid_heading.py:250-285."""
+    root_vel = (root_pos - prev_root_pos) / dt
+    tar_dir_speed = (tar_dir * root_vel[..., :2]).sum(-1)
+    tangent_speed = (root_vel[..., :2] - tar_dir_speed.unsqueeze(-1) * tar_dir).sum(-1)
+    verr = tar_speed - tar_dir_speed
+    dir_reward = torch.exp(-0.25 * (verr * verr + 0.1 * tangent_speed * tangent_speed))
+    dir_reward = torch.where(tar_dir_speed <= 0, torch.zeros_like(dir_reward), dir_reward)
+    ex = torch.zeros_like(root_pos); ex[..., 0] = 1.0
+    facing = quat_rotate(calc_heading_quat(root_rot), ex)
+    facing_reward = torch.clamp_min((tar_face_dir * facing[..., 0:2]).sum(-1), 0.0)
+    return 0.7 * dir_reward + 0.3 * facing_reward
+
+
 def amp_hist_step(amp_buf, new_frame):
     """env/tasks/humanoid_amp.py:248-275: shift history by one slot, newest frame at slot 0.
     amp_buf [N,S,F] (modified in place), new_frame [N,F]."""
@@ -295,14 +327,16 @@ def eval_style(p, z):
     return torch.tanh(F.linear(h, p['actor_mlp._style_dense.weight'], p['actor_mlp._style_dense.bias']))
 
 
-def eval_actor(p, obs_n, z=None):
-    """ASE: ase_network_builder.py:123-144,305-324.  AMP: amp_network_builder.py:51-72.  -> mu."""
+def eval_actor(p, obs_n, z=None, mu_tanh=False):
+    """ASE: ase_network_builder.py:123-144,305-324.  AMP: amp_network_builder.py:51-72.  HRL high-level policy:
+    hrl_network_builder.py:26-29 (mu_tanh).  -> mu."""
     if is_ase(p):
         h = torch.cat([obs_n, eval_style(p, z)], dim=-1)
         h = _mlp(h, p, _layer_names(p, 'actor_mlp._dense_layers.', '.'))
     else:
         h = _mlp(obs_n, p, _layer_names(p, 'actor_mlp.', '.'))
-    return F.linear(h, p['mu.weight'], p['mu.bias'])
+    mu = F.linear(h, p['mu.weight'], p['mu.bias'])
+    return torch.tanh(mu) if mu_tanh else mu
 
 
 def eval_critic(p, obs_n, z=None):
@@ -437,7 +471,7 @@ def calc_gradients(st, d, cfg, new_z=None, apply_adam=True, world=1):
         mask = d['rand_action_mask']
         msum = mask.sum()
     z = d.get('ase_latents') if kind == 'ase' else None
-    mu = eval_actor(p, obs_n, z)
+    mu = eval_actor(p, obs_n, z, mu_tanh=cfg.get('mu_tanh', False))
     logstd = mu * 0.0 + p['sigma']
     sigma = torch.exp(logstd)
     values = eval_critic(p, obs_n, z)

@@ -124,6 +124,56 @@ def gen_calc_gradients():
     print('calc_grad_amp_cfg', r['steps'][-1]['scalars'])
 
 
+def gen_heading():
+    rh.import_env_fns()
+    from env.tasks import humanoid_heading
+    g = torch.Generator().manual_seed(31)
+    n = 64
+    root = torch.randn(n, 13, generator=g); root[:, 3:7] = torch.nn.functional.normalize(torch.randn(n, 4, generator=g), dim=-1)
+    prev = root[:, 0:3] - 0.03 * torch.randn(n, 3, generator=g)
+    td = torch.nn.functional.normalize(torch.randn(n, 2, generator=g), dim=-1); fd = torch.nn.functional.normalize(torch.randn(n, 2, generator=g), dim=-1)
+    sp = 1.0 + 4.0 * torch.rand(n, generator=g)
+    obs = humanoid_heading.compute_heading_observations(root, td, sp, fd)
+    rew = humanoid_heading.compute_heading_reward(root[:, 0:3], prev, root[:, 3:7], td, sp, fd, 1.0 / 30.0)
+    torch.save(dict(root=root, prev=prev, tar_dir=td, tar_speed=sp, tar_face_dir=fd, obs=obs, reward=rew), os.path.join(OUT, 'heading.pt'))
+    print('heading.pt ok')
+
+
+def gen_hrl_calc_gradients():
+    """HLC learner (config 5): CommonAgent.calc_gradients over HRLBuilder's tanh-mu network, obs 258, act 64, units [1024,512]."""
+    B = 128
+    import ref_harness
+    orig = ref_harness.load_train_cfg
+
+    def patched(name):
+        c = orig(name); c['params']['network']['mlp']['units'] = [96, 64]; return c
+    ref_harness.load_train_cfg = patched
+    try:
+        agent, params = rh.make_ref_agent('hrl', num_envs=B // 32, overrides={'minibatch_size': B}, obs_dim=258, act_dim=64)
+    finally:
+        ref_harness.load_train_cfg = orig
+    shapes = O.amp_param_shapes(obs=258, act=64, amp=0, units=(96, 64))
+    P = synth.params(shapes, seed=13)
+    agent.model.load_state_dict({'a2c_network.' + k: v.clone() for k, v in P.items()}, strict=True)
+    cfg = dict(O.DEFAULT_CFG); cfg['mu_tanh'] = True
+    st = O.LearnerState(P, 258, 0, 'ppo')
+    steps = []
+    for s in range(2):
+        d, _ = synth.minibatch(st, cfg, B, 0, seed=1300 + s, kind='ppo', obs_dim=258, act=64)
+        agent.calc_gradients(d)
+        tr = agent.train_result
+        rec = {'scalars': {k: float(v) for k, v in tr.items() if torch.is_tensor(v) and v.numel() == 1}, 'grads': {}, 'params_after': {}}
+        for n, prm in agent.model.named_parameters():
+            k = n[len('a2c_network.'):]
+            if k == 'sigma':
+                continue
+            rec['grads'][k] = prm.grad.detach().clone(); rec['params_after'][k] = prm.detach().clone()
+        steps.append(rec)
+        O.calc_gradients(st, d, cfg, None)
+    torch.save({'meta': dict(B=B, seed=13, units=(96, 64), cfg=cfg), 'steps': steps}, os.path.join(OUT, 'calc_grad_hrl_small.pt'))
+    print('calc_grad_hrl_small', steps[-1]['scalars'])
+
+
 def gen_rollout_math():
     agent, _ = rh.make_ref_agent('ase', num_envs=8, overrides={'minibatch_size': 256, 'amp_minibatch_size': 64})
     g = torch.Generator().manual_seed(21)
@@ -152,5 +202,7 @@ if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     gen_obs()
+    gen_heading()
     gen_rollout_math()
+    gen_hrl_calc_gradients()
     gen_calc_gradients()

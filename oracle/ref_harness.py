@@ -96,7 +96,7 @@ def make_ref_agent(kind='ase', num_envs=8, overrides=None, obs_dim=253, amp_dim=
     from learning import amp_models, ase_models, amp_network_builder, ase_network_builder
     torch.manual_seed(seed)
     np.random.seed(seed)
-    yaml_name = {'ase': 'ase_humanoid.yaml', 'amp': 'amp_humanoid.yaml'}[kind]
+    yaml_name = {'ase': 'ase_humanoid.yaml', 'amp': 'amp_humanoid.yaml', 'hrl': 'hrl_humanoid.yaml'}[kind]
     params = copy.deepcopy(load_train_cfg(yaml_name))['params']
     config = params['config']
     config.update(overrides or {})
@@ -105,6 +105,13 @@ def make_ref_agent(kind='ase', num_envs=8, overrides=None, obs_dim=253, amp_dim=
         builder.load(params['network'])
         config['network'] = ase_models.ModelASEContinuous(builder)
         cls = ase_agent.ASEAgent
+    elif kind == 'hrl':
+        # the HLC learner of HRLAgent is CommonAgent.calc_gradients over HRLBuilder's network (hrl_agent.py:25, hrl_network_builder.py:8-39)
+        from learning import hrl_models, hrl_network_builder
+        builder = hrl_network_builder.HRLBuilder()
+        builder.load(params['network'])
+        config['network'] = hrl_models.ModelHRLContinuous(builder)
+        cls = common_agent.CommonAgent
     else:
         builder = amp_network_builder.AMPBuilder()
         builder.load(params['network'])

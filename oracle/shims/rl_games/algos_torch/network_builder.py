@@ -143,7 +143,23 @@ class A2CBuilder(NetworkBuilder):
                 sigma_init(self.sigma.weight)
 
         def forward(self, obs_dict):
-            raise NotImplementedError  # AMPBuilder.Network overrides forward
+            # [recollection] separate actor / critic MLP path of A2CBuilder.Network.forward (no cnn, no rnn)
+            obs = obs_dict['obs']
+            states = obs_dict.get('rnn_states', None)
+            assert self.separate
+            a_out = self.actor_cnn(obs)
+            a_out = a_out.contiguous().view(a_out.size(0), -1)
+            c_out = self.critic_cnn(obs)
+            c_out = c_out.contiguous().view(c_out.size(0), -1)
+            a_out = self.actor_mlp(a_out)
+            c_out = self.critic_mlp(c_out)
+            value = self.value_act(self.value(c_out))
+            mu = self.mu_act(self.mu(a_out))
+            if self.space_config['fixed_sigma']:
+                sigma = mu * 0.0 + self.sigma_act(self.sigma)
+            else:
+                sigma = self.sigma_act(self.sigma(a_out))
+            return mu, sigma, value, states
 
         def is_separate_critic(self):
             return self.separate

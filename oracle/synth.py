@@ -46,7 +46,7 @@ def minibatch(st, cfg, B, Ba, seed, kind='ase', obs_dim=253, amp_dim=1400, act=3
     new_z = F.normalize(torch.randn(B, zdim, generator=g), dim=-1) if kind == 'ase' else None
     with torch.no_grad():
         rms = st.obs_rms.clone(); rms.update(obs)
-        mu_cur = O.eval_actor(st.p, rms.norm(obs), z)
+        mu_cur = O.eval_actor(st.p, rms.norm(obs), z, mu_tanh=cfg.get('mu_tanh', False))
     sig = math.exp(-2.9)
     actions = mu_cur + sig * torch.randn(B, act, generator=g)
     logstd = torch.full((act,), -2.9)

@@ -91,3 +91,31 @@ def test_train_epochs_run_and_stay_finite_and_checkpoint_roundtrip():
     for k, v in agent.model.named_parameters().items():
         assert torch.equal(v, agent2.model.named_parameters()[k])
     assert torch.equal(agent2.model.exp_avg, agent.model.exp_avg) and agent2.model.step == agent.model.step
+
+
+def test_hrl_agent_epoch_config5_shapes():
+    """BASELINE config 5 (HumanoidHeading task-train over a frozen ASE LLC): play_steps + update run end to end; the
+    combined reward, LLC stepping and tanh-mu HLC learner are checked against the oracle on the stored buffers."""
+    from ase_b200 import configs
+    from ase_b200.agent import HRLAgent
+    from ase_b200.synthetic_env import SyntheticHumanoidEnv
+    torch.manual_seed(2)
+    n, h = 64, 8
+    env = SyntheticHumanoidEnv(n, device='cuda', seed=4, done_prob=0.05, demo_pool=256, heading_task=True)
+    cfg = configs.make('hrl', device='cuda:0', vec_env=env, num_actors=n, horizon_length=h, minibatch_size=128, mini_epochs=2, print_stats=False)
+    cfg['net_params']['mlp']['units'] = [128, 64]
+    cfg['llc_net_params'] = {'mlp': {'units': [128, 96, 64]}, 'disc': {'units': [128, 96, 64]}}
+    ag = HRLAgent('t', cfg)
+    assert ag.actions_num == 64 and ag.obs_shape[0] == 258
+    ag.init_tensors(); ag.obs = ag.env_reset()
+    ag.update_epoch(); info = ag.train_epoch()
+    for k, v in info.items():
+        assert torch.isfinite(v).all(), k
+    with torch.no_grad():
+        bd = ag.play_steps()
+    eb = {k: v.cpu() for k, v in ag.experience_buffer.items()}
+    assert float(eb['mus'].abs().max()) <= 1.0                       # tanh'd means
+    rew = 0.9 * eb['rewards'] + 0.1 * eb['disc_rewards']
+    adv = O.discount_values(eb['dones'].float(), eb['values'], rew, eb['next_values'], 0.99, 0.95)
+    assert torch.allclose(bd['returns'].cpu(), O.swap_and_flatten01(adv + eb['values']), rtol=1e-4, atol=1e-4)
+    assert float(eb['disc_rewards'].min()) >= 0.0 and float(eb['rewards'].max()) <= 1.0 + 1e-6     # heading reward in [0,1]

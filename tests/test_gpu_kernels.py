@@ -125,3 +125,18 @@ def test_gae_full_size_properties():
     a = ops.calc_advs(O.swap_and_flatten01(ret.cpu()).cuda(), O.swap_and_flatten01(v).cuda(), None).cpu()
     assert abs(float(a.mean())) < 1e-4 and abs(float(a.std()) - 1.0) < 1e-3
     assert torch.allclose(a, O.calc_advs(O.swap_and_flatten01(ref + v), O.swap_and_flatten01(v), None), rtol=1e-3, atol=1e-4)
+
+
+def test_heading_task_kernels_golden():
+    from ase_b200 import ops
+    fx = G.load('heading.pt')
+    root = fx['root'].cuda()
+    obs = ops.compute_heading_observations(root, fx['tar_dir'].cuda(), fx['tar_speed'].cuda(), fx['tar_face_dir'].cuda())
+    assert torch.allclose(obs.cpu(), fx['obs'], rtol=RTOL, atol=ATOL)
+    # written behind the humanoid features of a wider observation buffer (humanoid_amp_task.py:51-64)
+    buf = torch.zeros(64, 258, device='cuda')
+    ops.compute_heading_observations(root, fx['tar_dir'].cuda(), fx['tar_speed'].cuda(), fx['tar_face_dir'].cuda(), out=buf, col0=253)
+    assert torch.allclose(buf[:, 253:].cpu(), fx['obs'], rtol=RTOL, atol=ATOL) and float(buf[:, :253].abs().max()) == 0.0
+    rew = ops.compute_heading_reward(root[:, 0:3], fx['prev'].cuda(), root[:, 3:7], fx['tar_dir'].cuda(), fx['tar_speed'].cuda(),
+                                     fx['tar_face_dir'].cuda(), 1.0 / 30.0)
+    assert torch.allclose(rew.cpu(), fx['reward'], rtol=RTOL, atol=ATOL)

@@ -192,3 +192,30 @@ def test_full_size_minibatch_properties():
         elif not k.startswith('_enc'):
             assert float((g10[k] - g5[k]).abs().max()) <= 2e-4 * float(g5[k].abs().max()), k
     assert abs(outs[0][1]['disc_loss'] - outs[1][1]['disc_loss']) < 1e-4 * abs(outs[0][1]['disc_loss'])
+
+
+@pytest.mark.parametrize('backend', [0, 1])
+def test_hrl_high_level_learner_vs_reference_golden(backend):
+    """BASELINE config 5 learner: plain PPO over the tanh-mu HLC network (hrl_network_builder.py:26-29), obs 258, act 64."""
+    from ase_b200 import Learner
+    fx = G.load('calc_grad_hrl_small.pt')
+    meta = fx['meta']
+    P = synth.params(O.amp_param_shapes(obs=258, act=64, amp=0, units=meta['units']), seed=meta['seed'])
+    st = O.LearnerState(P, 258, 0, 'ppo')
+    ln = Learner('ppo', 258, 64, meta['B'], units=tuple(meta['units']), hparams={'learning_rate': meta['cfg']['lr']}, gemm_backend=backend,
+                 mu_activation='tanh')
+    ln.load_named(P)
+    for s, rec in enumerate(fx['steps']):
+        d, _ = synth.minibatch(st, meta['cfg'], meta['B'], 0, seed=meta['seed'] * 100 + s, kind='ppo', obs_dim=258, act=64)
+        out = ln.calc_gradients(_cuda(d))
+        tr = ln.train_result(out)
+        for k, v in rec['scalars'].items():
+            if k in tr:
+                assert abs(tr[k] - v) <= 1e-4 * max(1.0, abs(v)), (k, tr[k], v)
+        for k, g in rec['grads'].items():
+            mine = ln.named_grads()[k].cpu()
+            assert float((mine - g).abs().max()) <= 1e-4 * max(float(g.abs().max()), 1e-9), k
+        ln.adam_step()
+        for k, p in rec['params_after'].items():
+            assert torch.allclose(ln.named_parameters()[k].cpu(), p, rtol=1e-5, atol=2e-7), k
+        O.calc_gradients(st, d, meta['cfg'], None)

@@ -63,3 +63,27 @@ def test_rms_count_arithmetic_matches_checkpoint_identity():
     for _ in range(3):
         r.train_forward(torch.randn(16, 4))
     assert float(r.count) == 1 + 3 * 16
+
+
+def test_heading_task_matches_reference_golden():
+    fx = G.load('heading.pt')
+    obs = O.compute_heading_observations(fx['root'], fx['tar_dir'], fx['tar_speed'], fx['tar_face_dir'])
+    assert torch.allclose(obs, fx['obs'], rtol=1e-5, atol=1e-6)
+    rew = O.compute_heading_reward(fx['root'][:, 0:3], fx['prev'], fx['root'][:, 3:7], fx['tar_dir'], fx['tar_speed'], fx['tar_face_dir'], 1.0 / 30.0)
+    assert torch.allclose(rew, fx['reward'], rtol=1e-5, atol=1e-6)
+
+
+def test_hrl_high_level_learner_matches_reference_golden():
+    """CommonAgent.calc_gradients over HRLBuilder's tanh-mu network (BASELINE config 5 learner), small units."""
+    fx = G.load('calc_grad_hrl_small.pt')
+    meta = fx['meta']
+    P = synth.params(O.amp_param_shapes(obs=258, act=64, amp=0, units=meta['units']), seed=meta['seed'])
+    st = O.LearnerState(P, 258, 0, 'ppo')
+    for s, rec in enumerate(fx['steps']):
+        d, _ = synth.minibatch(st, meta['cfg'], meta['B'], 0, seed=meta['seed'] * 100 + s, kind='ppo', obs_dim=258, act=64)
+        res, grads = O.calc_gradients(st, d, meta['cfg'], None)
+        for k, v in rec['scalars'].items():
+            assert abs(float(res[k]) - v) <= 1e-5 * max(1.0, abs(v)), k
+        for k, g in grads.items():
+            assert G.rel_err(g, rec['grads'][k]) < 1e-4, k
+            assert torch.allclose(st.p[k], rec['params_after'][k], rtol=1e-6, atol=1e-7), k
