@@ -217,5 +217,11 @@ def test_hrl_high_level_learner_vs_reference_golden(backend):
             assert float((mine - g).abs().max()) <= 1e-4 * max(float(g.abs().max()), 1e-9), k
         ln.adam_step()
         for k, p in rec['params_after'].items():
-            assert torch.allclose(ln.named_parameters()[k].cpu(), p, rtol=1e-5, atol=2e-7), k
+            # Adam's first steps move a weight by ~lr * g/|g|: an admissible gradient error of 1e-4 * max|g| maps to an update
+            # error of lr * (1e-4 * gmax / |g|), capped at 2 lr (sign flip of an essentially-zero gradient entry)
+            g = rec['grads'][k]
+            sens = torch.clamp(1e-4 * g.abs().max() / (g.abs() + 1e-20), max=1.0)
+            allowed = 2e-7 + 1e-5 * p.abs() + 2.0 * meta['cfg']['lr'] * sens
+            diff = (ln.named_parameters()[k].cpu() - p).abs()
+            assert bool((diff <= allowed).all()), (k, float((diff - allowed).max()))
         O.calc_gradients(st, d, meta['cfg'], None)
