@@ -6,7 +6,8 @@ is the thin host-side mirror of the reference's agent / env helper interfaces.  
 import importlib
 
 _LAZY = {'lib': '.lib', 'ops': '.ops', 'learner': '.learner', 'agent': '.agent', 'synthetic_env': '.synthetic_env',
-         'replay_buffer': '.replay_buffer', 'build': '.build'}
+         'replay_buffer': '.replay_buffer', 'build': '.build', 'motion_lib': '.motion_lib', 'configs': '.configs',
+         'dist_utils': '.dist_utils'}
 __all__ = ['lib', 'ops', 'Learner', 'param_names', 'build']
 
 

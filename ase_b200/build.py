@@ -6,7 +6,7 @@ import sys
 CSRC = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'csrc')
 LIB = os.path.join(CSRC, 'libase_b200.so')
 SOURCES = ['api.cu', 'obs_kernels.cu', 'rms_kernels.cu', 'rollout_kernels.cu', 'gemm_simt.cu', 'gemm_tc.cu',
-           'loss_kernels.cu', 'learner.cu']
+           'loss_kernels.cu', 'learner.cu', 'motion_kernels.cu']
 HEADERS = ['common.cuh', 'kernels.h', os.path.join('..', '..', 'include', 'ase_b200.h')]
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo',
               '-Xcompiler', '-fPIC', '-shared']

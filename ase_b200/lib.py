@@ -31,6 +31,13 @@ class AmpObsBuildParams(C.Structure):
                 ('amp_obs', vp), ('hist_steps', i32), ('step_dim', i32), ('shift_history', i32)]
 
 
+class MotionLibParams(C.Structure):
+    _fields_ = [('gts', vp), ('grs', vp), ('lrs', vp), ('grvs', vp), ('gravs', vp), ('dvs', vp),
+                ('motion_lengths', vp), ('motion_num_frames', vp), ('motion_dt', vp), ('length_starts', vp),
+                ('num_bodies', i32), ('num_dofs', i32), ('num_joints', i32), ('dof_body_ids', C.POINTER(C.c_int32)),
+                ('dof_offsets', C.POINTER(C.c_int32)), ('num_key_bodies', i32), ('key_body_ids', C.POINTER(C.c_int32))]
+
+
 class GemmParams(C.Structure):
     _fields_ = [('A', vp), ('lda', i64), ('a_trans', i32), ('B', vp), ('ldb', i64), ('b_trans', i32),
                 ('C', vp), ('ldc', i64), ('M', i32), ('N', i32), ('K', i32), ('alpha', f32), ('bias', vp), ('act', i32),
@@ -67,7 +74,7 @@ class TrainResult(C.Structure):
 
 # every symbol declared in include/ase_b200.h (tests/test_abi.py checks the two lists agree)
 EXPORTS = ['ase_abi_version', 'ase_last_error', 'ase_launch_count', 'ase_obs_build', 'ase_amp_obs_build',
-           'ase_rms_scratch_bytes', 'ase_rms_update', 'ase_rms_apply', 'ase_gae', 'ase_amp_rewards', 'ase_heading_obs', 'ase_heading_reward', 'ase_policy_sample', 'ase_adv_normalize',
+           'ase_rms_scratch_bytes', 'ase_rms_update', 'ase_rms_apply', 'ase_gae', 'ase_amp_rewards', 'ase_heading_obs', 'ase_heading_reward', 'ase_motion_state', 'ase_amp_obs_demo', 'ase_policy_sample', 'ase_adv_normalize',
            'ase_gemm', 'ase_gemm_tc_workspace_bytes', 'ase_gemm_tc_profile', 'ase_gemm_tc_profile_read', 'ase_learner_num_params', 'ase_learner_param_desc',
            'ase_learner_arena_floats', 'ase_learner_workspace_bytes', 'ase_learner_create', 'ase_learner_destroy', 'ase_learner_params_changed',
            'ase_learner_calc_gradients', 'ase_learner_adam_step', 'ase_learner_eval_actor_critic',
@@ -95,6 +102,8 @@ def _load():
     lib.ase_amp_rewards.argtypes = [vp, vp, vp, i32, i32, f32, f32, vp, f32, f32, f32, vp, vp, vp, vp]
     lib.ase_heading_obs.argtypes = [vp, i64, vp, vp, vp, i32, vp, i64, i32, vp]
     lib.ase_heading_reward.argtypes = [vp, i64, vp, i64, vp, i64, vp, vp, vp, f32, i32, vp, vp]
+    lib.ase_motion_state.argtypes = [C.POINTER(MotionLibParams), vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.ase_amp_obs_demo.argtypes = [C.POINTER(MotionLibParams), vp, vp, i32, f32, i32, i32, i32, vp, vp]
     lib.ase_policy_sample.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
     lib.ase_adv_normalize.argtypes = [vp, vp, vp, i32, vp, vp, vp]
     lib.ase_obs_build.argtypes = [C.POINTER(ObsBuildParams), vp]

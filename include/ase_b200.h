@@ -108,6 +108,27 @@ int ase_amp_rewards(const float* disc_logits, const float* enc_pred, const float
                     int rows, float disc_scale, float enc_scale,
                     const float* task_rewards, float task_w, float disc_w, float enc_w,
                     float* disc_r, float* enc_r, float* combined, void* stream);
+/* ------------------------------------------------------------------------------------------------
+ * Motion library (demo data for the discriminator).  Replaces MotionLib.get_motion_state (utils/motion_lib.py:123-172,
+ * 263-272,296-324) and HumanoidAMP.build_amp_obs_demo (env/tasks/humanoid_amp.py:85-101).  The tables are the flat
+ * per-frame device tensors MotionLib builds at load time (motion_lib.py:65-89): gts [F,J,3], grs/lrs [F,J,4] xyzw,
+ * grvs/gravs [F,3], dvs [F,dofs]; per clip: length (s), frame count, frame dt, offset of its first frame.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const float *gts, *grs, *lrs, *grvs, *gravs, *dvs;
+  const float* motion_lengths; const int32_t* motion_num_frames; const float* motion_dt; const int32_t* length_starts;
+  int num_bodies, num_dofs;
+  int num_joints; const int32_t* dof_body_ids; const int32_t* dof_offsets;   /* HOST pointers (humanoid.py:191-192) */
+  int num_key_bodies; const int32_t* key_body_ids;                            /* HOST pointer */
+} AseMotionLib;
+/* outputs: root_pos [n,3], root_rot [n,4], dof_pos [n,dofs], root_vel [n,3], root_ang_vel [n,3], dof_vel [n,dofs], key_pos [n,keys,3] */
+int ase_motion_state(const AseMotionLib* m, const int32_t* motion_ids, const float* motion_times, int n,
+                     float* root_pos, float* root_rot, float* dof_pos, float* root_vel, float* root_ang_vel, float* dof_vel,
+                     float* key_pos, void* stream);
+/* amp_obs [n, num_steps * step_dim]: frame i is the AMP observation of the clip at motion_times0 - i * sim_dt */
+int ase_amp_obs_demo(const AseMotionLib* m, const int32_t* motion_ids, const float* motion_times0, int n, float sim_dt,
+                     int num_steps, int local_root_obs, int root_height_obs, float* amp_obs, void* stream);
+
 /* HRL heading task (config 5): compute_heading_observations / compute_heading_reward, env/tasks/humanoid_heading.py:232-285.
  * root_states [N, 13] rows with stride root_stride; tar_dir / tar_face_dir [N,2]; tar_speed [N]; task_obs [N, 5] written at
  * obs + obs_col0 with row stride obs_ld (so it can land behind the 253 humanoid features, humanoid_amp_task.py:51-64). */

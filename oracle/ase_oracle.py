@@ -181,6 +181,113 @@ def compute_heading_reward(root_pos, prev_root_pos, root_rot, tar_dir, tar_speed
     return 0.7 * dir_reward + 0.3 * facing_reward
 
 
+# --------------------------------------------------------------------------------------------------
+# motion library: (clip, time) -> interpolated reference state -> demo AMP observations      utils/motion_lib.py
+# --------------------------------------------------------------------------------------------------
+DOF_BODY_IDS_SWORD_SHIELD = [1, 2, 3, 4, 5, 7, 8, 11, 12, 13, 14, 15, 16]     # env/tasks/humanoid.py:191
+
+
+def slerp(q0, q1, t):
+    """utils/torch_utils.py:93-115."""
+    cos_half = (q0 * q1).sum(-1)
+    neg = cos_half < 0
+    q1 = torch.where(neg.unsqueeze(-1), -q1, q1)
+    cos_half = torch.abs(cos_half).unsqueeze(-1)
+    half = torch.acos(cos_half)
+    sin_half = torch.sqrt(1.0 - cos_half * cos_half)
+    ra = torch.sin((1 - t) * half) / sin_half
+    rb = torch.sin(t * half) / sin_half
+    new_q = ra * q0 + rb * q1
+    new_q = torch.where(torch.abs(sin_half) < 0.001, 0.5 * q0 + 0.5 * q1, new_q)
+    new_q = torch.where(torch.abs(cos_half) >= 1, q0, new_q)
+    return new_q
+
+
+def quat_to_angle_axis(q):
+    """utils/torch_utils.py:6-27."""
+    sin_theta = torch.sqrt(1 - q[..., 3] * q[..., 3])
+    angle = normalize_angle(2 * torch.acos(q[..., 3]))
+    axis = q[..., 0:3] / sin_theta.unsqueeze(-1)
+    mask = torch.abs(sin_theta) > 1e-5
+    default_axis = torch.zeros_like(axis); default_axis[..., 2] = 1
+    angle = torch.where(mask, angle, torch.zeros_like(angle))
+    axis = torch.where(mask.unsqueeze(-1), axis, default_axis)
+    return angle, axis
+
+
+def quat_to_exp_map(q):
+    """utils/torch_utils.py:37-44."""
+    angle, axis = quat_to_angle_axis(q)
+    return angle.unsqueeze(-1) * axis
+
+
+class MotionTables:
+    """The flat per-frame tensors MotionLib builds (utils/motion_lib.py:65-89,174-238): gts [F,J,3], grs/lrs [F,J,4],
+    grvs/gravs [F,3], dvs [F,dofs]; per motion: length (s), num_frames, dt, first-frame offset."""
+
+    def __init__(self, gts, grs, lrs, grvs, gravs, dvs, lengths, num_frames, dts):
+        self.gts, self.grs, self.lrs, self.grvs, self.gravs, self.dvs = gts, grs, lrs, grvs, gravs, dvs
+        self.lengths, self.num_frames, self.dts = lengths, num_frames, dts
+        shifted = num_frames.roll(1); shifted[0] = 0
+        self.length_starts = shifted.cumsum(0)
+
+
+def synthetic_motion_tables(seed=0, frames=(40, 75, 23, 2), fps=(30.0, 30.0, 60.0, 30.0), bodies=17, dofs=31):
+    """Smooth random clips in MotionLib's table format (incl. a 2-frame clip: the shortest a clip can be)."""
+    g = torch.Generator().manual_seed(seed)
+    gts, grs, lrs, grvs, gravs, dvs = [], [], [], [], [], []
+    for nf in frames:
+        def smooth_quat():
+            q = torch.randn(1, bodies, 4, generator=g) + 0.15 * torch.randn(nf, bodies, 4, generator=g).cumsum(0)
+            return F.normalize(q, dim=-1)
+        gts.append(torch.randn(1, bodies, 3, generator=g) + 0.05 * torch.randn(nf, bodies, 3, generator=g).cumsum(0))
+        grs.append(smooth_quat()); lrs.append(smooth_quat())
+        grvs.append(torch.randn(nf, 3, generator=g)); gravs.append(torch.randn(nf, 3, generator=g)); dvs.append(torch.randn(nf, dofs, generator=g))
+    nfr = torch.tensor(frames, dtype=torch.long)
+    dts = torch.tensor([1.0 / f for f in fps], dtype=torch.float32)
+    lengths = torch.tensor([1.0 / f * (n - 1) for f, n in zip(fps, frames)], dtype=torch.float32)
+    lrs = torch.cat(lrs); lrs[5, 3] = torch.tensor([0., 0., 0., 1.])      # identity joint rotation: default-axis branch of quat_to_angle_axis
+    return MotionTables(torch.cat(gts), torch.cat(grs), lrs, torch.cat(grvs), torch.cat(gravs), torch.cat(dvs), lengths, nfr, dts)
+
+
+def get_motion_state(mt, motion_ids, motion_times, dof_body_ids=DOF_BODY_IDS_SWORD_SHIELD, dof_offsets=DOF_OFFSETS_SWORD_SHIELD,
+                     key_body_ids=KEY_BODY_IDS_SWORD_SHIELD):
+    """utils/motion_lib.py:123-172 (+ _calc_frame_blend :263-272, _local_rotation_to_dof :296-324)."""
+    mlen, nfr, dt = mt.lengths[motion_ids], mt.num_frames[motion_ids], mt.dts[motion_ids]
+    phase = torch.clip(motion_times / mlen, 0.0, 1.0)
+    f0 = (phase * (nfr - 1)).long()
+    f1 = torch.min(f0 + 1, nfr - 1)
+    blend = ((motion_times - f0 * dt) / dt).unsqueeze(-1)
+    f0l, f1l = f0 + mt.length_starts[motion_ids], f1 + mt.length_starts[motion_ids]
+    root_pos = (1.0 - blend) * mt.gts[f0l, 0] + blend * mt.gts[f1l, 0]
+    root_rot = slerp(mt.grs[f0l, 0], mt.grs[f1l, 0], blend)
+    kid = torch.tensor(key_body_ids)
+    be = blend.unsqueeze(-1)
+    key_pos = (1.0 - be) * mt.gts[f0l.unsqueeze(-1), kid.unsqueeze(0)] + be * mt.gts[f1l.unsqueeze(-1), kid.unsqueeze(0)]
+    local_rot = slerp(mt.lrs[f0l], mt.lrs[f1l], be)
+    n = motion_ids.shape[0]
+    dof_pos = torch.zeros(n, dof_offsets[-1])
+    for j, body in enumerate(dof_body_ids):
+        o, sz = dof_offsets[j], dof_offsets[j + 1] - dof_offsets[j]
+        q = local_rot[:, body]
+        if sz == 3:
+            dof_pos[:, o:o + 3] = quat_to_exp_map(q)
+        else:
+            theta, axis = quat_to_angle_axis(q)
+            dof_pos[:, o] = normalize_angle(theta * axis[..., 1])
+    return root_pos, root_rot, dof_pos, mt.grvs[f0l], mt.gravs[f0l], mt.dvs[f0l], key_pos
+
+
+def build_amp_obs_demo(mt, motion_ids, motion_times0, sim_dt, num_steps, local_root_obs=True, root_height_obs=True):
+    """env/tasks/humanoid_amp.py:85-101: `num_steps` frames going back in time by sim_dt -> [n, num_steps * 140]."""
+    n = motion_ids.shape[0]
+    ids = motion_ids.unsqueeze(-1).expand(n, num_steps).reshape(-1)
+    times = (motion_times0.unsqueeze(-1) - sim_dt * torch.arange(0, num_steps)).reshape(-1)
+    rp, rr, dp, rv, rw, dv, kp = get_motion_state(mt, ids, times)
+    obs = build_amp_observations(rp, rr, rv, rw, dp, dv, kp, local_root_obs, root_height_obs, DOF_OFFSETS_SWORD_SHIELD)
+    return obs.reshape(n, -1)
+
+
 def amp_hist_step(amp_buf, new_frame):
     """env/tasks/humanoid_amp.py:248-275: shift history by one slot, newest frame at slot 0.
     amp_buf [N,S,F] (modified in place), new_frame [N,F]."""

@@ -124,6 +124,37 @@ def gen_calc_gradients():
     print('calc_grad_amp_cfg', r['steps'][-1]['scalars'])
 
 
+def gen_motion_lib():
+    """The reference's own MotionLib.get_motion_state + build_amp_observations on synthetic clip tables (the object is
+    assembled field by field so no .npy clip has to travel; the real loader only fills these same tensors)."""
+    humanoid, humanoid_amp, _ = rh.import_env_fns()
+    from utils.motion_lib import MotionLib
+    mt = O.synthetic_motion_tables(seed=7)
+    ml = MotionLib.__new__(MotionLib)
+    ml._dof_body_ids = O.DOF_BODY_IDS_SWORD_SHIELD; ml._dof_offsets = O.DOF_OFFSETS_SWORD_SHIELD; ml._num_dof = 31
+    ml._key_body_ids = torch.tensor(O.KEY_BODY_IDS_SWORD_SHIELD); ml._device = 'cpu'
+    ml.gts, ml.grs, ml.lrs, ml.grvs, ml.gravs, ml.dvs = mt.gts, mt.grs, mt.lrs, mt.grvs, mt.gravs, mt.dvs
+    ml._motion_lengths, ml._motion_num_frames, ml._motion_dt, ml.length_starts = mt.lengths, mt.num_frames, mt.dts, mt.length_starts
+
+    class _M: num_joints = 17
+    ml._motions = [_M()]
+    g = torch.Generator().manual_seed(8)
+    n = 96
+    ids = torch.randint(0, 4, (n,), generator=g)
+    sim_dt, steps = 1.0 / 30.0, 10
+    trunc = sim_dt * (steps - 1)
+    t0 = torch.rand(n, generator=g) * torch.clamp(mt.lengths[ids] - trunc, min=0.0) + trunc        # humanoid_amp.py:64-83
+    t0[0] = trunc; t0[1] = mt.lengths[ids[1]] + 0.5          # clip start / beyond the end (phase clipped to 1)
+    state = ml.get_motion_state(ids, t0)
+    tid = ids.unsqueeze(-1).expand(n, steps).reshape(-1)
+    tt = (t0.unsqueeze(-1) - sim_dt * torch.arange(0, steps)).reshape(-1)
+    rp, rr, dp, rv, rw, dv, kp = ml.get_motion_state(tid, tt)
+    demo = humanoid_amp.build_amp_observations(rp, rr, rv, rw, dp, dv, kp, True, True, 78, O.DOF_OFFSETS_SWORD_SHIELD).reshape(n, -1)
+    torch.save(dict(seed=7, ids=ids, t0=t0, sim_dt=sim_dt, steps=steps, state=[s.clone() for s in state], demo=demo),
+               os.path.join(OUT, 'motion_lib.pt'))
+    print('motion_lib.pt', tuple(demo.shape))
+
+
 def gen_heading():
     rh.import_env_fns()
     from env.tasks import humanoid_heading
@@ -202,6 +233,7 @@ if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     gen_obs()
+    gen_motion_lib()
     gen_heading()
     gen_rollout_math()
     gen_hrl_calc_gradients()

@@ -140,3 +140,20 @@ def test_heading_task_kernels_golden():
     rew = ops.compute_heading_reward(root[:, 0:3], fx['prev'].cuda(), root[:, 3:7], fx['tar_dir'].cuda(), fx['tar_speed'].cuda(),
                                      fx['tar_face_dir'].cuda(), 1.0 / 30.0)
     assert torch.allclose(rew.cpu(), fx['reward'], rtol=RTOL, atol=ATOL)
+
+
+def test_motion_lib_state_and_demo_obs_golden():
+    """ase_motion_state / ase_amp_obs_demo vs the reference MotionLib + build_amp_observations outputs (tests/golden/motion_lib.pt)
+    on the same synthetic clip tables; incl. a 2-frame clip, a query beyond the clip end and an identity joint rotation."""
+    from ase_b200.motion_lib import MotionLib
+    fx = G.load('motion_lib.pt')
+    mt = O.synthetic_motion_tables(seed=fx['seed'])
+    ml = MotionLib(mt.gts, mt.grs, mt.lrs, mt.grvs, mt.gravs, mt.dvs, mt.lengths, mt.num_frames, mt.dts)
+    state = ml.get_motion_state(fx['ids'], fx['t0'])
+    for mine, ref, name in zip(state, fx['state'], ('root_pos', 'root_rot', 'dof_pos', 'root_vel', 'root_ang_vel', 'dof_vel', 'key_pos')):
+        assert torch.allclose(mine.cpu(), ref, rtol=RTOL, atol=2e-5), name
+    demo = ml.build_amp_obs_demo(fx['ids'], fx['t0'], fx['sim_dt'], fx['steps'])
+    assert torch.allclose(demo.cpu(), fx['demo'], rtol=RTOL, atol=2e-5)
+    # sampler plumbing: shapes, times inside [truncate, len]
+    d = ml.fetch_amp_obs_demo(512, 1.0 / 30.0, 10)
+    assert d.shape == (512, 1400) and torch.isfinite(d).all()

@@ -87,3 +87,14 @@ def test_hrl_high_level_learner_matches_reference_golden():
         for k, g in grads.items():
             assert G.rel_err(g, rec['grads'][k]) < 1e-4, k
             assert torch.allclose(st.p[k], rec['params_after'][k], rtol=1e-6, atol=1e-7), k
+
+
+def test_motion_lib_matches_reference_golden():
+    """MotionLib.get_motion_state + build_amp_obs_demo (reference, on synthetic clip tables) vs the oracle restatement."""
+    fx = G.load('motion_lib.pt')
+    mt = O.synthetic_motion_tables(seed=fx['seed'])
+    state = O.get_motion_state(mt, fx['ids'], fx['t0'])
+    for mine, ref, name in zip(state, fx['state'], ('root_pos', 'root_rot', 'dof_pos', 'root_vel', 'root_ang_vel', 'dof_vel', 'key_pos')):
+        assert torch.allclose(mine, ref, rtol=1e-5, atol=1e-5), name
+    demo = O.build_amp_obs_demo(mt, fx['ids'], fx['t0'], fx['sim_dt'], fx['steps'])
+    assert torch.allclose(demo, fx['demo'], rtol=1e-5, atol=1e-5)
