@@ -218,13 +218,20 @@ def test_hrl_high_level_learner_vs_reference_golden(backend):
         for k, g in rec['grads'].items():
             mine = ln.named_grads()[k].cpu()
             assert float((mine - g).abs().max()) <= gtol * max(float(g.abs().max()), 1e-9), k
+        # Adam is checked in isolation (same gradients in, torch.optim.Adam formula on the CPU): comparing post-update parameters
+        # against the reference run instead would test the chaotic map g -> lr * m_hat / sqrt(v_hat) at m_hat ~ 0, not the kernel
+        p0, g0 = ln.params.cpu().clone(), ln.grads.cpu().clone()
+        m0, v0 = ln.exp_avg.cpu().clone(), ln.exp_avg_sq.cpu().clone()
         ln.adam_step()
-        for k, p in rec['params_after'].items():
-            # Adam's first steps move a weight by ~lr * g/|g|: an admissible gradient error of gtol * max|g| maps to an update
-            # error of ~lr * (gtol * gmax / |g|) (x2 margin), capped at 2 lr (sign flip of an essentially-zero gradient entry)
+        t = ln.step
+        lr, b1, b2, eps = meta['cfg']['lr'], 0.9, 0.999, 1e-8
+        m1 = b1 * m0 + (1 - b1) * g0
+        v1 = b2 * v0 + (1 - b2) * g0 * g0
+        p1 = p0 - (lr / (1 - b1 ** t)) * m1 / (v1.sqrt() / (1 - b2 ** t) ** 0.5 + eps)
+        assert torch.allclose(ln.exp_avg.cpu(), m1, rtol=1e-6, atol=1e-12) and torch.allclose(ln.exp_avg_sq.cpu(), v1, rtol=1e-6, atol=1e-20)
+        assert torch.allclose(ln.params.cpu(), p1, rtol=1e-6, atol=1e-9)
+        for k, p in rec['params_after'].items():       # and the reference's parameters are matched wherever the update is well conditioned
             g = rec['grads'][k]
-            sens = torch.clamp(2.0 * gtol * g.abs().max() / (g.abs() + 1e-20), max=1.0)
-            allowed = 2e-7 + 1e-5 * p.abs() + 2.0 * meta['cfg']['lr'] * sens
-            diff = (ln.named_parameters()[k].cpu() - p).abs()
-            assert bool((diff <= allowed).all()), (k, float((diff - allowed).max()))
+            ok = g.abs() > 0.05 * g.abs().max()
+            assert torch.allclose(ln.named_parameters()[k].cpu()[ok], p[ok], rtol=1e-5, atol=1e-6), k
         O.calc_gradients(st, d, meta['cfg'], None)
