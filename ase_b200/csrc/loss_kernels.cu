@@ -2,6 +2,7 @@
 // bias-gradient column sums, weight regularisers and the fused Adam step.  All scalar statistics are
 // accumulated as doubles in `acc` (one atomicAdd per block) and turned into the reference's train_result by
 // finalize_scalars_kernel -- no host synchronisation anywhere (the reference .item()s the KL every minibatch).
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -265,13 +266,13 @@ __global__ void finalize_scalars_kernel(FinalizeArgs f) {
 // torch.optim.Adam single-tensor path (common_agent.py:45): denom = sqrt(v)/sqrt(bc2) + eps; p -= lr/bc1 * m/denom
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, int64_t n,
-            float grad_scale, float b1, float b2, float step_size, float inv_bc2_sqrt, float eps) {
+            float grad_scale, float b1, float b2, float omb1, float omb2, float step_size, float bc2_sqrt, float eps) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gi = g[i] * grad_scale;
-    const float mi = b1 * m[i] + (1.0f - b1) * gi;
-    const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    const float mi = b1 * m[i] + omb1 * gi;             // exp_avg.mul_(beta1).add_(grad, alpha=1-beta1)
+    const float vi = b2 * v[i] + omb2 * gi * gi;        // exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1-beta2)
     m[i] = mi; v[i] = vi;
-    const float denom = sqrtf(vi) * inv_bc2_sqrt + eps;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
     p[i] = p[i] - step_size * (mi / denom);
   }
 }
@@ -319,8 +320,13 @@ int launch_finalize(const FinalizeArgs& f, cudaStream_t st) {
 }
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float grad_scale, float b1, float b2, float lr, float eps,
                 int64_t step, cudaStream_t st) {
-  const double bc1 = 1.0 - pow((double)b1, (double)step), bc2 = 1.0 - pow((double)b2, (double)step);
-  adam_kernel<<<ew_blocks(n), 256, 0, st>>>(p, g, m, v, n, grad_scale, b1, b2, (float)((double)lr / bc1), (float)(1.0 / sqrt(bc2)), eps);
+  // torch.optim.Adam evaluates 1-beta, the bias corrections and lr/bc1 in Python doubles from the decimal hyper-parameters
+  // (0.9, 0.999, 2e-5) and only then rounds to fp32: recover those decimals from the fp32 config values
+  auto dec = [](float x) { char buf[32]; snprintf(buf, sizeof(buf), "%.7g", (double)x); return strtod(buf, nullptr); };
+  const double db1 = dec(b1), db2 = dec(b2), dlr = dec(lr), deps = dec(eps);
+  const double bc1 = 1.0 - pow(db1, (double)step), bc2 = 1.0 - pow(db2, (double)step);
+  adam_kernel<<<ew_blocks(n), 256, 0, st>>>(p, g, m, v, n, grad_scale, (float)db1, (float)db2, (float)(1.0 - db1), (float)(1.0 - db2),
+                                           (float)(dlr / bc1), (float)sqrt(bc2), (float)deps);
   ASE_LAUNCH_OK(); return ASE_OK;
 }
 
