@@ -228,8 +228,9 @@ def test_hrl_high_level_learner_vs_reference_golden(backend):
         m1 = b1 * m0 + (1 - b1) * g0
         v1 = b2 * v0 + (1 - b2) * g0 * g0
         p1 = p0 - (lr / (1 - b1 ** t)) * m1 / (v1.sqrt() / (1 - b2 ** t) ** 0.5 + eps)
-        assert torch.allclose(ln.exp_avg.cpu(), m1, rtol=1e-6, atol=1e-12) and torch.allclose(ln.exp_avg_sq.cpu(), v1, rtol=1e-6, atol=1e-20)
-        assert torch.allclose(ln.params.cpu(), p1, rtol=1e-6, atol=1e-9)
+        close = lambda a, b, tol: float((a - b).abs().max()) <= tol * float(b.abs().max())       # fma contraction: ~1 ulp of the larger term
+        assert close(ln.exp_avg.cpu(), m1, 1e-6) and close(ln.exp_avg_sq.cpu(), v1, 1e-6)
+        assert float((ln.params.cpu() - p1).abs().max()) <= 1e-3 * lr           # the update itself is <= ~lr per step
         for k, p in rec['params_after'].items():       # and the reference's parameters are matched wherever the update is well conditioned
             g = rec['grads'][k]
             ok = g.abs() > 0.05 * g.abs().max()
