@@ -33,7 +33,7 @@ class SyntheticHumanoidEnv:
     NUM_BODIES, NUM_DOFS, AMP_STEPS, AMP_STEP_DIM = 17, 31, 10, 140
 
     def __init__(self, num_envs, device='cuda', seed=0, pool=8, state_source='device', done_prob=1.0 / 300.0,
-                 local_root_obs=True, root_height_obs=True, demo_pool=8192, heading_task=False, dt=1.0 / 30.0):
+                 local_root_obs=True, root_height_obs=True, demo_pool=8192, heading_task=False, dt=1.0 / 30.0, demo_source='motion_lib'):
         self.device = torch.device(device)
         self.num_envs = num_envs
         self.local_root_obs, self.root_height_obs = local_root_obs, root_height_obs
@@ -72,7 +72,12 @@ class SyntheticHumanoidEnv:
         self.reset_buf = torch.zeros(n, dtype=torch.uint8, device=self.device)
         self._terminate_buf = torch.zeros(n, dtype=torch.uint8, device=self.device)
         self.extras = {}
-        # demo AMP observations: a fixed pool built by the same kernel from synthetic "motion" states
+        # demo AMP observations.  'motion_lib': synthetic clips in MotionLib's table format, sampled and turned into 10-frame AMP
+        # observations by the ase_amp_obs_demo kernel every fetch (what HumanoidAMP.fetch_amp_obs_demo does, humanoid_amp.py:64-83);
+        # 'pool': a fixed pool of rows built once by the AMP-obs kernel.
+        self.demo_source = demo_source
+        if demo_source == 'motion_lib':
+            self._motion_lib = self._synthetic_motion_lib(g)
         dn = demo_pool
         dpos = torch.randn(dn, J, 3, generator=g); dpos[:, 0, 2] = 0.8 + 0.1 * torch.rand(dn, generator=g)
         drot = torch.nn.functional.normalize(torch.randn(dn, J, 4, generator=g) * 0.3 + torch.tensor([0., 0., 0., 1.]), dim=-1)
@@ -101,7 +106,27 @@ class SyntheticHumanoidEnv:
         return {'action_space': self.action_space, 'observation_space': self.observation_space,
                 'amp_observation_space': self.amp_observation_space}
 
+    def _synthetic_motion_lib(self, g, clips=24):
+        """Smooth random clips (1.3 - 6 s at 30 fps, upright root) in the flat per-frame layout of utils/motion_lib.py:65-89."""
+        from .motion_lib import MotionLib
+        J, D = self.NUM_BODIES, self.NUM_DOFS
+        nf = torch.randint(40, 180, (clips,), generator=g)
+        F = int(nf.sum())
+        def smooth(shape_tail, scale):
+            return torch.randn(F, *shape_tail, generator=g).cumsum(0) * scale
+        gts = torch.randn(1, J, 3, generator=g) + smooth((J, 3), 0.01)
+        gts[:, 0, 2] = 0.9 + 0.05 * torch.randn(F, generator=g)
+        yaw = smooth((), 0.05)
+        tilt = 0.1 * torch.randn(F, 2, generator=g)
+        grs = torch.nn.functional.normalize(torch.randn(1, J, 4, generator=g) + smooth((J, 4), 0.03), dim=-1)
+        grs[:, 0] = torch.nn.functional.normalize(torch.stack([tilt[:, 0], tilt[:, 1], torch.sin(yaw / 2), torch.cos(yaw / 2)], dim=-1), dim=-1)
+        lrs = torch.nn.functional.normalize(torch.tensor([0., 0., 0., 1.]) + smooth((J, 4), 0.03), dim=-1)
+        grvs, gravs, dvs = torch.randn(F, 3, generator=g), torch.randn(F, 3, generator=g), torch.randn(F, D, generator=g)
+        return MotionLib(gts, grs, lrs, grvs, gravs, dvs, (nf - 1).float() / 30.0, nf, torch.full((clips,), 1.0 / 30.0), device=self.device)
+
     def fetch_amp_obs_demo(self, num_samples):
+        if self.demo_source == 'motion_lib':
+            return self._motion_lib.fetch_amp_obs_demo(num_samples, self.dt, self.AMP_STEPS, self.local_root_obs, self.root_height_obs)
         idx = torch.randint(0, self._demo_pool.shape[0], (num_samples,), device=self.device, generator=self._gen)
         return self._demo_pool[idx]
 

@@ -13,7 +13,7 @@ def _small_agent(kind='ase', n=64, h=8, mb=128, amb=32):
     from ase_b200 import configs
     from ase_b200.agent import ASEAgent, AMPAgent
     from ase_b200.synthetic_env import SyntheticHumanoidEnv
-    env = SyntheticHumanoidEnv(n, device='cuda', seed=3, done_prob=0.05, demo_pool=512)
+    env = SyntheticHumanoidEnv(n, device='cuda', seed=3, done_prob=0.05, demo_pool=512, demo_source='motion_lib' if kind == 'ase' else 'pool')
     cfg = configs.make(kind, device='cuda:0', vec_env=env, num_actors=n, horizon_length=h, minibatch_size=mb, amp_minibatch_size=amb,
                        mini_epochs=2, amp_obs_demo_buffer_size=2048, amp_replay_buffer_size=2048, amp_batch_size=64, print_stats=False)
     cfg['net_params']['mlp']['units'] = [128, 64] if kind == 'amp' else [128, 96, 64]
