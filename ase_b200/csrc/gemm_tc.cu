@@ -15,6 +15,7 @@
 // Descriptor formats follow the PTX ISA "tcgen05 shared memory descriptor" / "instruction descriptor" tables
 // (cross-checked against cute/arch/mma_sm100_desc.hpp in the image's CUTLASS headers).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <vector>
 #include <unordered_map>
 #include <string.h>
@@ -27,6 +28,19 @@ namespace ase {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 32;                 // fp32 elements per k-block = one 128-byte swizzle row
 constexpr int TC_THREADS = 192;
+
+// Operand-plane formats.  H = false: TF32 hi/lo planes stored as fp32 words (kind::tf32, K = 8 per MMA).
+// H = true: SCALED FP16 hi/lo planes (kind::f16, K = 16 per MMA, twice the MMA rate and half the plane bytes): each tensor is
+// multiplied by a per-tensor power of two that puts its max |x| in [2^12, 2^13) before the split, so hi + lo carries 22
+// significant bits for every element within 2^-26 of the tensor max (absolute floor 2^-25 / scale); the epilogue multiplies
+// by the two inverse scales (exact).  In both formats a k-block is ONE 128-byte swizzle row per operand row, so the shared
+// memory tiles, the TMA transaction bytes and the 4-MMAs-per-k-block structure are identical.
+template <bool H> struct TcFmt {
+  static constexpr int BK = H ? 64 : 32;              // elements per k-block (128 bytes)
+  static constexpr int MN_BOX = H ? 64 : 32;          // MN elements per MN-major TMA box row (128 bytes)
+  static constexpr int MN_BOX_BYTES = H ? 8192 : 4096;   // BK k-rows x 128 bytes
+  static constexpr int MN_KSTEP = H ? 2048 : 1024;    // bytes between the MN-major k-slices of consecutive MMAs (16 / 8 k-rows)
+};
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -80,6 +94,18 @@ __device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t adesc, uin
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
       "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
+template <bool H>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  if (H) tc_mma_f16(tmem_d, adesc, bdesc, idesc, accum); else tc_mma_tf32(tmem_d, adesc, bdesc, idesc, accum);
+}
 // 32 lanes x 32 consecutive fp32 columns: thread `lane` receives row (lane_base + lane), columns [col, col+32)
 __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, float (&v)[32]) {
   uint32_t r[32];
@@ -115,6 +141,38 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (1ull << 61);
 }
 
+// MN-major 16-bit operands: the canonical SWIZZLE_128B layout (layout type 2), ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units
+// (cute/atom/mma_traits_sm100.hpp): a TMA box is [64 k-rows x 64 mn] = 8 KB with the 16-byte chunks of row r XORed with r mod 8;
+// LBO = distance between 64-wide MN blocks (one box, 8192), SBO = distance between 8-row k groups (1024); a K=16 MMA slice is
+// two k groups.
+__device__ __forceinline__ uint64_t make_smem_desc_mn_h(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+template <bool H, bool MN>
+__device__ __forceinline__ uint64_t tc_desc(uint32_t base, int k) {
+  if (!MN) return make_smem_desc(base + k * 32);                       // K-major: 32 bytes along the swizzled row per MMA
+  return H ? make_smem_desc_mn_h(base + k * TcFmt<true>::MN_KSTEP) : make_smem_desc_mn(base + k * TcFmt<false>::MN_KSTEP);
+}
+// instruction descriptor: D = f32 (bits 4-5 = 1); A/B format at bits 7-9 / 10-12 (kind::tf32: 2 = TF32; kind::f16: 0 = F16);
+// bit 15 / 16 = A / B MN-major; N >> 3 at 17, M >> 4 at 24
+template <bool H>
+__device__ __forceinline__ uint32_t tc_idesc(bool amn, bool bmn, int bn) {
+  const uint32_t fmt = H ? 0u : 2u;
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((amn ? 1u : 0u) << 15) | ((bmn ? 1u : 0u) << 16) | ((uint32_t)(bn >> 3) << 17) |
+         ((uint32_t)(TC_BM >> 4) << 24);
+}
+
+// scale that puts amax into [2^12, 2^13); 1 for an all-zero / non-finite tensor
+__device__ __forceinline__ float scale_from_amax(float amax) {
+  if (!(amax > 0.0f) || !(amax < 3.0e38f)) return 1.0f;
+  int e; frexpf(amax, &e);                      // amax = m * 2^e, m in [0.5, 1)
+  return ldexpf(1.0f, max(-100, min(100, 13 - e)));
+}
+__device__ __forceinline__ void split_f16(float xs, __half& hi, __half& lo) {
+  hi = __float2half_rn(xs);
+  lo = __float2half_rn(xs - __half2float(hi));   // the residual is exact in fp32
+}
+
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
   uint32_t h, l;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
@@ -134,18 +192,25 @@ struct TcEpi {
   const float* mask_src; int64_t ldm; int mask_mode;
   int accumulate;
   float* colsum;                           // optional: colsum[n] += sum_m C[m,n] (bias gradient of the layer whose dZ this GEMM produces)
-  float* Chi; float* Clo; int64_t ldp;     // optional TF32 hi/lo planes of C (operand cache for the consumers of C)
+  void* Chi; void* Clo; int64_t ldp;       // optional hi/lo planes of C (operand cache for the consumers of C): fp32 words (TF32) or halfs
+  const float* a_inv; const float* b_inv;  // FP16 planes: device pointers to the operands' inverse scales (null = 1)
+  const float* c_scale;                    // FP16 planes of C: device pointer to the scale they are written with
+  unsigned* c_amax;                        // optional: atomicMax of |C| (as uint bits) -- the scale source for the consumers of C
   int debug;   // experiments only (env ASE_TC_DEBUG): 1 skip global stores, 2 skip TMEM drain loads, 4 skip correction MMAs, 8 skip bias/act
 };
 
 // Phase 2 of the epilogue, shared by the tile shapes: a warp writes rows [row0, row0+nrows) of the staged tile; a row is
 // written as BNT/4 float4 by consecutive lanes (full 128-byte lines); bias / activation / mask operands are read with the
-// same coalesced mapping; optional TF32 planes of C and the fused column sums (bias gradient) ride along.
+// same coalesced mapping; optional hi/lo planes of C, the running max |C| and the fused column sums (bias gradient) ride along.
+template <bool H>
 __device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* cs, int cs_ld, int row0, int nrows, int BNT, int m0, int n0, int lane) {
   const bool vec_ok = ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0) &&
                       (!e.mask_mode || (((e.ldm & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.mask_src) & 15) == 0)));
   const bool add_bias = e.bias && (!e.accumulate || blockIdx.z == 0);
-  const bool pvec = e.Chi && ((e.ldp & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.Chi) & 15) == 0) && ((reinterpret_cast<uintptr_t>(e.Clo) & 15) == 0);
+  const uintptr_t pal = H ? 7 : 15;         // 4 plane elements per lane: 8 bytes (halfs) / 16 bytes (fp32 words)
+  const bool pvec = e.Chi && ((e.ldp & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.Chi) & pal) == 0) && ((reinterpret_cast<uintptr_t>(e.Clo) & pal) == 0);
+  const float cscale = (H && e.Chi && e.c_scale) ? *e.c_scale : 1.0f;
+  float amax = 0.0f;
 #pragma unroll 1
   for (int cc = lane * 4; cc < BNT; cc += 128) {
     const int n = n0 + cc;
@@ -178,24 +243,42 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* cs, i
       if (vec_ok && nvalid == 4) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
       else for (int j = 0; j < nvalid; ++j) cp[j] = x[j];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) cs4[j] += x[j];
+      for (int j = 0; j < 4; ++j) { cs4[j] += x[j]; if (j < nvalid) amax = fmaxf(amax, fabsf(x[j])); }
       if (e.Chi) {       // the consumers of C read these planes directly through TMA: no separate split pass
-        float h[4], l[4];
+        if (!H) {
+          float h[4], l[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) split_tf32(x[j], h[j], l[j]);
-        float* hp = e.Chi + (int64_t)m * e.ldp + n; float* lp = e.Clo + (int64_t)m * e.ldp + n;
-        if (pvec && nvalid == 4) { *reinterpret_cast<float4*>(hp) = make_float4(h[0], h[1], h[2], h[3]); *reinterpret_cast<float4*>(lp) = make_float4(l[0], l[1], l[2], l[3]); }
-        else for (int j = 0; j < nvalid; ++j) { hp[j] = h[j]; lp[j] = l[j]; }
+          for (int j = 0; j < 4; ++j) split_tf32(x[j], h[j], l[j]);
+          float* hp = (float*)e.Chi + (int64_t)m * e.ldp + n; float* lp = (float*)e.Clo + (int64_t)m * e.ldp + n;
+          if (pvec && nvalid == 4) { *reinterpret_cast<float4*>(hp) = make_float4(h[0], h[1], h[2], h[3]); *reinterpret_cast<float4*>(lp) = make_float4(l[0], l[1], l[2], l[3]); }
+          else for (int j = 0; j < nvalid; ++j) { hp[j] = h[j]; lp[j] = l[j]; }
+        } else {
+          __half h[4], l[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) split_f16(x[j] * cscale, h[j], l[j]);
+          __half* hp = (__half*)e.Chi + (int64_t)m * e.ldp + n; __half* lp = (__half*)e.Clo + (int64_t)m * e.ldp + n;
+          if (pvec && nvalid == 4) {
+            uint2 hv, lv;
+            hv.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16); hv.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+            lv.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16); lv.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+            *reinterpret_cast<uint2*>(hp) = hv; *reinterpret_cast<uint2*>(lp) = lv;
+          } else for (int j = 0; j < nvalid; ++j) { hp[j] = h[j]; lp[j] = l[j]; }
+        }
       }
     }
     if (e.colsum && !e.accumulate) for (int j = 0; j < nvalid; ++j) atomicAdd(e.colsum + n + j, cs4[j]);
+  }
+  if (e.c_amax && !e.accumulate) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0 && amax > 0.0f) atomicMax(e.c_amax, __float_as_uint(amax));
   }
 }
 
 template <int BN, int STAGES>
 struct TcSmem {
-  static constexpr int A_BYTES = TC_BM * TC_BK * 4;           // 16 KB per plane
-  static constexpr int B_BYTES = BN * TC_BK * 4;
+  static constexpr int A_BYTES = TC_BM * 128;                // 16 KB per plane: one 128-byte k-block row per operand row
+  static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
@@ -214,11 +297,12 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // CL = cluster size along N (1 or 2).  With CL = 2 the two CTAs of a cluster work on the same 128 rows of A: each
 // loads HALF of the A planes and multicasts it into both CTAs' shared memory, halving the A traffic out of L2
 // (the mainloop is operand-feed bound: 64 KB per k-block per CTA against ~768 MMA cycles).
-template <int BN, int STAGES, bool AMN, bool BMN, int CL>
+template <int BN, int STAGES, bool AMN, bool BMN, int CL, bool H>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const TcEpi e) {
   using SM = TcSmem<BN, STAGES>;
+  using F = TcFmt<H>;
   constexpr uint32_t TMEM_COLS = (3 * BN <= 256) ? 256u : 512u;      // main[0], main[1], corr
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -262,16 +346,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], SM::STAGE_BYTES);
         uint8_t* st = smem + s * SM::STAGE_BYTES;
-        const int k0 = (kb_begin + kb) * TC_BK;
+        const int k0 = (kb_begin + kb) * F::BK;
         if (CL == 1) {
-          if (!AMN) {          // K-major planes [rows, K]: one box of 128 rows x 32 k
+          if (!AMN) {          // K-major planes [rows, K]: one box of 128 rows x one k-block
             tma_load_2d(st, &tmAhi, &full[s], k0, m0);
             tma_load_2d(st + SM::A_BYTES, &tmAlo, &full[s], k0, m0);
-          } else {             // MN-major planes [K, rows]: 4 boxes of 32 k-rows x 32 m
+          } else {             // MN-major planes [K, rows]: boxes of BK k-rows x 128 bytes of m
 #pragma unroll
-            for (int b = 0; b < TC_BM / 32; ++b) {
-              tma_load_2d(st + b * 4096, &tmAhi, &full[s], m0 + b * 32, k0);
-              tma_load_2d(st + SM::A_BYTES + b * 4096, &tmAlo, &full[s], m0 + b * 32, k0);
+            for (int b = 0; b < TC_BM / F::MN_BOX; ++b) {
+              tma_load_2d(st + b * F::MN_BOX_BYTES, &tmAhi, &full[s], m0 + b * F::MN_BOX, k0);
+              tma_load_2d(st + SM::A_BYTES + b * F::MN_BOX_BYTES, &tmAlo, &full[s], m0 + b * F::MN_BOX, k0);
             }
           }
         } else {               // this CTA's half of A, multicast to the whole cluster (the A maps have 128/CL-row boxes)
@@ -293,9 +377,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
           tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES, &tmBlo, &full[s], k0, n0);
         } else {
 #pragma unroll
-          for (int b = 0; b < BN / 32; ++b) {
-            tma_load_2d(st + 2 * SM::A_BYTES + b * 4096, &tmBhi, &full[s], n0 + b * 32, k0);
-            tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES + b * 4096, &tmBlo, &full[s], n0 + b * 32, k0);
+          for (int b = 0; b < BN / F::MN_BOX; ++b) {
+            tma_load_2d(st + 2 * SM::A_BYTES + b * F::MN_BOX_BYTES, &tmBhi, &full[s], n0 + b * F::MN_BOX, k0);
+            tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES + b * F::MN_BOX_BYTES, &tmBlo, &full[s], n0 + b * F::MN_BOX, k0);
           }
         }
       }
@@ -303,12 +387,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
     __syncwarp();
   } else if (warp == 1) {
     if (lane == 0) {
-      // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=tf32 (bits 7-9, 10-12 = 2), K-major A/B, N>>3 at 17, M>>4 at 24
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((AMN ? 1u : 0u) << 15) | ((BMN ? 1u : 0u) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      // per K=8 MMA slice: K-major operands advance 32 bytes along the swizzled row, MN-major ones one 1024-byte atom
-      auto adesc = [](uint32_t base, int k) { return AMN ? make_smem_desc_mn(base + k * 1024) : make_smem_desc(base + k * 32); };
-      auto bdesc = [](uint32_t base, int k) { return BMN ? make_smem_desc_mn(base + k * 1024) : make_smem_desc(base + k * 32); };
+      const uint32_t idesc = tc_idesc<H>(AMN, BMN, BN);
+      // per MMA slice (32 bytes of K): K-major operands advance 32 bytes along the swizzled row, MN-major ones F::MN_KSTEP
+      auto adesc = [](uint32_t base, int k) { return tc_desc<H, AMN>(base, k); };
+      auto bdesc = [](uint32_t base, int k) { return tc_desc<H, BMN>(base, k); };
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -321,14 +403,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         const uint32_t a_hi = sa, a_lo = sa + SM::A_BYTES, b_hi = sa + 2 * SM::A_BYTES, b_lo = b_hi + SM::B_BYTES;
         const uint32_t tmem_main = tmem_base + (uint32_t)b * BN;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k)     // 8 tf32 = 32 bytes along the swizzled row per MMA
-          tc_mma_tf32(tmem_main, adesc(a_hi, k), bdesc(b_hi, k), idesc, k > 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k)     // 4 MMAs per k-block: 8 tf32 / 16 f16 = 32 bytes along the swizzled row each
+          tc_mma<H>(tmem_main, adesc(a_hi, k), bdesc(b_hi, k), idesc, k > 0 ? 1u : 0u);
         tc_commit(&main_full[b]);              // this k-block's A_hi.B_hi partial tile is complete
         if (!(e.debug & 4))
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {
-          tc_mma_tf32(tmem_corr, adesc(a_lo, k), bdesc(b_hi, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          tc_mma_tf32(tmem_corr, adesc(a_hi, k), bdesc(b_lo, k), idesc, 1u);
+        for (int k = 0; k < 4; ++k) {
+          tc_mma<H>(tmem_corr, adesc(a_lo, k), bdesc(b_hi, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_mma<H>(tmem_corr, adesc(a_hi, k), bdesc(b_lo, k), idesc, 1u);
         }
         if (CL == 1) tc_commit(&empty[s]);     // all 12 MMAs have read this smem stage
         else tc_commit_mc(&empty[s], MC_MASK); // ... and tell every CTA that multicasts into it
@@ -366,6 +448,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
     // has completed (corr_full) and every TMA load was consumed.  One accumulator row per thread.
     float* cs = reinterpret_cast<float*>(smem);
     constexpr int CS_LD = BN + 4;
+    // FP16 planes: undo the operands' power-of-two scales (two exact multiplies; their product alone could underflow)
+    const float s1 = (H && e.a_inv) ? *e.a_inv : 1.0f;
+    const float s2 = e.alpha * ((H && e.b_inv) ? *e.b_inv : 1.0f);
     {
       float* crow_s = cs + (lg * 32 + lane) * CS_LD;
 #pragma unroll
@@ -374,13 +459,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         tc_ld_32x32(tmem_corr + lane_off + (uint32_t)c, v);
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(crow_s + c + j) = make_float4(e.alpha * (acc[c + j] + v[j]), e.alpha * (acc[c + j + 1] + v[j + 1]),
-                                                                   e.alpha * (acc[c + j + 2] + v[j + 2]), e.alpha * (acc[c + j + 3] + v[j + 3]));
+          *reinterpret_cast<float4*>(crow_s + c + j) = make_float4(s2 * (s1 * (acc[c + j] + v[j])), s2 * (s1 * (acc[c + j + 1] + v[j + 1])),
+                                                                   s2 * (s1 * (acc[c + j + 2] + v[j + 2])), s2 * (s1 * (acc[c + j + 3] + v[j + 3])));
       }
     }
     asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 epilogue warps only
     // Phase 2: coalesced epilogue -- warp w owns rows [32w, 32w+32)
-    if (!(e.debug & 1)) epilogue_rows(e, cs, CS_LD, lg * 32, 32, BN, m0, n0, lane);
+    if (!(e.debug & 1)) epilogue_rows<H>(e, cs, CS_LD, lg * 32, 32, BN, m0, n0, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -403,12 +488,13 @@ constexpr int TC256_THREADS = 384;       // WG0: warp 0 TMA, warp 1 MMA (+2 idle
 constexpr int TC256_BN = 256;
 constexpr int TC256_STAGES = 2;
 
-template <bool AMN, bool BMN>
+template <bool AMN, bool BMN, bool H>
 __global__ void __launch_bounds__(TC256_THREADS, 1)
 gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                   const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const TcEpi e) {
   constexpr int BN = TC256_BN, STAGES = TC256_STAGES;
   using SM = TcSmem<BN, STAGES>;
+  using F = TcFmt<H>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES);
@@ -448,15 +534,15 @@ gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
         mbar_wait(&empty[s], ph ^ 1);
         mbar_expect_tx(&full[s], SM::STAGE_BYTES);
         uint8_t* st = smem + s * SM::STAGE_BYTES;
-        const int k0 = (kb_begin + kb) * TC_BK;
+        const int k0 = (kb_begin + kb) * F::BK;
         if (!AMN) {
           tma_load_2d(st, &tmAhi, &full[s], k0, m0);
           tma_load_2d(st + SM::A_BYTES, &tmAlo, &full[s], k0, m0);
         } else {
 #pragma unroll
-          for (int b = 0; b < TC_BM / 32; ++b) {
-            tma_load_2d(st + b * 4096, &tmAhi, &full[s], m0 + b * 32, k0);
-            tma_load_2d(st + SM::A_BYTES + b * 4096, &tmAlo, &full[s], m0 + b * 32, k0);
+          for (int b = 0; b < TC_BM / F::MN_BOX; ++b) {
+            tma_load_2d(st + b * F::MN_BOX_BYTES, &tmAhi, &full[s], m0 + b * F::MN_BOX, k0);
+            tma_load_2d(st + SM::A_BYTES + b * F::MN_BOX_BYTES, &tmAlo, &full[s], m0 + b * F::MN_BOX, k0);
           }
         }
         if (!BMN) {        // the B maps have 128-row boxes: two per plane
@@ -467,17 +553,16 @@ gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
           }
         } else {
 #pragma unroll
-          for (int b = 0; b < BN / 32; ++b) {
-            tma_load_2d(st + 2 * SM::A_BYTES + b * 4096, &tmBhi, &full[s], n0 + b * 32, k0);
-            tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES + b * 4096, &tmBlo, &full[s], n0 + b * 32, k0);
+          for (int b = 0; b < BN / F::MN_BOX; ++b) {
+            tma_load_2d(st + 2 * SM::A_BYTES + b * F::MN_BOX_BYTES, &tmBhi, &full[s], n0 + b * F::MN_BOX, k0);
+            tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES + b * F::MN_BOX_BYTES, &tmBlo, &full[s], n0 + b * F::MN_BOX, k0);
           }
         }
       }
     } else if (warp == 1 && lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((AMN ? 1u : 0u) << 15) | ((BMN ? 1u : 0u) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
-      auto adesc = [](uint32_t base, int k) { return AMN ? make_smem_desc_mn(base + k * 1024) : make_smem_desc(base + k * 32); };
-      auto bdesc = [](uint32_t base, int k) { return BMN ? make_smem_desc_mn(base + k * 1024) : make_smem_desc(base + k * 32); };
+      const uint32_t idesc = tc_idesc<H>(AMN, BMN, BN);
+      auto adesc = [](uint32_t base, int k) { return tc_desc<H, AMN>(base, k); };
+      auto bdesc = [](uint32_t base, int k) { return tc_desc<H, BMN>(base, k); };
       for (int kb = 0; kb < nkb; ++kb) {
         const int s = kb % STAGES;
         const uint32_t ph = (kb / STAGES) & 1;
@@ -487,14 +572,14 @@ gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
         const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
         const uint32_t a_hi = sa, a_lo = sa + SM::A_BYTES, b_hi = sa + 2 * SM::A_BYTES, b_lo = b_hi + SM::B_BYTES;
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k)
-          tc_mma_tf32(tmem_base, adesc(a_hi, k), bdesc(b_hi, k), idesc, k > 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k)
+          tc_mma<H>(tmem_base, adesc(a_hi, k), bdesc(b_hi, k), idesc, k > 0 ? 1u : 0u);
         tc_commit(main_full);
         if (!(e.debug & 4))
 #pragma unroll
-        for (int k = 0; k < TC_BK / 8; ++k) {
-          tc_mma_tf32(tmem_corr, adesc(a_lo, k), bdesc(b_hi, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          tc_mma_tf32(tmem_corr, adesc(a_hi, k), bdesc(b_lo, k), idesc, 1u);
+        for (int k = 0; k < 4; ++k) {
+          tc_mma<H>(tmem_corr, adesc(a_lo, k), bdesc(b_hi, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_mma<H>(tmem_corr, adesc(a_hi, k), bdesc(b_lo, k), idesc, 1u);
         }
         tc_commit(&empty[s]);
       }
@@ -528,6 +613,8 @@ gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
     tc_fence_after();
     float* cs = reinterpret_cast<float*>(smem);
     constexpr int CS_LD = BN + 4;
+    const float s1 = (H && e.a_inv) ? *e.a_inv : 1.0f;
+    const float s2 = e.alpha * ((H && e.b_inv) ? *e.b_inv : 1.0f);
     {
       float* crow_s = cs + (lg * 32 + lane) * CS_LD + half * 128;
 #pragma unroll
@@ -536,12 +623,12 @@ gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
         tc_ld_32x32(tmem_corr + lane_off + (uint32_t)(half * 128 + c), v);
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(crow_s + c + j) = make_float4(e.alpha * (acc[c + j] + v[j]), e.alpha * (acc[c + j + 1] + v[j + 1]),
-                                                                   e.alpha * (acc[c + j + 2] + v[j + 2]), e.alpha * (acc[c + j + 3] + v[j + 3]));
+          *reinterpret_cast<float4*>(crow_s + c + j) = make_float4(s2 * (s1 * (acc[c + j] + v[j])), s2 * (s1 * (acc[c + j + 1] + v[j + 1])),
+                                                                   s2 * (s1 * (acc[c + j + 2] + v[j + 2])), s2 * (s1 * (acc[c + j + 3] + v[j + 3])));
       }
     }
     asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps only
-    if (!(e.debug & 1)) epilogue_rows(e, cs, CS_LD, (warp - 4) * 16, 16, BN, m0, n0, lane);
+    if (!(e.debug & 1)) epilogue_rows<H>(e, cs, CS_LD, (warp - 4) * 16, 16, BN, m0, n0, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -565,6 +652,60 @@ tc_prep_kernel(const float* __restrict__ src, int64_t ld, int rows, int cols, in
   }
 }
 
+// FP16 format: max |src| over the [rows, cols] view -> atomicMax on the uint bits (non-negative floats order like uints)
+__global__ void __launch_bounds__(256)
+tc_amax_kernel(const float* __restrict__ src, int64_t ld, int rows, int cols, unsigned* __restrict__ amax) {
+  const int64_t total = (int64_t)rows * cols;
+  float m = 0.0f;
+  if (cols == ld) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(src[i]));
+  } else {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+      m = fmaxf(m, fabsf(src[(int64_t)r * ld + c]));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __shared__ float sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, sm[w]);
+    if (m > 0.0f) atomicMax(amax, __float_as_uint(m));
+  }
+}
+
+// FP16 format: scale from the tensor's max (read from device memory: no host sync), split src[rows, cols] (ld) into
+// zero-padded half planes [rows_p, cols_p]; 4 consecutive columns per thread (cols_p is a multiple of 8).  The scale and its
+// inverse are published in scale_out[0..1] for the epilogues of the GEMMs that consume these planes.
+__global__ void __launch_bounds__(256)
+tc_prep_h_kernel(const float* __restrict__ src, int64_t ld, int rows, int cols, int rows_p, int cols_p, __half* __restrict__ hi,
+                 __half* __restrict__ lo, const unsigned* __restrict__ amax, float* __restrict__ scale_out) {
+  const float s = scale_from_amax(__uint_as_float(*amax));
+  if (blockIdx.x == 0 && threadIdx.x == 0) { scale_out[0] = s; scale_out[1] = 1.0f / s; }
+  const int c4n = cols_p >> 2;
+  const int64_t total = (int64_t)rows_p * c4n;
+  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / c4n), c = (int)(i - (int64_t)r * c4n) * 4;
+    float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (r < rows) {
+      const float* sp = src + (int64_t)r * ld + c;
+      if (vec && c + 4 <= cols) { const float4 t = *reinterpret_cast<const float4*>(sp); x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w; }
+      else for (int j = 0; j < 4; ++j) if (c + j < cols) x[j] = sp[j];
+    }
+    __half h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_f16(x[j] * s, h[j], l[j]);
+    uint2 hv, lv;
+    hv.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16); hv.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+    lv.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16); lv.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+    *reinterpret_cast<uint2*>(hi + (int64_t)r * cols_p + c) = hv;
+    *reinterpret_cast<uint2*>(lo + (int64_t)r * cols_p + c) = lv;
+  }
+}
+
 // ------------------------------------------------------------------------------------------ host side
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -585,7 +726,7 @@ static PFN_encodeTiled get_encode() {
 
 // cuTensorMapEncodeTiled costs microseconds and the learner re-issues the same ~230 maps every minibatch: memoise.
 struct MapKey {
-  const void* base; int rows, cols; int64_t ld; int box_rows; int mn;
+  const void* base; int rows, cols; int64_t ld; int box_rows; int mn;     // mn: bit 0 = MN-major, bit 1 = half planes
   bool operator==(const MapKey& o) const { return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && mn == o.mn; }
 };
 struct MapKeyHash {
@@ -599,20 +740,23 @@ struct MapKeyHash {
 };
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash>& map_cache() { static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> c; return c; }
 
-static int encode_cached(CUtensorMap* tm, const float* base, int rows, int cols, int64_t ld, int box_rows, bool mn_major) {
-  MapKey k{base, rows, cols, ld, box_rows, mn_major ? 1 : 0};
+// 2D map over [rows, cols] elements (cols contiguous, row stride ld elements); the box is one 128-byte row chunk
+// (32 fp32 words / 64 halfs) x box_rows
+static int encode_cached(CUtensorMap* tm, const void* base, int rows, int cols, int64_t ld, int box_rows, bool mn_major, bool half = false) {
+  MapKey k{base, rows, cols, ld, box_rows, (mn_major ? 1 : 0) | (half ? 2 : 0)};
   auto& c = map_cache();
   auto it = c.find(k);
   if (it != c.end()) { memcpy(tm, &it->second, sizeof(CUtensorMap)); return ASE_OK; }
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return ASE_ERR_UNSUPPORTED; }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t gstr[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)ld * (half ? 2 : 4)};
+  cuuint32_t box[2] = {half ? 64u : 32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                   mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  // MN-major: fp32 words need the 32-byte-atom flavour of the 128B swizzle, halfs the plain one (see the smem descriptors)
+  CUresult r = enc(tm, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, (mn_major && !half) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(%d x %d, ld %lld, box %d) failed with CUresult %d", rows, cols, (long long)ld, box_rows, (int)r); return ASE_ERR_CUDA; }
   if (c.size() > 8192) c.clear();
   c.emplace(k, *tm);
@@ -620,16 +764,19 @@ static int encode_cached(CUtensorMap* tm, const float* base, int rows, int cols,
 }
 
 // 2D tensor map over a zero-padded plane [rows_p, cols_p] (cols contiguous); box = [box_rows x 32 cols], 128B swizzle
-static int make_map(CUtensorMap* tm, const float* base, int rows_p, int cols_p, int box_rows, bool mn_major = false) {
-  return encode_cached(tm, base, rows_p, cols_p, cols_p, box_rows, mn_major);
+static int make_map(CUtensorMap* tm, const void* base, int rows_p, int cols_p, int box_rows, bool mn_major = false, bool half = false) {
+  return encode_cached(tm, base, rows_p, cols_p, cols_p, box_rows, mn_major, half);
 }
 
 static inline int pad_to(int x, int m) { return (x + m - 1) / m * m; }
 
 // planes are padded to whole tiles in both dimensions (zero filled by the prep kernel): no reliance on TMA OOB fill
+// (the FP16 format needs half of it: [*, pad(K, 64)] halfs <= [*, pad(K, 32)] words; the first TC_WS_HEAD bytes hold the
+// amax / scale slots of a registry-less call)
+constexpr int64_t TC_WS_HEAD = 1024;
 int64_t gemm_tc_workspace_bytes(int M, int N, int K) {
   const int64_t Mp = pad_to(M, 128), Np = pad_to(N, 128), Kp = pad_to(K, TC_BK);
-  return 2 * align_up(Mp * Kp * 4, 1024) + 2 * align_up(Np * Kp * 4, 1024);
+  return TC_WS_HEAD + 2 * align_up(Mp * Kp * 4, 1024) + 2 * align_up(Np * Kp * 4, 1024);
 }
 
 // every shape runs on the tensor cores (small heads are padded up to one tile)
@@ -657,6 +804,29 @@ static int prep_operand(const float* src, int64_t ld, int trans, int rows, int K
   return ASE_OK;
 }
 
+static int launch_amax(const float* src, int64_t ld, int rows, int cols, unsigned* amax, cudaStream_t st) {
+  const int64_t total = (int64_t)rows * cols;
+  tc_amax_kernel<<<(int)imin64((total + 1023) / 1024, 148 * 8), 256, 0, st>>>(src, ld, rows, cols, amax);
+  ASE_LAUNCH_OK();
+  return ASE_OK;
+}
+static int launch_prep_h(const float* src, int64_t ld, int rows, int cols, int rows_p, int cols_p, void* hi, void* lo, const unsigned* amax,
+                         float* scale_out, cudaStream_t st) {
+  const int64_t total = (int64_t)rows_p * (cols_p / 4);
+  tc_prep_h_kernel<<<(int)imin64((total + 255) / 256, 148 * 16), 256, 0, st>>>(src, ld, rows, cols, rows_p, cols_p, (__half*)hi, (__half*)lo, amax, scale_out);
+  ASE_LAUNCH_OK();
+  return ASE_OK;
+}
+// FP16 format, unregistered operand: max pass + scaled split into the shared workspace
+static int prep_operand_h(const float* src, int64_t ld, int trans, int rows, int K, int rows_p, int Kp, void* hi, void* lo, unsigned* amax,
+                          float* scale_out, cudaStream_t st) {
+  const int pr = trans ? Kp : rows_p, pc = trans ? rows_p : Kp;
+  const int sr = trans ? K : rows, sc = trans ? rows : K;
+  int rc;
+  if ((rc = launch_amax(src, ld, sr, sc, amax, st))) return rc;
+  return launch_prep_h(src, ld, sr, sc, pr, pc, hi, lo, amax, scale_out, st);
+}
+
 // Optional per-launch timing of the main kernel (bench.py's live roofline measurement): CUDA events recorded on
 // the launching stream around every gemm_tc_kernel launch; read back (with a sync) by ase_gemm_tc_profile_read.
 struct TcProfile {
@@ -676,13 +846,13 @@ static void prof_mark(cudaStream_t st) {
   cudaEventRecord(g_prof.ev[g_prof.used++], st);
 }
 
-template <int BN, int STAGES, bool AMN, bool BMN, int CL>
+template <int BN, int STAGES, bool AMN, bool BMN, int CL, bool H>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcEpi& e,
                      int splits, cudaStream_t st) {
   using SM = TcSmem<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    ASE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, AMN, BMN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    ASE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, AMN, BMN, CL, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr_set = true;
   }
   dim3 grid(ceil_div(e.N, BN), ceil_div(e.M, TC_BM), splits);
@@ -695,46 +865,48 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  ASE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, AMN, BMN, CL>, ah, al, bh, bl, e));
+  ASE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, AMN, BMN, CL, H>, ah, al, bh, bl, e));
   if (prof) { prof_mark(st); g_prof.flops += 2.0 * (double)e.M * (double)e.N * (double)e.K; }
   ASE_LAUNCH_OK();
   return ASE_OK;
 }
 
-template <int BN, int STAGES, int CL>
+template <int BN, int STAGES, int CL, bool H>
 static int launch_tc_major(bool amn, bool bmn, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                            const TcEpi& e, int splits, cudaStream_t st) {
-  if (!amn && !bmn) return launch_tc<BN, STAGES, false, false, CL>(ah, al, bh, bl, e, splits, st);
-  if (!amn && bmn) return launch_tc<BN, STAGES, false, true, CL>(ah, al, bh, bl, e, splits, st);
-  if (amn && !bmn) return launch_tc<BN, STAGES, true, false, CL>(ah, al, bh, bl, e, splits, st);
-  return launch_tc<BN, STAGES, true, true, CL>(ah, al, bh, bl, e, splits, st);
+  if (!amn && !bmn) return launch_tc<BN, STAGES, false, false, CL, H>(ah, al, bh, bl, e, splits, st);
+  if (!amn && bmn) return launch_tc<BN, STAGES, false, true, CL, H>(ah, al, bh, bl, e, splits, st);
+  if (amn && !bmn) return launch_tc<BN, STAGES, true, false, CL, H>(ah, al, bh, bl, e, splits, st);
+  return launch_tc<BN, STAGES, true, true, CL, H>(ah, al, bh, bl, e, splits, st);
 }
 
 // A-multicast clusters are OFF by default: measured on B200 (profiles/experiments_r01.md) they do not help -- the
-// mainloop is bound by the per-SM ingest port (~64 B/clk), which multicast does not relieve.  ASE_TC_CLUSTER=2|4 enables them.
-template <bool AMN, bool BMN>
+// mainloop is bound by the per-SM ingest port (~64 B/clk), which multicast does not relieve.  ASE_TC_CLUSTER=2|4 enables them
+// (TF32 format only).
+template <bool AMN, bool BMN, bool H>
 static int launch_tc256(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcEpi& e,
                         int splits, cudaStream_t st) {
   using SM = TcSmem<TC256_BN, TC256_STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    ASE_CUDA_OK(cudaFuncSetAttribute(gemm_tc256_kernel<AMN, BMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    ASE_CUDA_OK(cudaFuncSetAttribute(gemm_tc256_kernel<AMN, BMN, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr_set = true;
   }
   dim3 grid(ceil_div(e.N, TC256_BN), ceil_div(e.M, TC_BM), splits);
   const bool prof = g_prof.on;
   if (prof) prof_mark(st);
-  gemm_tc256_kernel<AMN, BMN><<<grid, TC256_THREADS, SM::TOTAL, st>>>(ah, al, bh, bl, e);
+  gemm_tc256_kernel<AMN, BMN, H><<<grid, TC256_THREADS, SM::TOTAL, st>>>(ah, al, bh, bl, e);
   if (prof) { prof_mark(st); g_prof.flops += 2.0 * (double)e.M * (double)e.N * (double)e.K; }
   ASE_LAUNCH_OK();
   return ASE_OK;
 }
+template <bool H>
 static int launch_tc256_major(bool amn, bool bmn, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                               const TcEpi& e, int splits, cudaStream_t st) {
-  if (!amn && !bmn) return launch_tc256<false, false>(ah, al, bh, bl, e, splits, st);
-  if (!amn && bmn) return launch_tc256<false, true>(ah, al, bh, bl, e, splits, st);
-  if (amn && !bmn) return launch_tc256<true, false>(ah, al, bh, bl, e, splits, st);
-  return launch_tc256<true, true>(ah, al, bh, bl, e, splits, st);
+  if (!amn && !bmn) return launch_tc256<false, false, H>(ah, al, bh, bl, e, splits, st);
+  if (!amn && bmn) return launch_tc256<false, true, H>(ah, al, bh, bl, e, splits, st);
+  if (amn && !bmn) return launch_tc256<true, false, H>(ah, al, bh, bl, e, splits, st);
+  return launch_tc256<true, true, H>(ah, al, bh, bl, e, splits, st);
 }
 int gemm_tc_tile_n(int N);
 static int tc_tile256() {   // env ASE_TC_TILE256=0 keeps every GEMM on the 128x128 kernel
@@ -765,61 +937,99 @@ void PlaneRegistry::add(const float* base, int64_t capacity, float* hi, float* l
   if (n >= MAX) return;
   PlaneBuf& x = b[n++];
   x.base = base; x.capacity = capacity; x.hi = hi; x.lo = lo; x.plane_capacity = plane_capacity;
-  x.ld = 0; x.rows = x.cols = 0; x.ldp = 0; x.valid = false;
+  x.ld = 0; x.rows = x.cols = 0; x.ldp = 0; x.valid = false; x.amax_slot = -1;
 }
 PlaneBuf* PlaneRegistry::declare(const float* base, int64_t ld, int rows, int cols) {
   PlaneBuf* x = find(base);
   if (!x || x->base != base) return nullptr;
+  x->amax_slot = -1;
+  if (f16) { x->valid = false; return nullptr; }      // FP16 planes need the tensor's max first: the first reader splits
   const int64_t ldp = (cols + 3) / 4 * 4;
   if ((int64_t)rows * ldp > x->plane_capacity) { x->valid = false; return nullptr; }
   x->ld = ld; x->rows = rows; x->cols = cols; x->ldp = ldp; x->valid = true;
   return x;
 }
-void PlaneRegistry::invalidate(const float* p) { if (PlaneBuf* x = find(p)) x->valid = false; }
+void PlaneRegistry::invalidate(const float* p) { if (PlaneBuf* x = find(p)) { x->valid = false; x->amax_slot = -1; } }
 void PlaneRegistry::invalidate_range(const float* lo_, const float* hi_) {
-  for (int i = 0; i < n; ++i) if (b[i].base >= lo_ && b[i].base < hi_) b[i].valid = false;
+  for (int i = 0; i < n; ++i) if (b[i].base >= lo_ && b[i].base < hi_) { b[i].valid = false; b[i].amax_slot = -1; }
+}
+// FP16 format: start of a top-level call (one stream-ordered sequence of GEMMs): the transient amax slots are zeroed and
+// handed out again from 0; knowledge of tracked maxima does not survive the call (valid planes and their scales do).
+int PlaneRegistry::begin_call(cudaStream_t st) {
+  if (!f16) return ASE_OK;
+  next_slot = 0;
+  for (int i = 0; i < n; ++i) b[i].amax_slot = -1;
+  ASE_CUDA_OK(cudaMemsetAsync(amax, 0, (size_t)n_slots * sizeof(unsigned), st));
+  return ASE_OK;
+}
+int PlaneRegistry::new_slot() {
+  if (next_slot >= n_slots) return -1;
+  return next_slot++;
 }
 
-struct OpView { const float* hi; const float* lo; int64_t ldp; bool ok; };
+struct OpView { const void* hi; const void* lo; int64_t ldp; bool ok; const float* scale; };
 
 // View [nat_rows, nat_cols] (ld) at `ptr` as planes.  Geometry of a registered buffer is whatever its last full
 // writer declared; a first read of a buffer without valid planes splits the WHOLE declared buffer once.
 static int resolve_operand(PlaneRegistry* reg, const float* ptr, int64_t ld, int nat_rows, int nat_cols, OpView* v, cudaStream_t st) {
-  v->ok = false;
+  v->ok = false; v->scale = nullptr;
   if (!reg) return ASE_OK;
   PlaneBuf* x = reg->find(ptr);
   if (!x) return ASE_OK;
+  const bool H = reg->f16;
+  const int pal = H ? 8 : 4;                 // plane leading dimensions / column offsets: 16-byte granules
   if (!x->valid) {
     // adopt the reader's geometry if it starts at the buffer base (inputs written by non-GEMM kernels, weights)
     if (ptr != x->base) return ASE_OK;
-    const int64_t ldp = pad_to(nat_cols, 4);
-    if ((int64_t)nat_rows * ldp > x->plane_capacity || (int64_t)(nat_rows - 1) * ld + nat_cols > x->capacity) return ASE_OK;
-    x->ld = ld; x->rows = nat_rows; x->cols = nat_cols; x->ldp = ldp;
-    const int64_t total = (int64_t)nat_rows * ldp;
-    tc_prep_kernel<<<(int)imin64((total + 255) / 256, 148 * 16), 256, 0, st>>>(ptr, ld, nat_rows, nat_cols, nat_rows, (int)ldp, x->hi, x->lo);
-    ASE_LAUNCH_OK();
+    if (!H) {
+      const int64_t ldp = pad_to(nat_cols, 4);
+      if ((int64_t)nat_rows * ldp > x->plane_capacity || (int64_t)(nat_rows - 1) * ld + nat_cols > x->capacity) return ASE_OK;
+      x->ld = ld; x->rows = nat_rows; x->cols = nat_cols; x->ldp = ldp;
+      const int64_t total = (int64_t)nat_rows * ldp;
+      tc_prep_kernel<<<(int)imin64((total + 255) / 256, 148 * 16), 256, 0, st>>>(ptr, ld, nat_rows, nat_cols, nat_rows, (int)ldp, x->hi, x->lo);
+      ASE_LAUNCH_OK();
+    } else {
+      int as = x->amax_slot;
+      if (as < 0) {                          // written by a non-GEMM kernel (or accumulated into): one max pass over the reader's view
+        const int64_t ldp = pad_to(nat_cols, 8);
+        if ((int64_t)nat_rows * ldp > 2 * x->plane_capacity || (int64_t)(nat_rows - 1) * ld + nat_cols > x->capacity) return ASE_OK;
+        as = reg->new_slot();
+        if (as < 0) { set_error("tcgen05 FP16 GEMM: out of amax slots"); return ASE_ERR_WORKSPACE; }
+        x->ld = ld; x->rows = nat_rows; x->cols = nat_cols;
+        int rc = launch_amax(ptr, ld, nat_rows, nat_cols, reg->amax + as, st);
+        if (rc) return rc;
+      }                                      // else: produced by a GEMM of this call, which declared the geometry and tracked max |C|
+      x->ldp = pad_to(x->cols, 8);
+      int rc = launch_prep_h(ptr, x->ld, x->rows, x->cols, x->rows, (int)x->ldp, x->hi, x->lo, reg->amax + as, reg->bscale + 2 * (x - reg->b), st);
+      if (rc) return rc;
+    }
     x->valid = true;
   }
   if (ld != x->ld) return ASE_OK;
   const int64_t off = ptr - x->base;
   const int64_t r0 = off / x->ld, c0 = off - r0 * x->ld;
-  if ((c0 & 3) || r0 + nat_rows > x->rows || c0 + nat_cols > x->cols) return ASE_OK;
-  v->hi = x->hi + r0 * x->ldp + c0; v->lo = x->lo + r0 * x->ldp + c0; v->ldp = x->ldp; v->ok = true;
+  if ((c0 & (pal - 1)) || r0 + nat_rows > x->rows || c0 + nat_cols > x->cols) return ASE_OK;
+  if (!H) { v->hi = x->hi + r0 * x->ldp + c0; v->lo = x->lo + r0 * x->ldp + c0; }
+  else { v->hi = (const __half*)x->hi + r0 * x->ldp + c0; v->lo = (const __half*)x->lo + r0 * x->ldp + c0; v->scale = reg->bscale + 2 * (x - reg->b); }
+  v->ldp = x->ldp; v->ok = true;
   return ASE_OK;
 }
 
 // tensor map over a (sub-)view of a plane with TRUE extents: TMA zero-fills everything outside [rows, cols]
-static int make_view_map(CUtensorMap* tm, const float* base, int rows, int cols, int64_t ldp, int box_rows, bool mn_major) {
-  return encode_cached(tm, base, rows, cols, ldp, box_rows, mn_major);
+static int make_view_map(CUtensorMap* tm, const void* base, int rows, int cols, int64_t ldp, int box_rows, bool mn_major, bool half) {
+  return encode_cached(tm, base, rows, cols, ldp, box_rows, mn_major, half);
 }
 
 int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
+  const bool H = p.backend == 2;             // scaled FP16 hi/lo planes instead of TF32 ones
+  if (reg && reg->f16 != H) { set_error("tcgen05 GEMM: plane registry format does not match backend %d", p.backend); return ASE_ERR_INVALID; }
+  const int BK = H ? 64 : 32, MNB = H ? 64 : 32;
   const int BN = (p.N > 64) ? 128 : 64;
   const bool use256 = tc_tile256() && p.N >= 384;               // 128x256 tiles (B maps keep 128-row boxes: two per stage)
-  int CL = (BN == 128 && p.N > 128 && !use256) ? tc_cluster() : 1;       // A-multicast groups need >= 2 N tiles
+  int CL = (!H && BN == 128 && p.N > 128 && !use256) ? tc_cluster() : 1;       // A-multicast groups need >= 2 N tiles
   if (CL == 4 && p.N <= 384) CL = 2;
   const int a_box = TC_BM / CL;
-  const int Mp = pad_to(p.M, 128), Np = pad_to(p.N, 128), Kp = pad_to(p.K, TC_BK);
+  const int Mp = pad_to(p.M, 128), Np = pad_to(p.N, 128), Kp = pad_to(p.K, BK);
   int rc;
   // ---- operands: cached planes when the buffer is registered, else a split pass into the shared workspace
   OpView va, vb;
@@ -830,32 +1040,53 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   CUtensorMap ah, al, bh, bl;
   char* ws = (char*)p.workspace;
   if (!va.ok || !vb.ok) { if ((rc = gemm_tc_check_workspace(p))) return rc; }
+  // FP16 format, unregistered operands: transient amax / scale slots from the registry, or the workspace head without one
+  unsigned* t_amax[2] = {nullptr, nullptr}; float* t_scale[2] = {nullptr, nullptr};
+  if (H && (!va.ok || !vb.ok)) {
+    if (reg) {
+      for (int i = 0; i < 2; ++i) {
+        if (i == 0 ? va.ok : vb.ok) continue;
+        const int sl = reg->new_slot();
+        if (sl < 0) { set_error("tcgen05 FP16 GEMM: out of amax slots"); return ASE_ERR_WORKSPACE; }
+        t_amax[i] = reg->amax + sl; t_scale[i] = reg->tscale + 2 * sl;
+      }
+    } else {
+      ASE_CUDA_OK(cudaMemsetAsync(ws, 0, 2 * sizeof(unsigned), st));
+      t_amax[0] = (unsigned*)ws; t_amax[1] = (unsigned*)ws + 1; t_scale[0] = (float*)(ws + 16); t_scale[1] = (float*)(ws + 32);
+    }
+  }
+  char* wsp = ws + TC_WS_HEAD;
   if (va.ok) {
-    if ((rc = make_view_map(&ah, va.hi, a_rows, a_cols, va.ldp, p.a_trans ? 32 : a_box, p.a_trans != 0)) ||
-        (rc = make_view_map(&al, va.lo, a_rows, a_cols, va.ldp, p.a_trans ? 32 : a_box, p.a_trans != 0))) return rc;
+    if ((rc = make_view_map(&ah, va.hi, a_rows, a_cols, va.ldp, p.a_trans ? BK : a_box, p.a_trans != 0, H)) ||
+        (rc = make_view_map(&al, va.lo, a_rows, a_cols, va.ldp, p.a_trans ? BK : a_box, p.a_trans != 0, H))) return rc;
   } else {
-    float* Ahi = (float*)ws; float* Alo = (float*)(ws + align_up((int64_t)Mp * Kp * 4, 1024));
-    if ((rc = prep_operand(p.A, p.lda, p.a_trans, p.M, p.K, Mp, Kp, Ahi, Alo, st))) return rc;
-    if (!p.a_trans) { if ((rc = make_map(&ah, Ahi, Mp, Kp, a_box)) || (rc = make_map(&al, Alo, Mp, Kp, a_box))) return rc; }
-    else            { if ((rc = make_map(&ah, Ahi, Kp, Mp, 32, true)) || (rc = make_map(&al, Alo, Kp, Mp, 32, true))) return rc; }
+    float* Ahi = (float*)wsp; float* Alo = (float*)(wsp + align_up((int64_t)Mp * Kp * 4, 1024));
+    if (!H) { if ((rc = prep_operand(p.A, p.lda, p.a_trans, p.M, p.K, Mp, Kp, Ahi, Alo, st))) return rc; }
+    else { if ((rc = prep_operand_h(p.A, p.lda, p.a_trans, p.M, p.K, Mp, Kp, Ahi, Alo, t_amax[0], t_scale[0], st))) return rc; va.scale = t_scale[0]; }
+    if (!p.a_trans) { if ((rc = make_map(&ah, Ahi, Mp, Kp, a_box, false, H)) || (rc = make_map(&al, Alo, Mp, Kp, a_box, false, H))) return rc; }
+    else            { if ((rc = make_map(&ah, Ahi, Kp, Mp, BK, true, H)) || (rc = make_map(&al, Alo, Kp, Mp, BK, true, H))) return rc; }
   }
   if (vb.ok) {
-    if ((rc = make_view_map(&bh, vb.hi, b_rows, b_cols, vb.ldp, p.b_trans ? 32 : BN, p.b_trans != 0)) ||
-        (rc = make_view_map(&bl, vb.lo, b_rows, b_cols, vb.ldp, p.b_trans ? 32 : BN, p.b_trans != 0))) return rc;
+    if ((rc = make_view_map(&bh, vb.hi, b_rows, b_cols, vb.ldp, p.b_trans ? BK : BN, p.b_trans != 0, H)) ||
+        (rc = make_view_map(&bl, vb.lo, b_rows, b_cols, vb.ldp, p.b_trans ? BK : BN, p.b_trans != 0, H))) return rc;
   } else {
-    char* wb = ws + 2 * align_up((int64_t)Mp * Kp * 4, 1024);
+    char* wb = wsp + 2 * align_up((int64_t)Mp * Kp * 4, 1024);
     float* Bhi = (float*)wb; float* Blo = (float*)(wb + align_up((int64_t)Np * Kp * 4, 1024));
-    if ((rc = prep_operand(p.B, p.ldb, p.b_trans, p.N, p.K, Np, Kp, Bhi, Blo, st))) return rc;
-    if (!p.b_trans) { if ((rc = make_map(&bh, Bhi, Np, Kp, BN)) || (rc = make_map(&bl, Blo, Np, Kp, BN))) return rc; }
-    else            { if ((rc = make_map(&bh, Bhi, Kp, Np, 32, true)) || (rc = make_map(&bl, Blo, Kp, Np, 32, true))) return rc; }
+    if (!H) { if ((rc = prep_operand(p.B, p.ldb, p.b_trans, p.N, p.K, Np, Kp, Bhi, Blo, st))) return rc; }
+    else { if ((rc = prep_operand_h(p.B, p.ldb, p.b_trans, p.N, p.K, Np, Kp, Bhi, Blo, t_amax[1], t_scale[1], st))) return rc; vb.scale = t_scale[1]; }
+    if (!p.b_trans) { if ((rc = make_map(&bh, Bhi, Np, Kp, BN, false, H)) || (rc = make_map(&bl, Blo, Np, Kp, BN, false, H))) return rc; }
+    else            { if ((rc = make_map(&bh, Bhi, Kp, Np, BK, true, H)) || (rc = make_map(&bl, Blo, Kp, Np, BK, true, H))) return rc; }
   }
+  (void)MNB;
   TcEpi e;
   e.C = p.C; e.ldc = p.ldc; e.M = p.M; e.N = p.N; e.K = p.K; e.alpha = p.alpha; e.bias = p.bias; e.act = p.act;
   e.mask_src = p.mask_src; e.ldm = p.ldm; e.mask_mode = p.mask_src ? p.mask_mode : 0; e.accumulate = p.accumulate;
   e.Chi = e.Clo = nullptr; e.ldp = 0; e.colsum = p.colsum_out;
+  e.a_inv = (H && va.scale) ? va.scale + 1 : nullptr; e.b_inv = (H && vb.scale) ? vb.scale + 1 : nullptr;
+  e.c_scale = nullptr; e.c_amax = nullptr;
   // ---- output planes: a full write at the base of a registered buffer (re)declares its geometry; a partial write
   // keeps planes in sync only if they are currently valid with the same leading dimension; accumulation invalidates
-  if (reg) {
+  if (reg && !H) {
     if (PlaneBuf* x = reg->find(p.C)) {
       if (p.accumulate) x->valid = false;
       else if (p.C == x->base && (int64_t)p.M * pad_to(p.N, 4) <= x->plane_capacity && !(x->valid && x->ld == p.ldc && (x->rows > p.M || x->cols > p.N))) {
@@ -867,18 +1098,34 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
         else x->valid = false;
       } else x->valid = false;
     }
+  } else if (reg && H) {
+    // FP16 format: the planes of C need C's max first, so the epilogue only TRACKS max |C| (a full write at the buffer base);
+    // the first consumer turns it into the scale and splits.  Anything else leaves the max unknown (one extra pass on first read).
+    if (PlaneBuf* x = reg->find(p.C)) {
+      x->valid = false; x->amax_slot = -1;
+      if (!p.accumulate && p.C == x->base && (int64_t)p.M * pad_to(p.N, 8) <= 2 * x->plane_capacity && (int64_t)(p.M - 1) * p.ldc + p.N <= x->capacity) {
+        const int sl = reg->new_slot();
+        if (sl >= 0) { x->ld = p.ldc; x->rows = p.M; x->cols = p.N; x->amax_slot = sl; e.c_amax = reg->amax + sl; }
+      }
+    }
   }
-  e.kb_total = Kp / TC_BK;
+  e.kb_total = Kp / BK;
   { static int dbg = -1; if (dbg < 0) { const char* d = getenv("ASE_TC_DEBUG"); dbg = d ? atoi(d) : 0; } e.debug = dbg; }
   int splits = (p.accumulate && p.split_k > 1) ? p.split_k : 1;
   splits = min(splits, e.kb_total);
   e.kb_per_split = ceil_div(e.kb_total, splits);
   splits = ceil_div(e.kb_total, e.kb_per_split);
-  if (use256) return launch_tc256_major(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
-  if (BN == 128 && CL == 4) return launch_tc_major<128, 3, 4>(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
-  if (BN == 128 && CL == 2) return launch_tc_major<128, 3, 2>(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
-  if (BN == 128) return launch_tc_major<128, 3, 1>(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
-  return launch_tc_major<64, 4, 1>(p.a_trans != 0, p.b_trans != 0, ah, al, bh, bl, e, splits, st);
+  const bool amn = p.a_trans != 0, bmn = p.b_trans != 0;
+  if (H) {
+    if (use256) return launch_tc256_major<true>(amn, bmn, ah, al, bh, bl, e, splits, st);
+    if (BN == 128) return launch_tc_major<128, 3, 1, true>(amn, bmn, ah, al, bh, bl, e, splits, st);
+    return launch_tc_major<64, 4, 1, true>(amn, bmn, ah, al, bh, bl, e, splits, st);
+  }
+  if (use256) return launch_tc256_major<false>(amn, bmn, ah, al, bh, bl, e, splits, st);
+  if (BN == 128 && CL == 4) return launch_tc_major<128, 3, 4, false>(amn, bmn, ah, al, bh, bl, e, splits, st);
+  if (BN == 128 && CL == 2) return launch_tc_major<128, 3, 2, false>(amn, bmn, ah, al, bh, bl, e, splits, st);
+  if (BN == 128) return launch_tc_major<128, 3, 1, false>(amn, bmn, ah, al, bh, bl, e, splits, st);
+  return launch_tc_major<64, 4, 1, false>(amn, bmn, ah, al, bh, bl, e, splits, st);
 }
 
 }  // namespace ase

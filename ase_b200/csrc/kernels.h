@@ -24,13 +24,25 @@ int gemm_simt(const AseGemmParams& p, cudaStream_t st);
 // TF32 hi/lo operand planes kept next to registered fp32 buffers (gemm_tc.cu)
 struct PlaneBuf {
   const float* base; int64_t capacity;          // fp32 buffer (floats)
-  float* hi; float* lo; int64_t plane_capacity; // planes (floats each)
+  float* hi; float* lo; int64_t plane_capacity; // planes (floats each; the FP16 format stores halfs in the same space)
   int64_t ld; int rows, cols; int64_t ldp;      // geometry declared by the last full writer / first reader
   bool valid;
+  int amax_slot;                                // FP16 format: transient slot holding max |x| of the current contents, -1 = unknown
 };
 struct PlaneRegistry {
   static constexpr int MAX = 160;
+  static constexpr int SLOTS = 1024;
   PlaneBuf b[MAX]; int n = 0;
+  // FP16 format (backend 2): per-tensor power-of-two scales live in device memory (no host sync anywhere)
+  bool f16 = false;
+  unsigned* amax = nullptr;     // [SLOTS] transient max |x| slots (uint bits), zeroed by begin_call
+  float* tscale = nullptr;      // [SLOTS][2] scale / inverse of unregistered operands split into the shared workspace
+  float* bscale = nullptr;      // [MAX][2] scale / inverse of each registered buffer's current planes
+  int n_slots = 0, next_slot = 0;
+  static int64_t device_bytes() { return (int64_t)SLOTS * 4 + (int64_t)SLOTS * 8 + (int64_t)MAX * 8; }
+  void attach_device(void* mem) { amax = (unsigned*)mem; tscale = (float*)((char*)mem + SLOTS * 4); bscale = tscale + 2 * SLOTS; n_slots = SLOTS; }
+  int begin_call(cudaStream_t st);
+  int new_slot();
   PlaneBuf* find(const float* p);
   // a non-GEMM kernel is about to write the whole buffer [rows, cols] (ld) INCLUDING its planes: returns the entry (valid) or null
   PlaneBuf* declare(const float* base, int64_t ld, int rows, int cols);
@@ -38,7 +50,7 @@ struct PlaneRegistry {
   void invalidate(const float* p);
   void invalidate_range(const float* lo_, const float* hi_);
 };
-int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg = nullptr);   // tcgen05 3xTF32 (gemm_tc.cu)
+int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg = nullptr);   // tcgen05 3xTF32 (backend 1) / 3xFP16-scaled (backend 2) (gemm_tc.cu)
 bool gemm_tc_supported(const AseGemmParams& p);
 int64_t gemm_tc_workspace_bytes(int M, int N, int K);
 int gemm_tc_tile_n(int N);      // N extent of the output tile the tcgen05 backend will use for this N

@@ -91,6 +91,7 @@ struct AseLearner {
   float* act_planes; int64_t act_plane_floats;     // carved region for activation planes
   float* w_planes; int64_t w_plane_floats;         // carved region for weight planes
   const float* reg_params;                         // parameter arena the weight entries currently point at
+  void* reg_dev;                                   // FP16 format: device amax / scale slots of the registry
 };
 
 namespace ase {
@@ -106,7 +107,7 @@ struct Carver {
 };
 
 static int64_t tc_ws_need(const AseLearner& L) {
-  if (L.cfg.gemm_backend != 1) return 0;
+  if (L.cfg.gemm_backend < 1) return 0;
   int64_t need = 0;
   auto upd = [&](int64_t M, int64_t N, int64_t K) { need = imax64(need, gemm_tc_workspace_bytes((int)M, (int)N, (int)K)); };
   const AseLearnerConfig& c = L.cfg;
@@ -163,7 +164,8 @@ static void carve(AseLearner& L, void* ws, int64_t* total) {
   L.tc_ws_bytes = tc_ws_need(L);
   cv.off = align_up(cv.off, 1024);
   L.tc_ws = L.tc_ws_bytes ? cv.take<char>(L.tc_ws_bytes) : nullptr;
-  if (c.gemm_backend == 1) {
+  L.reg_dev = (c.gemm_backend == 2) ? cv.take<char>(PlaneRegistry::device_bytes()) : nullptr;
+  if (c.gemm_backend >= 1) {
     // activation planes: registered lazily in register_planes(); size = 2 x (sum of registered fp32 buffers, ld padded to 4)
     int64_t act = 0;
     auto add = [&](int64_t rows, int64_t cols) { act += rows * align_up(cols, 4); };
@@ -187,9 +189,9 @@ static void carve(AseLearner& L, void* ws, int64_t* total) {
 
 // (Re)build the plane registry: activation buffers once, weight entries whenever the parameter arena pointer changes.
 static void register_planes(AseLearner& L, const float* params) {
-  if (L.cfg.gemm_backend != 1) return;
+  if (L.cfg.gemm_backend < 1) return;
   const AseLearnerConfig& c = L.cfg;
-  if (!L.reg) L.reg = new PlaneRegistry;
+  if (!L.reg) { L.reg = new PlaneRegistry; if (c.gemm_backend == 2) { L.reg->f16 = true; L.reg->attach_device(L.reg_dev); } }
   if (L.reg->n > 0 && L.reg_params == params) return;
   PlaneRegistry& R = *L.reg;
   R.n = 0;
@@ -275,7 +277,7 @@ struct G {
     p.A = dZ; p.lda = ldz; p.a_trans = 1; p.B = X; p.ldb = ldx; p.b_trans = 1; p.C = GR + l.w; p.ldc = l.in;
     p.M = l.out; p.N = l.in; p.K = M; p.accumulate = 1;
     // split-K so that tiles x splits fills whole waves of the 148 SMs; every extra split adds one RED pass over dW
-    const int tiles = ceil_div(l.out, 128) * ceil_div(l.in, L.cfg.gemm_backend == 1 ? gemm_tc_tile_n(l.in) : 128);
+    const int tiles = ceil_div(l.out, 128) * ceil_div(l.in, L.cfg.gemm_backend >= 1 ? gemm_tc_tile_n(l.in) : 128);
     const int smax = max(1, min(16, M / 1024));
     int best = 1; double best_cost = 1e30;
     for (int s = 1; s <= smax; ++s) {
@@ -420,6 +422,7 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
   ASE_CHECK_ARG(out->scalars, "calc_gradients: scalars output");
   const int B = L.B, Ba = L.Ba, Ra = L.Ra, Z = c.latent_dim, A = c.act_dim;
   register_planes(L, s->params);
+  if (L.reg) RC(L.reg->begin_call(st));
   G g{L, st, s->params, s->grads};
 
   ASE_CUDA_OK(cudaMemsetAsync(L.acc, 0, ACC_COUNT * sizeof(double), st));
@@ -598,6 +601,7 @@ extern "C" int ase_learner_eval_actor_critic(AseLearner* lp, const AseLearnerSta
   ASE_CHECK_ARG(!L.ase || latents, "eval_actor_critic: latents required");
   cudaStream_t st = (cudaStream_t)stream;
   register_planes(L, s->params);
+  if (L.reg) RC(L.reg->begin_call(st));
   G g{L, st, s->params, s->grads};
   RC(rms_apply(obs, c.obs_dim, rows, c.obs_dim, s->obs_mean, s->obs_var, c.rms_eps, 0, L.Xa, L.ldx, st));
   g.inval(L.Xa); g.inval(L.Xc); g.inval(L.Zc);
@@ -621,6 +625,7 @@ extern "C" int ase_learner_eval_disc_enc(AseLearner* lp, const AseLearnerState* 
   ASE_CHECK_ARG(!enc_pred || L.ase, "eval_disc_enc: enc_pred needs an ASE learner");
   cudaStream_t st = (cudaStream_t)stream;
   register_planes(L, s->params);
+  if (L.reg) RC(L.reg->begin_call(st));
   G g{L, st, s->params, s->grads};
   RC(rms_apply(amp_obs, c.amp_dim, rows, c.amp_dim, s->amp_mean, s->amp_var, c.rms_eps, 0, L.Xd, L.amp_ld, st));
   g.inval(L.Xd);

@@ -194,7 +194,7 @@ def gemm(A, B, a_trans=False, b_trans=False, bias=None, act=0, mask_src=None, ma
     if out is None:
         out = torch.zeros(M, N, device=A.device, dtype=torch.float32)
     ws, wsb = None, 0
-    if backend == 1:
+    if backend >= 1:
         wsb = lib.ase_gemm_tc_workspace_bytes(M, N, K)
         ws = torch.empty(wsb + 1024, dtype=torch.uint8, device=A.device)
         off = (-ws.data_ptr()) % 1024

@@ -1,7 +1,8 @@
 """GPU parity tests for the GEMM backends through ase_gemm (C ABI).
   backend 0 (SIMT fp32)    vs torch fp64 matmul: <= 1e-5 relative to max|C| (fp32 accumulation order only)
   backend 1 (tcgen05 3xTF32) vs torch fp64 matmul: <= 2e-5 relative to max|C|  -- i.e. fp32-class accuracy,
-  two orders of magnitude tighter than single-pass TF32 (~2e-3) so a broken hi/lo split cannot hide."""
+  two orders of magnitude tighter than single-pass TF32 (~2e-3) so a broken hi/lo split cannot hide.
+  backend 2 (tcgen05 3xFP16, per-tensor power-of-two scaled hi/lo planes): the same bar."""
 import pytest
 import torch
 
@@ -72,56 +73,87 @@ def test_simt_learner_shapes():
     _run(1024, 317, 2048, True, True, 0, accumulate=True, split_k=4, tol=2e-5)
 
 
+TC_BACKENDS = [1, 2]      # 1: 3xTF32 planes, 2: 3xFP16 scaled planes -- same kernels, same bar
+
+
+@pytest.mark.parametrize('tc', TC_BACKENDS)
 @pytest.mark.parametrize('a_trans,b_trans', [(False, False), (False, True), (True, False), (True, True)])
-def test_tc_matches_fp64(a_trans, b_trans):
+def test_tc_matches_fp64(a_trans, b_trans, tc):
     # a_trans / b_trans operands are consumed MN-major by the tensor core (no transposition pass)
-    _run(256, 256, 64, a_trans, b_trans, 1, tol=1e-5)
-    _run(384, 192, 317, a_trans, b_trans, 1, lda_pad=3, tol=1e-5)     # ragged K (zero padded to 320), N tail with BN=128
-    _run(1000, 100, 96, a_trans, b_trans, 1, tol=1e-5)                # ragged M and N
-    _run(200, 40, 50, a_trans, b_trans, 1, tol=1e-5)                  # BN = 64 path
-    _run(31, 512, 700, a_trans, b_trans, 1, tol=1e-5)                 # M smaller than one tile (mu-head weight gradient)
-    _run(300, 1, 512, a_trans, b_trans, 1, tol=1e-5)                  # N = 1 (value / logit heads)
-    _run(512, 96, 1, a_trans, b_trans, 1, tol=1e-5)                   # K = 1 outer product
-    _run(1, 1, 1, a_trans, b_trans, 1, tol=1e-5)
+    _run(256, 256, 64, a_trans, b_trans, tc, tol=1e-5)
+    _run(384, 192, 317, a_trans, b_trans, tc, lda_pad=3, tol=1e-5)     # ragged K (zero padded to 320), N tail with BN=128
+    _run(1000, 100, 96, a_trans, b_trans, tc, tol=1e-5)                # ragged M and N
+    _run(200, 40, 50, a_trans, b_trans, tc, tol=1e-5)                  # BN = 64 path
+    _run(31, 512, 700, a_trans, b_trans, tc, tol=1e-5)                 # M smaller than one tile (mu-head weight gradient)
+    _run(300, 1, 512, a_trans, b_trans, tc, tol=1e-5)                  # N = 1 (value / logit heads)
+    _run(512, 96, 1, a_trans, b_trans, tc, tol=1e-5)                   # K = 1 outer product
+    _run(1, 1, 1, a_trans, b_trans, tc, tol=1e-5)
 
 
+@pytest.mark.parametrize('tc', TC_BACKENDS)
 @pytest.mark.parametrize('a_trans,b_trans', [(False, False), (False, True), (True, False), (True, True)])
-def test_tc_wide_tiles_128x256(a_trans, b_trans):
+def test_tc_wide_tiles_128x256(a_trans, b_trans, tc):
     """N >= 384 runs on the 128x256-tile kernel (8 drain warps, single-buffered main accumulator)."""
-    _run(256, 512, 96, a_trans, b_trans, 1, tol=1e-5)
-    _run(300, 1400, 317, a_trans, b_trans, 1, lda_pad=3, tol=1e-5)      # ragged everything, 6 N tiles with a tail
-    _run(1000, 384, 1024, a_trans, b_trans, 1, bias=True, act=1, tol=1e-5)
-    _run(512, 1024, 2048, a_trans, b_trans, 1, mask_mode=1, tol=1e-5)    # long K: many main/corr hand-offs
+    _run(256, 512, 96, a_trans, b_trans, tc, tol=1e-5)
+    _run(300, 1400, 317, a_trans, b_trans, tc, lda_pad=3, tol=1e-5)      # ragged everything, 6 N tiles with a tail
+    _run(1000, 384, 1024, a_trans, b_trans, tc, bias=True, act=1, tol=1e-5)
+    _run(512, 1024, 2048, a_trans, b_trans, tc, mask_mode=1, tol=1e-5)    # long K: many main/corr hand-offs
 
 
-def test_tc_wide_tiles_split_k_and_colsum():
+@pytest.mark.parametrize('tc', TC_BACKENDS)
+def test_tc_wide_tiles_split_k_and_colsum(tc):
     from ase_b200 import ops
-    _run(1024, 1024, 8192, True, True, 1, accumulate=True, split_k=3, tol=2e-5)
+    _run(1024, 1024, 8192, True, True, tc, accumulate=True, split_k=3, tol=2e-5)
     g = torch.Generator().manual_seed(5)
     A = torch.randn(700, 256, generator=g).cuda(); B = torch.randn(512, 256, generator=g).cuda()
     cs = torch.zeros(512, device='cuda')
-    C = ops.gemm(A, B, backend=1, colsum_out=cs)
+    C = ops.gemm(A, B, backend=tc, colsum_out=cs)
     ref = A.double() @ B.double().t()
     assert float((C.double() - ref).abs().max() / ref.abs().max()) < 1e-5
     assert float((cs.double() - ref.sum(0)).abs().max() / ref.sum(0).abs().max()) < 1e-5
 
 
-def test_tc_epilogues_and_split_k():
-    _run(512, 256, 512, False, False, 1, bias=True, act=1, tol=1e-5)
-    _run(256, 128, 256, False, False, 1, bias=True, act=2, alpha=1.0 / 16, tol=3e-5)   # O(1) pre-activations
-    _run(512, 320, 256, False, True, 1, mask_mode=1, tol=2e-5)
-    _run(256, 64, 128, False, True, 1, mask_mode=2, tol=2e-5)
-    _run(1024, 512, 4096, True, True, 1, accumulate=True, split_k=5, tol=3e-5)
-    _run(256, 256, 2048, False, False, 1, alpha=0.25, tol=2e-5)      # > STAGES k-blocks: ring wrap-around + phase flips
+@pytest.mark.parametrize('tc', TC_BACKENDS)
+def test_tc_epilogues_and_split_k(tc):
+    _run(512, 256, 512, False, False, tc, bias=True, act=1, tol=1e-5)
+    _run(256, 128, 256, False, False, tc, bias=True, act=2, alpha=1.0 / 16, tol=3e-5)   # O(1) pre-activations
+    _run(512, 320, 256, False, True, tc, mask_mode=1, tol=2e-5)
+    _run(256, 64, 128, False, True, tc, mask_mode=2, tol=2e-5)
+    _run(1024, 512, 4096, True, True, tc, accumulate=True, split_k=5, tol=3e-5)
+    _run(256, 256, 2048, False, False, tc, alpha=0.25, tol=2e-5)      # > STAGES k-blocks: ring wrap-around + phase flips
 
 
-def test_tc_accuracy_is_fp32_class_not_tf32():
+def test_tc_fp16_planes_dynamic_range():
+    """Backend 2 scales every tensor by a power of two before the FP16 hi/lo split: gradient-sized (1e-9) and large (1e+6)
+    operands, and a tensor whose entries span 7 decades, must come out as accurately as O(1) ones."""
+    from ase_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    A = torch.randn(300, 512, generator=g); B = torch.randn(200, 512, generator=g)
+    for sa, sb in ((1e-9, 1.0), (1e6, 1e-3), (3e-20, 7e12), (1e-30, 1e-5)):
+        a = (A * sa).cuda(); b = (B * sb).cuda()
+        C = ops.gemm(a, b, backend=2)
+        ref = a.double() @ b.double().t()
+        assert float((C.double() - ref).abs().max() / ref.abs().max()) < 1e-5, (sa, sb)
+    # rows of very different magnitude inside one tensor: each output row is judged against ITS OWN scale down to 1e-5 of the
+    # tensor max (hi + lo keeps 22 significant bits for every element within 2^-26 of the max)
+    rs = torch.logspace(0, -5, 300).unsqueeze(1)
+    a = (A * rs).cuda(); b = B.cuda()
+    C = ops.gemm(a, b, backend=2)
+    ref = a.double() @ b.double().t()
+    err = (C.double() - ref).abs().amax(1) / ref.abs().amax(1)
+    assert float(err.max()) < 2e-5, float(err.max())
+    z = ops.gemm(torch.zeros(64, 64, device='cuda'), b[:, :64].contiguous(), backend=2)       # all-zero operand: scale 1, exact zeros
+    assert float(z.abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('tc', TC_BACKENDS)
+def test_tc_accuracy_is_fp32_class_not_tf32(tc):
     """Inputs chosen so that single-pass TF32 would miss by ~1e-3: all products need the low halves."""
     from ase_b200 import ops
     g = torch.Generator().manual_seed(1)
     A = (1.0 + torch.rand(256, 1024, generator=g) * 1e-3).cuda()      # values whose information sits below TF32's 10 mantissa bits
     B = (1.0 + torch.rand(128, 1024, generator=g) * 1e-3).cuda()
-    C = ops.gemm(A, B, backend=1)
+    C = ops.gemm(A, B, backend=tc)
     ref = A.double() @ B.double().t()
     # single-pass TF32 rounds every operand to 10 mantissa bits: |err| ~ 0.25 on these sums of ~1025.  3xTF32 with the
     # tensor core accumulating across all of K left a one-sided 0.006 (truncating accumulator); with the k-block partials

@@ -93,12 +93,13 @@ def test_calc_gradients_vs_reference_golden_simt(name):
     _run_golden(name, backend=0)
 
 
+@pytest.mark.parametrize('backend', [1, 2])      # 1: 3xTF32 planes, 2: 3xFP16 scaled planes
 @pytest.mark.parametrize('name', ['calc_grad_ase_cfg1.pt', 'calc_grad_amp_cfg.pt'])
-def test_calc_gradients_vs_reference_golden_tcgen05(name):
+def test_calc_gradients_vs_reference_golden_tcgen05(name, backend):
     import ctypes as C
     from ase_b200 import lib as L
     L.lib.ase_gemm_tc_profile(1)
-    _run_golden(name, backend=1)
+    _run_golden(name, backend=backend)
     ms, n, fl = C.c_double(), C.c_int64(), C.c_double()
     L.check(L.lib.ase_gemm_tc_profile_read(C.byref(ms), C.byref(n), C.byref(fl)), 'profile_read')
     L.lib.ase_gemm_tc_profile(0)
@@ -194,7 +195,7 @@ def test_full_size_minibatch_properties():
     assert abs(outs[0][1]['disc_loss'] - outs[1][1]['disc_loss']) < 1e-4 * abs(outs[0][1]['disc_loss'])
 
 
-@pytest.mark.parametrize('backend', [0, 1])
+@pytest.mark.parametrize('backend', [0, 1, 2])
 def test_hrl_high_level_learner_vs_reference_golden(backend):
     """BASELINE config 5 learner: plain PPO over the tanh-mu HLC network (hrl_network_builder.py:26-29), obs 258, act 64."""
     from ase_b200 import Learner
