@@ -126,7 +126,7 @@ class CommonAgent:
         hp = {k: config[k] for k in ('e_clip', 'critic_coef', 'entropy_coef', 'bounds_loss_coef', 'learning_rate') if k in config}
         sigma = np_['space']['continuous']['sigma_init'].get('val', 0.0)
         return dict(obs_dim=self.obs_shape[0], act_dim=self.actions_num, batch=self.minibatch_size, units=tuple(np_['mlp']['units']),
-                    hparams=hp, device=self.ppo_device, gemm_backend=config.get('gemm_backend', 1), sigma_init=sigma,
+                    hparams=hp, device=self.ppo_device, gemm_backend=config.get('gemm_backend', 2), sigma_init=sigma,
                     mu_activation=getattr(self, '_mu_activation', 'None'))
 
     def _build_learner(self, config):
@@ -639,7 +639,7 @@ class HRLAgent(CommonAgent):
             act = self.env_info['action_space'].shape[0]
             ln = Learner('ase', self.obs_shape[0] - self._task_size, act, self.num_actors, amp_dim=amp_dim, latent_dim=self._latent_dim,
                          amp_batch=max(2, self.num_actors), units=tuple(np_['mlp']['units']), disc_units=tuple(np_['disc']['units']),
-                         device=self.ppo_device, gemm_backend=config.get('gemm_backend', 1))
+                         device=self.ppo_device, gemm_backend=config.get('gemm_backend', 2))
             ckpt = config.get('llc_checkpoint')
             if ckpt:
                 w = torch.load(ckpt, map_location='cpu', weights_only=True)

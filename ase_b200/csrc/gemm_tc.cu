@@ -31,8 +31,8 @@ constexpr int TC_THREADS = 192;
 
 // Operand-plane formats.  H = false: TF32 hi/lo planes stored as fp32 words (kind::tf32, K = 8 per MMA).
 // H = true: SCALED FP16 hi/lo planes (kind::f16, K = 16 per MMA, twice the MMA rate and half the plane bytes): each tensor is
-// multiplied by a per-tensor power of two that puts its max |x| in [2^12, 2^13) before the split, so hi + lo carries 22
-// significant bits for every element within 2^-26 of the tensor max (absolute floor 2^-25 / scale); the epilogue multiplies
+// multiplied by a per-tensor power of two that puts its max |x| in [2^8, 2^9) before the split, so hi + lo carries 22
+// significant bits for every element within 2^-22 of the tensor max (absolute floor 2^-25 / scale); the epilogue multiplies
 // by the two inverse scales (exact).  In both formats a k-block is ONE 128-byte swizzle row per operand row, so the shared
 // memory tiles, the TMA transaction bytes and the 4-MMAs-per-k-block structure are identical.
 template <bool H> struct TcFmt {
@@ -162,11 +162,14 @@ __device__ __forceinline__ uint32_t tc_idesc(bool amn, bool bmn, int bn) {
          ((uint32_t)(TC_BM >> 4) << 24);
 }
 
-// scale that puts amax into [2^12, 2^13); 1 for an all-zero / non-finite tensor
-__device__ __forceinline__ float scale_from_amax(float amax) {
+// scale that puts amax into [2^(top-1), 2^top); 1 for an all-zero / non-finite tensor.  Absolute split error 2^-25 / scale
+// = 2^-(24+top) of the tensor max.  TOP_SITE leaves 2^7 of headroom below the FP16 maximum for scales PREDICTED from the
+// previous call's max; TOP_EXACT is for a scale derived from the very tensor being split.
+constexpr int TOP_SITE = 9, TOP_EXACT = 13;
+__device__ __forceinline__ float scale_from_amax(float amax, int top) {
   if (!(amax > 0.0f) || !(amax < 3.0e38f)) return 1.0f;
   int e; frexpf(amax, &e);                      // amax = m * 2^e, m in [0.5, 1)
-  return ldexpf(1.0f, max(-100, min(100, 13 - e)));
+  return ldexpf(1.0f, max(-100, min(100, top - e)));
 }
 __device__ __forceinline__ void split_f16(float xs, __half& hi, __half& lo) {
   hi = __float2half_rn(xs);
@@ -196,7 +199,9 @@ struct TcEpi {
   const float* a_inv; const float* b_inv;  // FP16 planes: device pointers to the operands' inverse scales (null = 1)
   const float* c_scale;                    // FP16 planes of C: device pointer to the scale they are written with
   unsigned* c_amax;                        // optional: atomicMax of |C| (as uint bits) -- the scale source for the consumers of C
-  int debug;   // experiments only (env ASE_TC_DEBUG): 1 skip global stores, 2 skip TMEM drain loads, 4 skip correction MMAs, 8 skip bias/act
+  unsigned* flag;                          // FP16 planes of C written with a PREDICTED scale: sticky overflow flag (bit 0)
+  int debug;   // experiments only (env ASE_TC_DEBUG): 1 skip the whole store phase, 2 skip TMEM drain loads, 4 skip correction MMAs,
+               // 16 skip mask loads, 32 skip plane stores, 64 skip column-sum atomics, 128 skip the fp32 C store
 };
 
 // Phase 2 of the epilogue, shared by the tile shapes: a warp writes rows [row0, row0+nrows) of the staged tile; a row is
@@ -232,7 +237,7 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* cs, i
       }
       if (e.act == 1) { for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.0f); }
       else if (e.act == 2) { for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]); }
-      if (e.mask_mode) {
+      if (e.mask_mode && !(e.debug & 16)) {
         const float* mp = e.mask_src + (int64_t)m * e.ldm + n;
         float mv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         if (vec_ok && nvalid == 4) { const float4 q = *reinterpret_cast<const float4*>(mp); mv[0] = q.x; mv[1] = q.y; mv[2] = q.z; mv[3] = q.w; }
@@ -240,11 +245,12 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* cs, i
         if (e.mask_mode == 1) { for (int j = 0; j < 4; ++j) x[j] = (mv[j] > 0.0f) ? x[j] : 0.0f; }
         else { for (int j = 0; j < 4; ++j) x[j] *= (1.0f - mv[j] * mv[j]); }
       }
-      if (vec_ok && nvalid == 4) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+      if (e.debug & 128) {}
+      else if (vec_ok && nvalid == 4) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
       else for (int j = 0; j < nvalid; ++j) cp[j] = x[j];
 #pragma unroll
       for (int j = 0; j < 4; ++j) { cs4[j] += x[j]; if (j < nvalid) amax = fmaxf(amax, fabsf(x[j])); }
-      if (e.Chi) {       // the consumers of C read these planes directly through TMA: no separate split pass
+      if (e.Chi && !(e.debug & 32)) {       // the consumers of C read these planes directly through TMA: no separate split pass
         if (!H) {
           float h[4], l[4];
 #pragma unroll
@@ -266,12 +272,16 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* cs, i
         }
       }
     }
-    if (e.colsum && !e.accumulate) for (int j = 0; j < nvalid; ++j) atomicAdd(e.colsum + n + j, cs4[j]);
+    if (e.colsum && !e.accumulate && !(e.debug & 64)) for (int j = 0; j < nvalid; ++j) atomicAdd(e.colsum + n + j, cs4[j]);
   }
-  if (e.c_amax && !e.accumulate) {
+  if ((e.c_amax || (H && e.Chi && e.flag)) && !e.accumulate) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-    if (lane == 0 && amax > 0.0f) atomicMax(e.c_amax, __float_as_uint(amax));
+    if (lane == 0 && amax > 0.0f) {
+      if (e.c_amax) atomicMax(e.c_amax, __float_as_uint(amax));
+      if (H && e.Chi && e.flag && !(amax * cscale <= 60000.0f)) atomicOr(e.flag, 1u);     // the predicted scale was too large: report, never saturate silently
+      if (H && e.Chi && e.flag && cscale == 0.0f) atomicOr(e.flag, 2u);                   // the site only ever saw all-zero tensors, now there is data
+    }
   }
 }
 
@@ -676,17 +686,26 @@ tc_amax_kernel(const float* __restrict__ src, int64_t ld, int rows, int cols, un
   }
 }
 
-// FP16 format: scale from the tensor's max (read from device memory: no host sync), split src[rows, cols] (ld) into
-// zero-padded half planes [rows_p, cols_p]; 4 consecutive columns per thread (cols_p is a multiple of 8).  The scale and its
-// inverse are published in scale_out[0..1] for the epilogues of the GEMMs that consume these planes.
+// FP16 format: split src[rows, cols] (ld) into zero-padded half planes [rows_p, cols_p]; 4 consecutive columns per thread
+// (cols_p is a multiple of 8).  Two modes, both without a host sync:
+//   amax_in != null : EXACT  -- the scale is derived from the tensor's max (already in device memory) and published with its
+//                              inverse in scale_io[0..1] for the epilogues of the GEMMs that consume these planes;
+//   amax_in == null : PREDICTED -- scale_io holds the scale derived from the previous call's max at this site; this pass tracks
+//                              the current max into amax_out for the next call and raises flag bit 0 if a value does not fit.
 __global__ void __launch_bounds__(256)
 tc_prep_h_kernel(const float* __restrict__ src, int64_t ld, int rows, int cols, int rows_p, int cols_p, __half* __restrict__ hi,
-                 __half* __restrict__ lo, const unsigned* __restrict__ amax, float* __restrict__ scale_out) {
-  const float s = scale_from_amax(__uint_as_float(*amax));
-  if (blockIdx.x == 0 && threadIdx.x == 0) { scale_out[0] = s; scale_out[1] = 1.0f / s; }
+                 __half* __restrict__ lo, const unsigned* __restrict__ amax_in, float* __restrict__ scale_io, float* __restrict__ scale_copy,
+                 unsigned* __restrict__ amax_out, unsigned* __restrict__ flag, int top) {
+  float s;
+  if (amax_in) {
+    s = scale_from_amax(__uint_as_float(*amax_in), top);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { scale_io[0] = s; scale_io[1] = 1.0f / s; }
+  } else s = scale_io[0];
+  if (scale_copy && blockIdx.x == 0 && threadIdx.x == 0) { scale_copy[0] = s; scale_copy[1] = (s != 0.0f) ? 1.0f / s : 0.0f; }
   const int c4n = cols_p >> 2;
   const int64_t total = (int64_t)rows_p * c4n;
   const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  float m = 0.0f;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / c4n), c = (int)(i - (int64_t)r * c4n) * 4;
     float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
@@ -697,13 +716,40 @@ tc_prep_h_kernel(const float* __restrict__ src, int64_t ld, int rows, int cols, 
     }
     __half h[4], l[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) split_f16(x[j] * s, h[j], l[j]);
+    for (int j = 0; j < 4; ++j) { m = fmaxf(m, fabsf(x[j])); split_f16(x[j] * s, h[j], l[j]); }
     uint2 hv, lv;
     hv.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16); hv.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
     lv.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16); lv.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
     *reinterpret_cast<uint2*>(hi + (int64_t)r * cols_p + c) = hv;
     *reinterpret_cast<uint2*>(lo + (int64_t)r * cols_p + c) = lv;
   }
+  if (!amax_in) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) {
+      if (amax_out) atomicMax(amax_out, __float_as_uint(m));
+      if (flag && !(m * s <= 60000.0f)) atomicOr(flag, 1u);
+      if (flag && s == 0.0f) atomicOr(flag, 2u);       // the site only ever saw an all-zero tensor, now there is data
+    }
+  }
+}
+
+// FP16 format, start of every top-level call: fold the maxima tracked during the previous call into the sites' scales (the
+// prediction for this call), check that the previous prediction did not lose precision, and clear the maxima.
+__global__ void __launch_bounds__(256)
+tc_site_update_kernel(unsigned* __restrict__ amax, float* __restrict__ scale, int n, float* __restrict__ static_scale, float static_value,
+                      unsigned* __restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) { static_scale[0] = static_value; static_scale[1] = 1.0f / static_value; }
+  if (i >= n) return;
+  const float a = __uint_as_float(amax[i]);
+  const float s0 = scale[2 * i];
+  if (a > 0.0f) {
+    if (s0 != 0.0f && a * s0 < 0.015625f) atomicOr(flag, 2u);        // the tensor shrank by > 2^12 between two calls: the split lost bits
+    const float s = scale_from_amax(a, TOP_SITE);
+    scale[2 * i] = s; scale[2 * i + 1] = 1.0f / s;
+    amax[i] = 0u;
+  }                                          // a site that only ever saw all-zero tensors keeps scale 0 (zero planes, zero inverse)
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -810,21 +856,22 @@ static int launch_amax(const float* src, int64_t ld, int rows, int cols, unsigne
   ASE_LAUNCH_OK();
   return ASE_OK;
 }
-static int launch_prep_h(const float* src, int64_t ld, int rows, int cols, int rows_p, int cols_p, void* hi, void* lo, const unsigned* amax,
-                         float* scale_out, cudaStream_t st) {
+static int launch_prep_h(const float* src, int64_t ld, int rows, int cols, int rows_p, int cols_p, void* hi, void* lo, const unsigned* amax_in,
+                         float* scale_io, float* scale_copy, unsigned* amax_out, unsigned* flag, cudaStream_t st, int top = TOP_SITE) {
   const int64_t total = (int64_t)rows_p * (cols_p / 4);
-  tc_prep_h_kernel<<<(int)imin64((total + 255) / 256, 148 * 16), 256, 0, st>>>(src, ld, rows, cols, rows_p, cols_p, (__half*)hi, (__half*)lo, amax, scale_out);
+  tc_prep_h_kernel<<<(int)imin64((total + 255) / 256, 148 * 16), 256, 0, st>>>(src, ld, rows, cols, rows_p, cols_p, (__half*)hi, (__half*)lo, amax_in,
+                                                                              scale_io, scale_copy, amax_out, flag, top);
   ASE_LAUNCH_OK();
   return ASE_OK;
 }
-// FP16 format, unregistered operand: max pass + scaled split into the shared workspace
-static int prep_operand_h(const float* src, int64_t ld, int trans, int rows, int K, int rows_p, int Kp, void* hi, void* lo, unsigned* amax,
-                          float* scale_out, cudaStream_t st) {
-  const int pr = trans ? Kp : rows_p, pc = trans ? rows_p : Kp;
-  const int sr = trans ? K : rows, sc = trans ? rows : K;
+// FP16 format: materialise the planes of a tensor nobody split yet.  predicted: the site's scale from the previous call is used
+// (one pass); else a max pass runs first (two passes, exact scale).
+static int materialize_h(const float* src, int64_t ld, int sr, int sc, int pr, int pc, void* hi, void* lo, unsigned* amax, float* scale,
+                         float* scale_copy, bool predicted, unsigned* flag, cudaStream_t st, int top = TOP_SITE) {
+  if (predicted) return launch_prep_h(src, ld, sr, sc, pr, pc, hi, lo, nullptr, scale, scale_copy, amax, flag, st);
   int rc;
   if ((rc = launch_amax(src, ld, sr, sc, amax, st))) return rc;
-  return launch_prep_h(src, ld, sr, sc, pr, pc, hi, lo, amax, scale_out, st);
+  return launch_prep_h(src, ld, sr, sc, pr, pc, hi, lo, amax, scale, scale_copy, nullptr, nullptr, st, top);
 }
 
 // Optional per-launch timing of the main kernel (bench.py's live roofline measurement): CUDA events recorded on
@@ -937,41 +984,53 @@ void PlaneRegistry::add(const float* base, int64_t capacity, float* hi, float* l
   if (n >= MAX) return;
   PlaneBuf& x = b[n++];
   x.base = base; x.capacity = capacity; x.hi = hi; x.lo = lo; x.plane_capacity = plane_capacity;
-  x.ld = 0; x.rows = x.cols = 0; x.ldp = 0; x.valid = false; x.amax_slot = -1;
+  x.ld = 0; x.rows = x.cols = 0; x.ldp = 0; x.valid = false; x.scale_ptr = nullptr; x.amax_site = -1; x.is_static = false;
 }
 PlaneBuf* PlaneRegistry::declare(const float* base, int64_t ld, int rows, int cols) {
   PlaneBuf* x = find(base);
   if (!x || x->base != base) return nullptr;
-  x->amax_slot = -1;
-  if (f16) { x->valid = false; return nullptr; }      // FP16 planes need the tensor's max first: the first reader splits
-  const int64_t ldp = (cols + 3) / 4 * 4;
-  if ((int64_t)rows * ldp > x->plane_capacity) { x->valid = false; return nullptr; }
+  x->amax_site = -1; x->is_static = false;
+  const int64_t ldp = f16 ? (cols + 7) / 8 * 8 : (cols + 3) / 4 * 4;
+  if ((int64_t)rows * ldp > (f16 ? 2 : 1) * x->plane_capacity) { x->valid = false; return nullptr; }
   x->ld = ld; x->rows = rows; x->cols = cols; x->ldp = ldp; x->valid = true;
+  if (f16) { x->is_static = true; x->scale_ptr = static_scale; }
   return x;
 }
-void PlaneRegistry::invalidate(const float* p) { if (PlaneBuf* x = find(p)) { x->valid = false; x->amax_slot = -1; } }
+void* PlaneRegistry::plane(const PlaneBuf* x, bool lo, int64_t r0, int64_t c0) const {
+  float* p = lo ? x->lo : x->hi;
+  const int64_t off = r0 * x->ldp + c0;
+  return f16 ? (void*)((__half*)p + off) : (void*)(p + off);
+}
+void PlaneRegistry::invalidate(const float* p) { if (PlaneBuf* x = find(p)) { x->valid = false; x->amax_site = -1; x->is_static = false; } }
 void PlaneRegistry::invalidate_range(const float* lo_, const float* hi_) {
-  for (int i = 0; i < n; ++i) if (b[i].base >= lo_ && b[i].base < hi_) { b[i].valid = false; b[i].amax_slot = -1; }
+  for (int i = 0; i < n; ++i) if (b[i].base >= lo_ && b[i].base < hi_) { b[i].valid = false; b[i].amax_site = -1; b[i].is_static = false; }
 }
-// FP16 format: start of a top-level call (one stream-ordered sequence of GEMMs): the transient amax slots are zeroed and
-// handed out again from 0; knowledge of tracked maxima does not survive the call (valid planes and their scales do).
-int PlaneRegistry::begin_call(cudaStream_t st) {
+int PlaneRegistry::begin_call(cudaStream_t st, int base) {
+  call_base = base; gemm_index = 0;
   if (!f16) return ASE_OK;
-  next_slot = 0;
-  for (int i = 0; i < n; ++i) b[i].amax_slot = -1;
-  ASE_CUDA_OK(cudaMemsetAsync(amax, 0, (size_t)n_slots * sizeof(unsigned), st));
+  if (reset_pending) {      // new parameters: every scale is re-derived exactly on this call, nothing is compared with the old ones
+    ASE_CUDA_OK(cudaMemsetAsync(amax, 0, (size_t)SITES * 12, st));      // amax[SITES] + scale[SITES][2] are contiguous
+    reset_pending = false;
+  }
+  for (int i = 0; i < SITES; ++i) { if (touched[i]) { known[i] = true; touched[i] = false; } }
+  for (int i = 0; i < n; ++i) {
+    b[i].amax_site = -1;                                 // maxima tracked by GEMM epilogues are only meaningful within one call
+    // planes written by a GEMM epilogue refer to their site's scale slot, which is re-predicted right now: drop them
+    // (planes split by a prep pass -- the weights -- carry their own copy of the scale and stay valid)
+    if (b[i].valid && !b[i].is_static && b[i].scale_ptr >= scale && b[i].scale_ptr < scale + 2 * SITES) b[i].valid = false;
+    if (b[i].is_static) { b[i].valid = false; b[i].is_static = false; }
+  }
+  tc_site_update_kernel<<<ceil_div(SITES, 256), 256, 0, st>>>(amax, scale, SITES, static_scale, STATIC_SCALE, flag);
+  ASE_LAUNCH_OK();
   return ASE_OK;
-}
-int PlaneRegistry::new_slot() {
-  if (next_slot >= n_slots) return -1;
-  return next_slot++;
 }
 
 struct OpView { const void* hi; const void* lo; int64_t ldp; bool ok; const float* scale; };
 
 // View [nat_rows, nat_cols] (ld) at `ptr` as planes.  Geometry of a registered buffer is whatever its last full
 // writer declared; a first read of a buffer without valid planes splits the WHOLE declared buffer once.
-static int resolve_operand(PlaneRegistry* reg, const float* ptr, int64_t ld, int nat_rows, int nat_cols, OpView* v, cudaStream_t st) {
+// site: this reader's scale site (FP16 format; used when the buffer's max is not already tracked at its producer's site).
+static int resolve_operand(PlaneRegistry* reg, const float* ptr, int64_t ld, int nat_rows, int nat_cols, OpView* v, int site, cudaStream_t st) {
   v->ok = false; v->scale = nullptr;
   if (!reg) return ASE_OK;
   PlaneBuf* x = reg->find(ptr);
@@ -989,19 +1048,23 @@ static int resolve_operand(PlaneRegistry* reg, const float* ptr, int64_t ld, int
       tc_prep_kernel<<<(int)imin64((total + 255) / 256, 148 * 16), 256, 0, st>>>(ptr, ld, nat_rows, nat_cols, nat_rows, (int)ldp, x->hi, x->lo);
       ASE_LAUNCH_OK();
     } else {
-      int as = x->amax_slot;
-      if (as < 0) {                          // written by a non-GEMM kernel (or accumulated into): one max pass over the reader's view
+      int rc;
+      float* bs = reg->bscale + 2 * (x - reg->b);      // the buffer's own copy of the scale: survives the next begin_call
+      if (x->amax_site >= 0) {
+        // written earlier in this call by a GEMM whose scale was not known yet: it declared the geometry and tracked max |C|
+        const int ts = x->amax_site;
+        x->ldp = pad_to(x->cols, 8);
+        if ((rc = launch_prep_h(ptr, x->ld, x->rows, x->cols, x->rows, (int)x->ldp, x->hi, x->lo, reg->amax + ts, reg->scale + 2 * ts, bs, nullptr, nullptr, st))) return rc;
+      } else {
+        // written by a non-GEMM kernel (or accumulated into): split the reader's view with this reader's site
         const int64_t ldp = pad_to(nat_cols, 8);
-        if ((int64_t)nat_rows * ldp > 2 * x->plane_capacity || (int64_t)(nat_rows - 1) * ld + nat_cols > x->capacity) return ASE_OK;
-        as = reg->new_slot();
-        if (as < 0) { set_error("tcgen05 FP16 GEMM: out of amax slots"); return ASE_ERR_WORKSPACE; }
-        x->ld = ld; x->rows = nat_rows; x->cols = nat_cols;
-        int rc = launch_amax(ptr, ld, nat_rows, nat_cols, reg->amax + as, st);
-        if (rc) return rc;
-      }                                      // else: produced by a GEMM of this call, which declared the geometry and tracked max |C|
-      x->ldp = pad_to(x->cols, 8);
-      int rc = launch_prep_h(ptr, x->ld, x->rows, x->cols, x->rows, (int)x->ldp, x->hi, x->lo, reg->amax + as, reg->bscale + 2 * (x - reg->b), st);
-      if (rc) return rc;
+        if (site < 0 || (int64_t)nat_rows * ldp > 2 * x->plane_capacity || (int64_t)(nat_rows - 1) * ld + nat_cols > x->capacity) return ASE_OK;
+        x->ld = ld; x->rows = nat_rows; x->cols = nat_cols; x->ldp = ldp;
+        if ((rc = materialize_h(ptr, ld, nat_rows, nat_cols, nat_rows, (int)ldp, x->hi, x->lo, reg->amax + site, reg->scale + 2 * site, bs, reg->known[site],
+                                reg->flag, st))) return rc;
+        reg->touched[site] = true;
+      }
+      x->scale_ptr = bs; x->is_static = false;
     }
     x->valid = true;
   }
@@ -1009,8 +1072,8 @@ static int resolve_operand(PlaneRegistry* reg, const float* ptr, int64_t ld, int
   const int64_t off = ptr - x->base;
   const int64_t r0 = off / x->ld, c0 = off - r0 * x->ld;
   if ((c0 & (pal - 1)) || r0 + nat_rows > x->rows || c0 + nat_cols > x->cols) return ASE_OK;
-  if (!H) { v->hi = x->hi + r0 * x->ldp + c0; v->lo = x->lo + r0 * x->ldp + c0; }
-  else { v->hi = (const __half*)x->hi + r0 * x->ldp + c0; v->lo = (const __half*)x->lo + r0 * x->ldp + c0; v->scale = reg->bscale + 2 * (x - reg->b); }
+  v->hi = reg->plane(x, false, r0, c0); v->lo = reg->plane(x, true, r0, c0);
+  if (H) v->scale = x->scale_ptr;
   v->ldp = x->ldp; v->ok = true;
   return ASE_OK;
 }
@@ -1035,26 +1098,28 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   OpView va, vb;
   const int a_rows = p.a_trans ? p.K : p.M, a_cols = p.a_trans ? p.M : p.K;
   const int b_rows = p.b_trans ? p.K : p.N, b_cols = p.b_trans ? p.N : p.K;
-  if ((rc = resolve_operand(reg, p.A, p.lda, a_rows, a_cols, &va, st))) return rc;
-  if ((rc = resolve_operand(reg, p.B, p.ldb, b_rows, b_cols, &vb, st))) return rc;
+  // FP16 format: scale sites of this GEMM (A, B, C); without a registry the workspace head holds two transient slots
+  const int site_a = (H && reg) ? reg->site(0) : -1, site_b = (H && reg) ? reg->site(1) : -1, site_c = (H && reg) ? reg->site(2) : -1;
+  if (H && reg) { if (site_c < 0) { set_error("tcgen05 FP16 GEMM: more GEMMs in one call than scale sites"); return ASE_ERR_WORKSPACE; } reg->gemm_index++; }
+  if ((rc = resolve_operand(reg, p.A, p.lda, a_rows, a_cols, &va, site_a, st))) return rc;
+  if ((rc = resolve_operand(reg, p.B, p.ldb, b_rows, b_cols, &vb, site_b, st))) return rc;
   CUtensorMap ah, al, bh, bl;
   char* ws = (char*)p.workspace;
   if (!va.ok || !vb.ok) { if ((rc = gemm_tc_check_workspace(p))) return rc; }
-  // FP16 format, unregistered operands: transient amax / scale slots from the registry, or the workspace head without one
-  unsigned* t_amax[2] = {nullptr, nullptr}; float* t_scale[2] = {nullptr, nullptr};
+  unsigned* t_amax[2] = {nullptr, nullptr}; float* t_scale[2] = {nullptr, nullptr}; bool t_pred[2] = {false, false};
   if (H && (!va.ok || !vb.ok)) {
     if (reg) {
+      const int sites[2] = {site_a, site_b};
       for (int i = 0; i < 2; ++i) {
         if (i == 0 ? va.ok : vb.ok) continue;
-        const int sl = reg->new_slot();
-        if (sl < 0) { set_error("tcgen05 FP16 GEMM: out of amax slots"); return ASE_ERR_WORKSPACE; }
-        t_amax[i] = reg->amax + sl; t_scale[i] = reg->tscale + 2 * sl;
+        t_amax[i] = reg->amax + sites[i]; t_scale[i] = reg->scale + 2 * sites[i]; t_pred[i] = reg->known[sites[i]]; reg->touched[sites[i]] = true;
       }
     } else {
       ASE_CUDA_OK(cudaMemsetAsync(ws, 0, 2 * sizeof(unsigned), st));
       t_amax[0] = (unsigned*)ws; t_amax[1] = (unsigned*)ws + 1; t_scale[0] = (float*)(ws + 16); t_scale[1] = (float*)(ws + 32);
     }
   }
+  unsigned* oflag = (H && reg) ? reg->flag : nullptr;
   char* wsp = ws + TC_WS_HEAD;
   if (va.ok) {
     if ((rc = make_view_map(&ah, va.hi, a_rows, a_cols, va.ldp, p.a_trans ? BK : a_box, p.a_trans != 0, H)) ||
@@ -1062,7 +1127,10 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   } else {
     float* Ahi = (float*)wsp; float* Alo = (float*)(wsp + align_up((int64_t)Mp * Kp * 4, 1024));
     if (!H) { if ((rc = prep_operand(p.A, p.lda, p.a_trans, p.M, p.K, Mp, Kp, Ahi, Alo, st))) return rc; }
-    else { if ((rc = prep_operand_h(p.A, p.lda, p.a_trans, p.M, p.K, Mp, Kp, Ahi, Alo, t_amax[0], t_scale[0], st))) return rc; va.scale = t_scale[0]; }
+    else {
+      if ((rc = materialize_h(p.A, p.lda, a_rows, a_cols, p.a_trans ? Kp : Mp, p.a_trans ? Mp : Kp, Ahi, Alo, t_amax[0], t_scale[0], nullptr, t_pred[0], oflag, st, reg ? TOP_SITE : TOP_EXACT))) return rc;
+      va.scale = t_scale[0];
+    }
     if (!p.a_trans) { if ((rc = make_map(&ah, Ahi, Mp, Kp, a_box, false, H)) || (rc = make_map(&al, Alo, Mp, Kp, a_box, false, H))) return rc; }
     else            { if ((rc = make_map(&ah, Ahi, Kp, Mp, BK, true, H)) || (rc = make_map(&al, Alo, Kp, Mp, BK, true, H))) return rc; }
   }
@@ -1073,7 +1141,10 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
     char* wb = wsp + 2 * align_up((int64_t)Mp * Kp * 4, 1024);
     float* Bhi = (float*)wb; float* Blo = (float*)(wb + align_up((int64_t)Np * Kp * 4, 1024));
     if (!H) { if ((rc = prep_operand(p.B, p.ldb, p.b_trans, p.N, p.K, Np, Kp, Bhi, Blo, st))) return rc; }
-    else { if ((rc = prep_operand_h(p.B, p.ldb, p.b_trans, p.N, p.K, Np, Kp, Bhi, Blo, t_amax[1], t_scale[1], st))) return rc; vb.scale = t_scale[1]; }
+    else {
+      if ((rc = materialize_h(p.B, p.ldb, b_rows, b_cols, p.b_trans ? Kp : Np, p.b_trans ? Np : Kp, Bhi, Blo, t_amax[1], t_scale[1], nullptr, t_pred[1], oflag, st, reg ? TOP_SITE : TOP_EXACT))) return rc;
+      vb.scale = t_scale[1];
+    }
     if (!p.b_trans) { if ((rc = make_map(&bh, Bhi, Np, Kp, BN, false, H)) || (rc = make_map(&bl, Blo, Np, Kp, BN, false, H))) return rc; }
     else            { if ((rc = make_map(&bh, Bhi, Kp, Np, BK, true, H)) || (rc = make_map(&bl, Blo, Kp, Np, BK, true, H))) return rc; }
   }
@@ -1083,7 +1154,7 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   e.mask_src = p.mask_src; e.ldm = p.ldm; e.mask_mode = p.mask_src ? p.mask_mode : 0; e.accumulate = p.accumulate;
   e.Chi = e.Clo = nullptr; e.ldp = 0; e.colsum = p.colsum_out;
   e.a_inv = (H && va.scale) ? va.scale + 1 : nullptr; e.b_inv = (H && vb.scale) ? vb.scale + 1 : nullptr;
-  e.c_scale = nullptr; e.c_amax = nullptr;
+  e.c_scale = nullptr; e.c_amax = nullptr; e.flag = nullptr;
   // ---- output planes: a full write at the base of a registered buffer (re)declares its geometry; a partial write
   // keeps planes in sync only if they are currently valid with the same leading dimension; accumulation invalidates
   if (reg && !H) {
@@ -1099,14 +1170,25 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
       } else x->valid = false;
     }
   } else if (reg && H) {
-    // FP16 format: the planes of C need C's max first, so the epilogue only TRACKS max |C| (a full write at the buffer base);
-    // the first consumer turns it into the scale and splits.  Anything else leaves the max unknown (one extra pass on first read).
+    // FP16 format.  A full write at the buffer base: the epilogue tracks max |C| at this GEMM's C site; if the site's scale is
+    // already known (predicted from the previous call) it also writes the planes, else the first consumer splits with the exact
+    // scale.  A tanh-bounded partial write into statically scaled planes (the style columns behind the normalised
+    // observations) keeps them in sync.  Anything else leaves the buffer without planes.
     if (PlaneBuf* x = reg->find(p.C)) {
-      x->valid = false; x->amax_slot = -1;
-      if (!p.accumulate && p.C == x->base && (int64_t)p.M * pad_to(p.N, 8) <= 2 * x->plane_capacity && (int64_t)(p.M - 1) * p.ldc + p.N <= x->capacity) {
-        const int sl = reg->new_slot();
-        if (sl >= 0) { x->ld = p.ldc; x->rows = p.M; x->cols = p.N; x->amax_slot = sl; e.c_amax = reg->amax + sl; }
-      }
+      const bool full = !p.accumulate && p.C == x->base && (int64_t)p.M * pad_to(p.N, 8) <= 2 * x->plane_capacity && (int64_t)(p.M - 1) * p.ldc + p.N <= x->capacity &&
+                        !(x->valid && x->is_static && x->ld == p.ldc && (x->rows > p.M || x->cols > p.N));
+      if (full) {
+        x->ld = p.ldc; x->rows = p.M; x->cols = p.N; x->ldp = pad_to(p.N, 8); x->is_static = false;
+        reg->touched[site_c] = true; e.c_amax = reg->amax + site_c;
+        if (reg->known[site_c]) {
+          x->valid = true; x->amax_site = -1; x->scale_ptr = reg->scale + 2 * site_c;
+          e.Chi = x->hi; e.Clo = x->lo; e.ldp = x->ldp; e.c_scale = x->scale_ptr; e.flag = reg->flag;
+        } else { x->valid = false; x->amax_site = site_c; }
+      } else if (!p.accumulate && x->valid && x->is_static && x->ld == p.ldc && p.act == 2 && !p.mask_src) {
+        const int64_t off = p.C - x->base, r0 = off / x->ld, c0 = off - r0 * x->ld;
+        if (r0 + p.M <= x->rows && c0 + p.N <= x->cols) { e.Chi = reg->plane(x, false, r0, c0); e.Clo = reg->plane(x, true, r0, c0); e.ldp = x->ldp; e.c_scale = x->scale_ptr; e.flag = reg->flag; }
+        else { x->valid = false; x->amax_site = -1; x->is_static = false; }
+      } else { x->valid = false; x->amax_site = -1; x->is_static = false; }
     }
   }
   e.kb_total = Kp / BK;

@@ -8,7 +8,8 @@ namespace ase {
 
 // ------------------------------------------------------------------ RunningMeanStd
 struct RmsBatchList { const float* x[3]; int64_t ld[3]; int rows; };
-struct RmsDst { float* y[3]; int64_t ld[3]; float* hi[3]; float* lo[3]; int64_t ldp[3]; };   // optional TF32 planes per destination
+// optional operand planes per destination: fp32 words holding TF32 values, or (half != 0) halfs of y * pscale
+struct RmsDst { float* y[3]; int64_t ld[3]; void* hi[3]; void* lo[3]; int64_t ldp[3]; int half; float pscale; };
 int64_t rms_scratch_bytes(int cols, int rows, int nbatch);
 int rms_update_batches(const RmsBatchList& bl, int nbatch, int cols, double* mean, double* var, double* count, float eps,
                        int update, void* scratch, float** meanf_out, float** stdf_out, cudaStream_t st);
@@ -16,8 +17,8 @@ int rms_normalize(const float* x, int64_t ldx, int rows, int cols, const float* 
                   const RmsDst& dst, cudaStream_t st);
 int rms_apply(const float* x, int64_t ldx, int rows, int cols, const double* mean, const double* var, float eps, int unnorm,
               float* y, int64_t ldy, cudaStream_t st);
-int copy_cols(const float* x, int64_t ldx, int rows, int cols, float* y, int64_t ldy, cudaStream_t st, float* hi = nullptr, float* lo = nullptr,
-              int64_t ldp = 0);
+int copy_cols(const float* x, int64_t ldx, int rows, int cols, float* y, int64_t ldy, cudaStream_t st, void* hi = nullptr, void* lo = nullptr,
+              int64_t ldp = 0, int half = 0, float pscale = 1.0f, unsigned* flag = nullptr);
 
 // ------------------------------------------------------------------ GEMM backends
 int gemm_simt(const AseGemmParams& p, cudaStream_t st);
@@ -27,25 +28,45 @@ struct PlaneBuf {
   float* hi; float* lo; int64_t plane_capacity; // planes (floats each; the FP16 format stores halfs in the same space)
   int64_t ld; int rows, cols; int64_t ldp;      // geometry declared by the last full writer / first reader
   bool valid;
-  int amax_slot;                                // FP16 format: transient slot holding max |x| of the current contents, -1 = unknown
+  // FP16 format
+  const float* scale_ptr;                       // device [scale, 1/scale] the current planes were written with
+  int amax_site;                                // site whose amax slot holds max |x| of the current fp32 contents (tracked by the GEMM that wrote them), -1 = unknown
+  bool is_static;                               // planes written with the registry's static scale by a bounded non-GEMM writer
 };
+// FP16 format (backend 2): every tensor is multiplied by a power of two before the hi/lo split.  Scales live in device memory,
+// one slot per SITE = (GEMM index within the top-level call, operand A / B / output C): the static kernel schedule of the learner
+// puts the same logical tensor at the same site every call.  The first time a site is used its scale comes from an exact max pass
+// (or from the max the producing GEMM tracked); afterwards the scale predicted from the previous call's max is used, which lets the
+// producing GEMM's epilogue write the planes itself.  The prediction leaves 2^9 of headroom above and 2^12 below; leaving that
+// window between two consecutive calls raises a sticky device flag (ase_learner_plane_status), never a silent wrong result.
 struct PlaneRegistry {
   static constexpr int MAX = 160;
-  static constexpr int SLOTS = 1024;
+  static constexpr int SITES = 1024;
+  static constexpr float STATIC_SCALE = 64.0f;  // bounded writers (normalised observations clamp at 5, tanh outputs, unit latents)
   PlaneBuf b[MAX]; int n = 0;
-  // FP16 format (backend 2): per-tensor power-of-two scales live in device memory (no host sync anywhere)
   bool f16 = false;
-  unsigned* amax = nullptr;     // [SLOTS] transient max |x| slots (uint bits), zeroed by begin_call
-  float* tscale = nullptr;      // [SLOTS][2] scale / inverse of unregistered operands split into the shared workspace
-  float* bscale = nullptr;      // [MAX][2] scale / inverse of each registered buffer's current planes
-  int n_slots = 0, next_slot = 0;
-  static int64_t device_bytes() { return (int64_t)SLOTS * 4 + (int64_t)SLOTS * 8 + (int64_t)MAX * 8; }
-  void attach_device(void* mem) { amax = (unsigned*)mem; tscale = (float*)((char*)mem + SLOTS * 4); bscale = tscale + 2 * SLOTS; n_slots = SLOTS; }
-  int begin_call(cudaStream_t st);
-  int new_slot();
+  unsigned* amax = nullptr;       // [SITES] max |x| seen at the site during the current call (uint bits)
+  float* scale = nullptr;         // [SITES][2] scale / inverse
+  float* static_scale = nullptr;  // [2]
+  float* bscale = nullptr;        // [MAX][2] copy of the scale a registered buffer's planes were SPLIT with by a prep pass: unlike the
+                                  // site slots (re-predicted at every begin_call) it stays put, so weight planes survive across calls
+  unsigned* flag = nullptr;       // [1] sticky: bit 0 overflow (|x * scale| > 60000), bit 1 underflow (max * scale < 2^-6, or a zero scale met data)
+  bool known[SITES], touched[SITES];
+  int call_base = 0, gemm_index = 0;
+  static int64_t device_bytes() { return (int64_t)SITES * 4 + (int64_t)SITES * 8 + (int64_t)MAX * 8 + 64; }
+  void attach_device(void* mem) {
+    amax = (unsigned*)mem; scale = (float*)((char*)mem + SITES * 4); bscale = scale + 2 * SITES; static_scale = bscale + 2 * MAX; flag = (unsigned*)(static_scale + 2);
+    for (int i = 0; i < SITES; ++i) known[i] = touched[i] = false;
+  }
+  int begin_call(cudaStream_t st, int base);    // start of one stream-ordered sequence of GEMMs (calc_gradients / eval_*)
+  int site(int which) const { const int s = call_base + 3 * gemm_index + which; return s < SITES ? s : -1; }
+  bool reset_pending = false;     // forget_sites(): the device slots are cleared at the next begin_call (stream-ordered)
+  void forget_sites() { for (int i = 0; i < SITES; ++i) known[i] = touched[i] = false; reset_pending = true; }
   PlaneBuf* find(const float* p);
-  // a non-GEMM kernel is about to write the whole buffer [rows, cols] (ld) INCLUDING its planes: returns the entry (valid) or null
+  // a non-GEMM kernel is about to write the whole buffer [rows, cols] (ld) INCLUDING its planes: returns the entry (valid) or null.
+  // FP16 format: only bounded writers may call this (the planes get the static scale).
   PlaneBuf* declare(const float* base, int64_t ld, int rows, int cols);
+  void* plane(const PlaneBuf* x, bool lo, int64_t r0, int64_t c0) const;   // element (r0, c0) of a plane, in either format
   void add(const float* base, int64_t capacity, float* hi, float* lo, int64_t plane_capacity);
   void invalidate(const float* p);
   void invalidate_range(const float* lo_, const float* hi_);

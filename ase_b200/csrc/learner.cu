@@ -175,7 +175,9 @@ static void carve(AseLearner& L, void* ws, int64_t* total) {
       add(3 * Ba, L.amp_ld);
       for (int k = 0; k < c.n_disc_units; ++k) { add(3 * Ba, c.disc_units[k]); add(Ba, c.disc_units[k]); }
       add(Ba, L.amp_ld);
+      add(3 * Ba, 1); if (L.ase) add(Ba, c.latent_dim);
     }
+    add(Ra, c.act_dim); add(B, 1);
     add(1, gsz); add(1, gsz);
     L.act_plane_floats = act;
     L.act_planes = cv.take<float>(2 * act);
@@ -215,6 +217,9 @@ static void register_planes(AseLearner& L, const float* params) {
     gsz = imax64(gsz, 3 * Ba * (int64_t)dmax);
   }
   add(L.G0, 1, gsz); add(L.G1, 1, gsz);
+  // head gradients (written by the loss kernels): split once for their dW and dX consumers
+  add(L.dMU, Ra, c.act_dim); add(L.dV, B, 1);
+  if (L.amp) { add(L.dLOGIT, 3 * Ba, 1); if (L.ase) add(L.dE, Ba, c.latent_dim); }
   float* wh = L.w_planes; float* wl = L.w_planes + L.w_plane_floats;
   int64_t woff = 0;
   for (int i = 0; i < L.net.n_tensors; ++i) {
@@ -405,6 +410,18 @@ extern "C" void ase_learner_destroy(AseLearner* l) { if (l) { delete l->reg; del
 extern "C" int ase_learner_params_changed(AseLearner* l) {
   ASE_CHECK_ARG(l != nullptr, "ase_learner_params_changed: null learner");
   if (l->reg && l->reg_params) l->reg->invalidate_range(l->reg_params, l->reg_params + l->net.arena);
+  if (l->reg) l->reg->forget_sites();     // new weights: the FP16 format recalibrates every scale exactly on the next call
+  return ASE_OK;
+}
+
+extern "C" int ase_learner_plane_status(AseLearner* l, int* flags, void* stream) {
+  ASE_CHECK_ARG(l && flags, "ase_learner_plane_status: null argument");
+  *flags = 0;
+  if (!l->reg || !l->reg->f16) return ASE_OK;
+  unsigned f = 0;
+  ASE_CUDA_OK(cudaMemcpyAsync(&f, l->reg->flag, sizeof(f), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  ASE_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+  *flags = (int)f;
   return ASE_OK;
 }
 
@@ -422,7 +439,7 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
   ASE_CHECK_ARG(out->scalars, "calc_gradients: scalars output");
   const int B = L.B, Ba = L.Ba, Ra = L.Ra, Z = c.latent_dim, A = c.act_dim;
   register_planes(L, s->params);
-  if (L.reg) RC(L.reg->begin_call(st));
+  if (L.reg) RC(L.reg->begin_call(st, 0));
   G g{L, st, s->params, s->grads};
 
   ASE_CUDA_OK(cudaMemsetAsync(L.acc, 0, ACC_COUNT * sizeof(double), st));
@@ -437,24 +454,32 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
     RmsDst d = {}; d.y[0] = L.Xa; d.ld[0] = L.ldx;
     if (L.has_div) { d.y[1] = L.Xa + (int64_t)B * L.ldx; d.ld[1] = L.ldx; }
     if (L.ase) { d.y[2] = L.Xc; d.ld[2] = L.ldx; }
-    // the normalise pass also writes the TF32 operand planes of the network inputs (the style / latent columns follow below)
-    PlaneBuf* pa = L.reg ? L.reg->declare(L.Xa, L.ldx, Ra, L.in0) : nullptr;
-    PlaneBuf* pc = (L.reg && L.ase) ? L.reg->declare(L.Xc, L.ldx, B, L.in0) : nullptr;
-    if (pa) { d.hi[0] = pa->hi; d.lo[0] = pa->lo; d.ldp[0] = pa->ldp; if (L.has_div) { d.hi[1] = pa->hi + (int64_t)B * pa->ldp; d.lo[1] = pa->lo + (int64_t)B * pa->ldp; d.ldp[1] = pa->ldp; } }
-    if (pc) { d.hi[2] = pc->hi; d.lo[2] = pc->lo; d.ldp[2] = pc->ldp; }
+    // the normalise pass also writes the operand planes of the network inputs (the style / latent columns follow below);
+    // FP16 format: with the static scale -- the values are clamped to +-5
+    PlaneRegistry* R = L.reg;
+    PlaneBuf* pa = R ? R->declare(L.Xa, L.ldx, Ra, L.in0) : nullptr;
+    PlaneBuf* pc = (R && L.ase) ? R->declare(L.Xc, L.ldx, B, L.in0) : nullptr;
+    d.half = (R && R->f16) ? 1 : 0; d.pscale = PlaneRegistry::STATIC_SCALE;
+    if (pa) { d.hi[0] = R->plane(pa, false, 0, 0); d.lo[0] = R->plane(pa, true, 0, 0); d.ldp[0] = pa->ldp; if (L.has_div) { d.hi[1] = R->plane(pa, false, B, 0); d.lo[1] = R->plane(pa, true, B, 0); d.ldp[1] = pa->ldp; } }
+    if (pc) { d.hi[2] = R->plane(pc, false, 0, 0); d.lo[2] = R->plane(pc, true, 0, 0); d.ldp[2] = pc->ldp; }
     RC(rms_normalize(mb->obs, c.obs_dim, B, c.obs_dim, mf, sf, 0, d, st));
     if (!pa) g.inval(L.Xa);
     if (!pc) g.inval(L.Xc);
   }
   if (L.ase) {
-    PlaneBuf* pc = L.reg ? L.reg->find(L.Xc) : nullptr;
+    PlaneRegistry* R = L.reg;
+    const int half = (R && R->f16) ? 1 : 0;
+    unsigned* fl = R ? R->flag : nullptr;
+    PlaneBuf* pc = R ? R->find(L.Xc) : nullptr;
     if (pc && !pc->valid) pc = nullptr;
-    RC(copy_cols(mb->ase_latents, Z, B, Z, L.Xc + c.obs_dim, L.ldx, st, pc ? pc->hi + c.obs_dim : nullptr, pc ? pc->lo + c.obs_dim : nullptr, pc ? pc->ldp : 0));
+    RC(copy_cols(mb->ase_latents, Z, B, Z, L.Xc + c.obs_dim, L.ldx, st, pc ? R->plane(pc, false, 0, c.obs_dim) : nullptr, pc ? R->plane(pc, true, 0, c.obs_dim) : nullptr,
+                 pc ? pc->ldp : 0, half, PlaneRegistry::STATIC_SCALE, fl));
     if (!pc) g.inval(L.Xc);
-    PlaneBuf* pz = L.reg ? L.reg->declare(L.Zc, Z, Ra, Z) : nullptr;
-    RC(copy_cols(mb->ase_latents, Z, B, Z, L.Zc, Z, st, pz ? pz->hi : nullptr, pz ? pz->lo : nullptr, pz ? pz->ldp : 0));
-    if (L.has_div) RC(copy_cols(mb->new_latents, Z, B, Z, L.Zc + (int64_t)B * Z, Z, st, pz ? pz->hi + (int64_t)B * pz->ldp : nullptr,
-                                pz ? pz->lo + (int64_t)B * pz->ldp : nullptr, pz ? pz->ldp : 0));
+    PlaneBuf* pz = R ? R->declare(L.Zc, Z, Ra, Z) : nullptr;
+    RC(copy_cols(mb->ase_latents, Z, B, Z, L.Zc, Z, st, pz ? R->plane(pz, false, 0, 0) : nullptr, pz ? R->plane(pz, true, 0, 0) : nullptr, pz ? pz->ldp : 0, half,
+                 PlaneRegistry::STATIC_SCALE, fl));
+    if (L.has_div) RC(copy_cols(mb->new_latents, Z, B, Z, L.Zc + (int64_t)B * Z, Z, st, pz ? R->plane(pz, false, B, 0) : nullptr, pz ? R->plane(pz, true, B, 0) : nullptr,
+                                pz ? pz->ldp : 0, half, PlaneRegistry::STATIC_SCALE, fl));
     if (!pz) g.inval(L.Zc);
   }
   if (L.amp) {
@@ -463,10 +488,12 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
     bl.ld[0] = bl.ld[1] = bl.ld[2] = c.amp_dim; bl.rows = Ba;
     float *mf, *sf;
     RC(rms_update_batches(bl, 3, c.amp_dim, s->amp_mean, s->amp_var, s->amp_count, c.rms_eps, mb->update_rms, L.rms_amp_scratch, &mf, &sf, st));
-    PlaneBuf* pd = L.reg ? L.reg->declare(L.Xd, L.amp_ld, 3 * Ba, c.amp_dim) : nullptr;
+    PlaneRegistry* R = L.reg;
+    PlaneBuf* pd = R ? R->declare(L.Xd, L.amp_ld, 3 * Ba, c.amp_dim) : nullptr;
     for (int b = 0; b < 3; ++b) {
       RmsDst d = {}; d.y[0] = L.Xd + (int64_t)b * Ba * L.amp_ld; d.ld[0] = L.amp_ld;
-      if (pd) { d.hi[0] = pd->hi + (int64_t)b * Ba * pd->ldp; d.lo[0] = pd->lo + (int64_t)b * Ba * pd->ldp; d.ldp[0] = pd->ldp; }
+      d.half = (R && R->f16) ? 1 : 0; d.pscale = PlaneRegistry::STATIC_SCALE;
+      if (pd) { d.hi[0] = R->plane(pd, false, (int64_t)b * Ba, 0); d.lo[0] = R->plane(pd, true, (int64_t)b * Ba, 0); d.ldp[0] = pd->ldp; }
       RC(rms_normalize(bl.x[b], c.amp_dim, Ba, c.amp_dim, mf + (int64_t)b * c.amp_dim, sf + (int64_t)b * c.amp_dim, 0, d, st));
     }
     if (!pd) g.inval(L.Xd);
@@ -485,9 +512,10 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
     a.e_clip = c.e_clip; a.critic_coef = c.critic_coef; a.bounds_coef = c.bounds_loss_coef; a.div_bonus = c.amp_diversity_bonus;
     a.div_tar = c.amp_diversity_tar; a.dmu = L.dMU; a.dv = L.dV; a.acc = L.acc; a.mu_tanh = c.mu_activation == 2 ? 1 : 0;
     RC(launch_ppo_head(a, st));
+    g.inval(L.dMU); g.inval(L.dV);
   }
-  if (L.amp) RC(launch_disc_head(L.LOGIT, Ba, c.disc_coef, L.dLOGIT, L.acc, out->disc_agent_logit, out->disc_demo_logit, st));
-  if (L.ase) RC(launch_enc_head(L.E, Ba, Z, mb->ase_latents, c.enc_coef, L.dE, nullptr, L.acc, st));
+  if (L.amp) { RC(launch_disc_head(L.LOGIT, Ba, c.disc_coef, L.dLOGIT, L.acc, out->disc_agent_logit, out->disc_demo_logit, st)); g.inval(L.dLOGIT); }
+  if (L.ase) { RC(launch_enc_head(L.E, Ba, Z, mb->ase_latents, c.enc_coef, L.dE, nullptr, L.acc, st)); g.inval(L.dE); }
 
   // ---- backward: actor ----------------------------------------------------------------------------------
   float *cur = L.G0, *oth = L.G1;
@@ -601,7 +629,7 @@ extern "C" int ase_learner_eval_actor_critic(AseLearner* lp, const AseLearnerSta
   ASE_CHECK_ARG(!L.ase || latents, "eval_actor_critic: latents required");
   cudaStream_t st = (cudaStream_t)stream;
   register_planes(L, s->params);
-  if (L.reg) RC(L.reg->begin_call(st));
+  if (L.reg) RC(L.reg->begin_call(st, 600));
   G g{L, st, s->params, s->grads};
   RC(rms_apply(obs, c.obs_dim, rows, c.obs_dim, s->obs_mean, s->obs_var, c.rms_eps, 0, L.Xa, L.ldx, st));
   g.inval(L.Xa); g.inval(L.Xc); g.inval(L.Zc);
@@ -625,7 +653,7 @@ extern "C" int ase_learner_eval_disc_enc(AseLearner* lp, const AseLearnerState* 
   ASE_CHECK_ARG(!enc_pred || L.ase, "eval_disc_enc: enc_pred needs an ASE learner");
   cudaStream_t st = (cudaStream_t)stream;
   register_planes(L, s->params);
-  if (L.reg) RC(L.reg->begin_call(st));
+  if (L.reg) RC(L.reg->begin_call(st, 800));
   G g{L, st, s->params, s->grads};
   RC(rms_apply(amp_obs, c.amp_dim, rows, c.amp_dim, s->amp_mean, s->amp_var, c.rms_eps, 0, L.Xd, L.amp_ld, st));
   g.inval(L.Xd);

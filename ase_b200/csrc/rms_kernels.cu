@@ -3,6 +3,7 @@
 // the parallel-Welford rule of the reference, and the normalise/clamp pass uses the UPDATED statistics
 // exactly as the reference's train-mode forward does.  Up to 3 batches can be merged sequentially in one
 // launch (the three AMP batches of calc_gradients, ase_agent.py:170-181).
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "kernels.h"
 
@@ -85,11 +86,19 @@ rms_normalize_kernel(const float* __restrict__ x, int64_t ldx, int rows, int col
     if (unnorm) y = stdf[c] * fminf(fmaxf(v, -5.0f), 5.0f) + meanf[c];
     else y = fminf(fmaxf((v - meanf[c]) / stdf[c], -5.0f), 5.0f);
     float h = 0.0f, l = 0.0f;
-    if (dst.hi[0] || dst.hi[1] || dst.hi[2]) split_tf32_rms(y, h, l);
+    __half hh = __float2half_rn(0.0f), hl = hh;
+    if (dst.hi[0] || dst.hi[1] || dst.hi[2]) {
+      if (!dst.half) split_tf32_rms(y, h, l);
+      else { const float ys = y * dst.pscale; hh = __float2half_rn(ys); hl = __float2half_rn(ys - __half2float(hh)); }
+    }
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
       if (dst.y[d]) dst.y[d][(int64_t)r * dst.ld[d] + c] = y;
-      if (dst.hi[d]) { dst.hi[d][(int64_t)r * dst.ldp[d] + c] = h; dst.lo[d][(int64_t)r * dst.ldp[d] + c] = l; }
+      if (dst.hi[d]) {
+        const int64_t o = (int64_t)r * dst.ldp[d] + c;
+        if (!dst.half) { ((float*)dst.hi[d])[o] = h; ((float*)dst.lo[d])[o] = l; }
+        else { ((__half*)dst.hi[d])[o] = hh; ((__half*)dst.lo[d])[o] = hl; }
+      }
     }
   }
 }
@@ -97,14 +106,25 @@ rms_normalize_kernel(const float* __restrict__ x, int64_t ldx, int rows, int col
 // just copy columns (used to place latents next to the normalised observations)
 __global__ void __launch_bounds__(256)
 copy_cols_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, float* __restrict__ y, int64_t ldy,
-                 float* __restrict__ hi, float* __restrict__ lo, int64_t ldp) {
+                 void* __restrict__ hi, void* __restrict__ lo, int64_t ldp, int half, float pscale, unsigned* __restrict__ flag) {
   const int64_t total = (int64_t)rows * cols;
+  bool over = false;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
     const float v = x[(int64_t)r * ldx + c];
     y[(int64_t)r * ldy + c] = v;
-    if (hi) { float h, l; split_tf32_rms(v, h, l); hi[(int64_t)r * ldp + c] = h; lo[(int64_t)r * ldp + c] = l; }
+    if (hi) {
+      const int64_t o = (int64_t)r * ldp + c;
+      if (!half) { float h, l; split_tf32_rms(v, h, l); ((float*)hi)[o] = h; ((float*)lo)[o] = l; }
+      else {
+        const float vs = v * pscale;
+        over |= fabsf(vs) > 60000.0f;
+        const __half hh = __float2half_rn(vs);
+        ((__half*)hi)[o] = hh; ((__half*)lo)[o] = __float2half_rn(vs - __half2float(hh));
+      }
+    }
   }
+  if (over && flag) atomicOr(flag, 1u);       // the static plane scale assumes bounded inputs (unit latents): report instead of saturating silently
 }
 
 int64_t rms_scratch_bytes(int cols, int rows, int nbatch) {
@@ -145,10 +165,11 @@ int rms_normalize(const float* x, int64_t ldx, int rows, int cols, const float* 
   return ASE_OK;
 }
 
-int copy_cols(const float* x, int64_t ldx, int rows, int cols, float* y, int64_t ldy, cudaStream_t st, float* hi, float* lo, int64_t ldp) {
+int copy_cols(const float* x, int64_t ldx, int rows, int cols, float* y, int64_t ldy, cudaStream_t st, void* hi, void* lo, int64_t ldp, int half,
+              float pscale, unsigned* flag) {
   const int64_t total = (int64_t)rows * cols;
   const int blocks = (int)imin64((total + 255) / 256, 148 * 16);
-  copy_cols_kernel<<<blocks, 256, 0, st>>>(x, ldx, rows, cols, y, ldy, hi, lo, ldp);
+  copy_cols_kernel<<<blocks, 256, 0, st>>>(x, ldx, rows, cols, y, ldy, hi, lo, ldp, half, pscale, flag);
   ASE_LAUNCH_OK();
   return ASE_OK;
 }

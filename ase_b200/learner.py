@@ -248,9 +248,21 @@ class Learner:
         st = self._state()
         check(lib.ase_learner_adam_step(self._h, C.byref(st), self.step, float(grad_scale), _stream()), 'ase_learner_adam_step')
 
+    def plane_status(self):
+        """gemm_backend 2: raises if a tensor left the window of its predicted FP16 plane scale (include/ase_b200.h,
+        ase_learner_plane_status) -- the flagged update would not be fp32-accurate.  One stream synchronisation."""
+        f = C.c_int(0)
+        check(lib.ase_learner_plane_status(self._h, C.byref(f), _stream()), 'ase_learner_plane_status')
+        if f.value:
+            raise L.AseError(f"FP16 operand-plane scale miss (flags {f.value}: bit0 overflow, bit1 underflow): a tensor's max moved by more "
+                             "than 2^9 up / 2^12 down between two consecutive calls; rerun with gemm_backend=1")
+        return 0
+
     def train_result(self, out):
         """Host-side view of the last train_result with the reference's key names (one D2H copy)."""
         s = out['scalars'].tolist()
+        if self.cfg.gemm_backend == 2:
+            self.plane_status()
         return dict(zip(L.TR_NAMES, s))
 
     def eval_actor_critic(self, obs, latents=None, want_value=True, want_actor=True):

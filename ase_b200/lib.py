@@ -76,7 +76,7 @@ class TrainResult(C.Structure):
 EXPORTS = ['ase_abi_version', 'ase_last_error', 'ase_launch_count', 'ase_obs_build', 'ase_amp_obs_build',
            'ase_rms_scratch_bytes', 'ase_rms_update', 'ase_rms_apply', 'ase_gae', 'ase_amp_rewards', 'ase_heading_obs', 'ase_heading_reward', 'ase_motion_state', 'ase_amp_obs_demo', 'ase_policy_sample', 'ase_adv_normalize',
            'ase_gemm', 'ase_gemm_tc_workspace_bytes', 'ase_gemm_tc_profile', 'ase_gemm_tc_profile_read', 'ase_learner_num_params', 'ase_learner_param_desc',
-           'ase_learner_arena_floats', 'ase_learner_workspace_bytes', 'ase_learner_create', 'ase_learner_destroy', 'ase_learner_params_changed',
+           'ase_learner_arena_floats', 'ase_learner_workspace_bytes', 'ase_learner_create', 'ase_learner_destroy', 'ase_learner_params_changed', 'ase_learner_plane_status',
            'ase_learner_calc_gradients', 'ase_learner_adam_step', 'ase_learner_eval_actor_critic',
            'ase_learner_eval_disc_enc']
 
@@ -119,6 +119,7 @@ def _load():
     lib.ase_learner_create.argtypes = [C.POINTER(LearnerConfig), vp, i64, C.POINTER(vp)]
     lib.ase_learner_destroy.argtypes = [vp]
     lib.ase_learner_params_changed.argtypes = [vp]
+    lib.ase_learner_plane_status.argtypes = [vp, C.POINTER(C.c_int), vp]
     lib.ase_learner_calc_gradients.argtypes = [vp, C.POINTER(LearnerState), C.POINTER(Minibatch), C.POINTER(TrainResult), vp]
     lib.ase_learner_adam_step.argtypes = [vp, C.POINTER(LearnerState), i64, f32, vp]
     lib.ase_learner_eval_actor_critic.argtypes = [vp, C.POINTER(LearnerState), vp, vp, i32, vp, vp, vp]

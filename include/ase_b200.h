@@ -157,7 +157,8 @@ int ase_adv_normalize(const float* returns, const float* values, const float* ma
  *   epilogue: + bias[N]; act 0 none / 1 relu / 2 tanh; mask_mode 1: *= (mask_src>0), 2: *= (1-mask_src^2);
  *   accumulate 1: C += result (atomic when split_k > 1)
  *   backend 0: SIMT fp32 FFMA kernel; 1: tcgen05 3xTF32 tensor-core kernel (sm_100a; operands are
- *   split on the fly into TF32 hi/lo pairs -- see DESIGN.md "GEMM").
+ *   split on the fly into TF32 hi/lo pairs -- see DESIGN.md "GEMM"); 2: tcgen05 3xFP16 kernel (operands scaled by
+ *   a per-tensor power of two and split into FP16 hi/lo pairs: same accuracy class, twice the MMA rate).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   const float* A; int64_t lda; int a_trans;
@@ -171,7 +172,7 @@ typedef struct {
   int accumulate;
   int split_k;              /* 0/1 = none */
   int backend;
-  void* workspace; int64_t workspace_bytes;   /* backend 1 only: >= ase_gemm_tc_workspace_bytes() */
+  void* workspace; int64_t workspace_bytes;   /* backends 1, 2: >= ase_gemm_tc_workspace_bytes(), 1024-byte aligned */
   float* colsum_out;        /* optional [N]: colsum_out[n] += sum_m C[m,n] (not with accumulate) */
 } AseGemmParams;
 int ase_gemm(const AseGemmParams* p, void* stream);
@@ -207,7 +208,7 @@ typedef struct {
   float enc_coef, amp_diversity_bonus, amp_diversity_tar;
   float lr, beta1, beta2, adam_eps;
   float rms_eps;      /* 1e-5 */
-  int gemm_backend;   /* 0 SIMT, 1 tcgen05 3xTF32 */
+  int gemm_backend;   /* 0 SIMT, 1 tcgen05 3xTF32, 2 tcgen05 3xFP16 (scaled planes) */
   int mu_activation;  /* 0 none (AMP/ASE), 2 tanh (HRL high-level policy, hrl_network_builder.py:26-29) */
 } AseLearnerConfig;
 
@@ -267,6 +268,11 @@ typedef struct {
 /* Must be called after the parameter arena was modified by anything other than ase_learner_adam_step (checkpoint load,
  * initialisation, broadcast): the tcgen05 backend caches TF32 hi/lo planes of the weights between calls. */
 int ase_learner_params_changed(AseLearner* l);
+/* gemm_backend 2 (scaled FP16 operand planes): sticky status of the per-tensor power-of-two scales, read with one
+ * stream synchronisation.  0 = fine.  Bit 0: a value did not fit the scale predicted from the previous call (> 2^9 growth of a
+ * tensor's max between two consecutive calls); bit 1: a tensor's max shrank by > 2^12 between two calls (its split lost
+ * precision).  Either means the results of the flagged call are not fp32-accurate: the host mirror raises. */
+int ase_learner_plane_status(AseLearner* l, int* flags, void* stream);
 
 /* forward + losses + backward: fills state->grads (sum over local rows; no Adam) */
 int ase_learner_calc_gradients(AseLearner* l, const AseLearnerState* st, const AseMinibatch* mb,

@@ -135,7 +135,7 @@ def test_tc_fp16_planes_dynamic_range():
         ref = a.double() @ b.double().t()
         assert float((C.double() - ref).abs().max() / ref.abs().max()) < 1e-5, (sa, sb)
     # rows of very different magnitude inside one tensor: each output row is judged against ITS OWN scale down to 1e-5 of the
-    # tensor max (hi + lo keeps 22 significant bits for every element within 2^-26 of the max)
+    # tensor max (an exactly scaled split keeps 22 significant bits for every element within 2^-26 of the max)
     rs = torch.logspace(0, -5, 300).unsqueeze(1)
     a = (A * rs).cuda(); b = B.cuda()
     C = ops.gemm(a, b, backend=2)

@@ -106,7 +106,8 @@ def test_calc_gradients_vs_reference_golden_tcgen05(name, backend):
     assert n.value >= 20, f"the tcgen05 kernel was launched only {n.value} times: the learner fell back to SIMT"
 
 
-def test_ppo_kind_vs_oracle():
+@pytest.mark.parametrize('backend', [0, 2])
+def test_ppo_kind_vs_oracle(backend):
     """CommonAgent.calc_gradients (common_agent.py:353-435): plain PPO, unmasked means (HRL high-level policy shape)."""
     from ase_b200 import Learner
     B = 192
@@ -114,9 +115,9 @@ def test_ppo_kind_vs_oracle():
     P = synth.params(shapes, seed=4)
     cfg = dict(O.DEFAULT_CFG)
     st = O.LearnerState(P, 258, 0, 'ppo')
-    ln = Learner('ppo', 258, 64, B, units=(128, 64), hparams={'learning_rate': cfg['lr']})
+    ln = Learner('ppo', 258, 64, B, units=(128, 64), hparams={'learning_rate': cfg['lr']}, gemm_backend=backend)
     ln.load_named(P)
-    for s in range(2):
+    for s in range(4 if backend else 2):       # backend 2: step 0 calibrates the FP16 plane scales exactly, steps 1.. run on predicted scales
         d, _ = synth.minibatch(st, cfg, B, 0, seed=40 + s, kind='ppo', obs_dim=258, act=64)
         out = ln.calc_gradients(_cuda(d))
         res, grads = O.calc_gradients(st, d, cfg, None)
@@ -131,12 +132,13 @@ def test_ppo_kind_vs_oracle():
             assert torch.allclose(ln.named_parameters()[k].cpu(), st.p[k], rtol=1e-5, atol=2e-7), k
 
 
-def test_inference_paths_vs_oracle():
+@pytest.mark.parametrize('backend', [0, 2])
+def test_inference_paths_vs_oracle(backend):
     """get_action_values / _eval_critic / _calc_amp_rewards building blocks (eval mode, no RMS update)."""
     from ase_b200 import Learner, ops
     B, Ba = 256, 64
     P = synth.params(O.ase_param_shapes(), seed=11)
-    ln = Learner('ase', 253, 31, B, amp_dim=1400, latent_dim=64, amp_batch=Ba)
+    ln = Learner('ase', 253, 31, B, amp_dim=1400, latent_dim=64, amp_batch=Ba, gemm_backend=backend)
     ln.load_named(P)
     st = O.LearnerState(P, 253, 1400, 'ase')
     g = torch.Generator().manual_seed(0)
@@ -163,6 +165,28 @@ def test_inference_paths_vs_oracle():
         dr, er, comb = ops.amp_rewards(logits, enc, z.cuda())
         dr_ref, er_ref = O.calc_amp_rewards(st, amp, z, O.DEFAULT_CFG)
         assert torch.allclose(dr.cpu(), dr_ref, rtol=1e-4, atol=1e-4) and torch.allclose(er.cpu(), er_ref, rtol=1e-4, atol=1e-5)
+
+
+def test_fp16_plane_scale_miss_is_reported():
+    """gemm_backend 2 predicts each tensor's power-of-two scale from the previous call.  A tensor whose max jumps by more than
+    2^9 between two calls cannot be represented: the library must say so (sticky flag -> AseError), never return silently wrong
+    gradients; after the parameters are re-announced the scales are re-derived exactly and the same input is fine."""
+    from ase_b200 import Learner, lib as L
+    B = 192
+    P = synth.params(O.amp_param_shapes(obs=258, act=64, amp=0, units=(128, 64)), seed=4)
+    cfg = dict(O.DEFAULT_CFG)
+    st = O.LearnerState(P, 258, 0, 'ppo')
+    ln = Learner('ppo', 258, 64, B, units=(128, 64), hparams={'learning_rate': cfg['lr']}, gemm_backend=2)
+    ln.load_named(P)
+    d, _ = synth.minibatch(st, cfg, B, 0, seed=40, kind='ppo', obs_dim=258, act=64)
+    d = _cuda(d)
+    for _ in range(2):
+        ln.train_result(ln.calc_gradients(d, update_rms=False))             # calibration + one predicted call: fine
+    g_ref = ln.grads.clone()
+    big = dict(d); big['advantages'] = d['advantages'] * 1e6; big['returns'] = d['returns'] * 1e6
+    out = ln.calc_gradients(big, update_rms=False)
+    with pytest.raises(L.AseError):
+        ln.train_result(out)
 
 
 def test_full_size_minibatch_properties():

@@ -7,7 +7,7 @@ from ase_b200.agent import ASEAgent
 from ase_b200.synthetic_env import SyntheticHumanoidEnv
 
 env = SyntheticHumanoidEnv(4096, device='cuda', seed=0)
-cfg = configs.make('ase', device='cuda:0', vec_env=env, num_actors=4096, print_stats=False, gemm_backend=1)
+cfg = configs.make('ase', device='cuda:0', vec_env=env, num_actors=4096, print_stats=False, gemm_backend=2)
 ag = ASEAgent('p', cfg); ag.init_tensors(); ag.obs = ag.env_reset(); ag._init_train()
 for _ in range(2):
     ag.update_epoch(); ag.train_epoch()

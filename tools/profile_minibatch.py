@@ -10,7 +10,7 @@ import torch
 from ase_b200 import Learner, lib as L
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-backend = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+backend = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 B, Ba = 16384, 4096
 g = torch.Generator(device='cuda').manual_seed(0)
 r = lambda *s: torch.randn(*s, device='cuda', generator=g)
