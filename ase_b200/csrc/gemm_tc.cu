@@ -200,44 +200,63 @@ struct TcEpi {
   const float* c_scale;                    // FP16 planes of C: device pointer to the scale they are written with
   unsigned* c_amax;                        // optional: atomicMax of |C| (as uint bits) -- the scale source for the consumers of C
   unsigned* flag;                          // FP16 planes of C written with a PREDICTED scale: sticky overflow flag (bit 0)
+  uint32_t* relu_bits; int64_t ldrb;       // optional: bit (n % 32) of word n / 32 of row m := C[m,n] > 0
+  const uint32_t* mask_bits; int64_t ldmb; // optional: replaces mask_src for mask_mode 1 (same bit layout)
+  int skip_c;                              // the planes are the only consumers of C: no fp32 store
   int debug;   // experiments only (env ASE_TC_DEBUG): 1 skip the whole store phase, 2 skip TMEM drain loads, 4 skip correction MMAs,
                // 16 skip mask loads, 32 skip plane stores, 64 skip column-sum atomics, 128 skip the fp32 C store
 };
 
 // Phase 2 of the epilogue, shared by the tile shapes: a warp writes rows [row0, row0+nrows) of the staged tile; a row is
 // written as BNT/4 float4 by consecutive lanes (full 128-byte lines); bias / activation / mask operands are read with the
-// same coalesced mapping; optional hi/lo planes of C, the running max |C| and the fused column sums (bias gradient) ride along.
+// same coalesced mapping; optional hi/lo planes of C, the ReLU activity bits, the running max |C| and the fused column sums
+// (bias gradient; reduced over the tile's rows in shared memory first: s_colsum[BNT], zeroed by the caller) ride along.
+// Every lane stays in both loops for the whole tile (columns past N are predicated off): the bit packing shuffles need all 32.
 template <bool H>
-__device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* cs, int cs_ld, int row0, int nrows, int BNT, int m0, int n0, int lane) {
+__device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* cs, int cs_ld, float* s_colsum, int row0, int nrows, int BNT, int m0, int n0, int lane) {
   const bool vec_ok = ((e.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.C) & 15) == 0) &&
-                      (!e.mask_mode || (((e.ldm & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.mask_src) & 15) == 0)));
+                      (!e.mask_mode || e.mask_bits || (((e.ldm & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.mask_src) & 15) == 0)));
   const bool add_bias = e.bias && (!e.accumulate || blockIdx.z == 0);
   const uintptr_t pal = H ? 7 : 15;         // 4 plane elements per lane: 8 bytes (halfs) / 16 bytes (fp32 words)
   const bool pvec = e.Chi && ((e.ldp & 3) == 0) && ((reinterpret_cast<uintptr_t>(e.Chi) & pal) == 0) && ((reinterpret_cast<uintptr_t>(e.Clo) & pal) == 0);
   const float cscale = (H && e.Chi && e.c_scale) ? *e.c_scale : 1.0f;
+  const bool use_bits = e.mask_mode == 1 && e.mask_bits != nullptr;
+  const int nib_shift = 4 * (lane & 7);
   float amax = 0.0f;
 #pragma unroll 1
-  for (int cc = lane * 4; cc < BNT; cc += 128) {
+  for (int cc = lane * 4; cc < ((BNT + 127) & ~127); cc += 128) {          // same trip count for every lane (BNT = 64: lanes 16.. idle along)
     const int n = n0 + cc;
-    if (n >= e.N) break;
-    const int nvalid = min(4, e.N - n);
+    const int nvalid = (cc < BNT) ? max(0, min(4, e.N - n)) : 0;
     float bv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     if (add_bias) for (int j = 0; j < nvalid; ++j) bv[j] = e.bias[n + j];
     float cs4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll 4
     for (int r = 0; r < nrows; ++r) {
       const int row = row0 + r, m = m0 + row;
-      if (m >= e.M) break;
-      const float4 t = *reinterpret_cast<const float4*>(cs + row * cs_ld + cc);
+      if (m >= e.M) break;                 // warp-uniform
+      const float4 t = (cc < BNT) ? *reinterpret_cast<const float4*>(cs + row * cs_ld + cc) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
       float x[4] = {t.x + bv[0], t.y + bv[1], t.z + bv[2], t.w + bv[3]};
       float* cp = e.C + (int64_t)m * e.ldc + n;
       if (e.accumulate) {
-        for (int j = 0; j < nvalid; ++j) atomicAdd(cp + j, x[j]);
+        if (vec_ok && nvalid == 4) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(x[0]), "f"(x[1]), "f"(x[2]), "f"(x[3]) : "memory");
+        else for (int j = 0; j < nvalid; ++j) atomicAdd(cp + j, x[j]);
         continue;
       }
       if (e.act == 1) { for (int j = 0; j < 4; ++j) x[j] = fmaxf(x[j], 0.0f); }
       else if (e.act == 2) { for (int j = 0; j < 4; ++j) x[j] = tanhf(x[j]); }
-      if (e.mask_mode && !(e.debug & 16)) {
+      if (e.relu_bits) {                   // 8 lanes x 4 columns = one 32-bit word of the row's activity mask
+        uint32_t w = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) w |= (j < nvalid && x[j] > 0.0f) ? (1u << j) : 0u;
+        w <<= nib_shift;
+        w |= __shfl_xor_sync(0xffffffffu, w, 1); w |= __shfl_xor_sync(0xffffffffu, w, 2); w |= __shfl_xor_sync(0xffffffffu, w, 4);
+        if ((lane & 7) == 0 && nvalid > 0) e.relu_bits[(int64_t)m * e.ldrb + (n >> 5)] = w;
+      }
+      if (use_bits) {
+        const uint32_t w = (nvalid > 0 && !(e.debug & 16)) ? e.mask_bits[(int64_t)m * e.ldmb + (n >> 5)] >> nib_shift : 0xFu;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) x[j] = ((w >> j) & 1u) ? x[j] : 0.0f;
+      } else if (e.mask_mode && !(e.debug & 16) && nvalid > 0) {
         const float* mp = e.mask_src + (int64_t)m * e.ldm + n;
         float mv[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         if (vec_ok && nvalid == 4) { const float4 q = *reinterpret_cast<const float4*>(mp); mv[0] = q.x; mv[1] = q.y; mv[2] = q.z; mv[3] = q.w; }
@@ -245,12 +264,12 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* cs, i
         if (e.mask_mode == 1) { for (int j = 0; j < 4; ++j) x[j] = (mv[j] > 0.0f) ? x[j] : 0.0f; }
         else { for (int j = 0; j < 4; ++j) x[j] *= (1.0f - mv[j] * mv[j]); }
       }
-      if (e.debug & 128) {}
+      if (e.skip_c || (e.debug & 128)) {}
       else if (vec_ok && nvalid == 4) *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
       else for (int j = 0; j < nvalid; ++j) cp[j] = x[j];
 #pragma unroll
       for (int j = 0; j < 4; ++j) { cs4[j] += x[j]; if (j < nvalid) amax = fmaxf(amax, fabsf(x[j])); }
-      if (e.Chi && !(e.debug & 32)) {       // the consumers of C read these planes directly through TMA: no separate split pass
+      if (e.Chi && !(e.debug & 32) && nvalid > 0) {       // the consumers of C read these planes directly through TMA: no separate split pass
         if (!H) {
           float h[4], l[4];
 #pragma unroll
@@ -272,7 +291,7 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* cs, i
         }
       }
     }
-    if (e.colsum && !e.accumulate && !(e.debug & 64)) for (int j = 0; j < nvalid; ++j) atomicAdd(e.colsum + n + j, cs4[j]);
+    if (e.colsum && !e.accumulate && !(e.debug & 64)) for (int j = 0; j < nvalid; ++j) atomicAdd(s_colsum + cc + j, cs4[j]);   // shared-memory atomics
   }
   if ((e.c_amax || (H && e.Chi && e.flag)) && !e.accumulate) {
 #pragma unroll
@@ -473,9 +492,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
                                                                    s2 * (s1 * (acc[c + j + 2] + v[j + 2])), s2 * (s1 * (acc[c + j + 3] + v[j + 3])));
       }
     }
+    float* s_colsum = cs + TC_BM * CS_LD;               // [BN] per-tile column sums, behind the staging tile (pipeline smem is idle)
+    if (e.colsum) for (int c = (lg * 32 + lane); c < BN; c += 128) s_colsum[c] = 0.0f;
     asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 epilogue warps only
     // Phase 2: coalesced epilogue -- warp w owns rows [32w, 32w+32)
-    if (!(e.debug & 1)) epilogue_rows<H>(e, cs, CS_LD, lg * 32, 32, BN, m0, n0, lane);
+    if (!(e.debug & 1)) epilogue_rows<H>(e, cs, CS_LD, s_colsum, lg * 32, 32, BN, m0, n0, lane);
+    if (e.colsum && !e.accumulate) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int c = (lg * 32 + lane); c < BN; c += 128) if (n0 + c < e.N) atomicAdd(e.colsum + n0 + c, s_colsum[c]);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -637,8 +662,15 @@ gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
                                                                    s2 * (s1 * (acc[c + j + 2] + v[j + 2])), s2 * (s1 * (acc[c + j + 3] + v[j + 3])));
       }
     }
+    float* s_colsum = cs + TC_BM * CS_LD;               // [BN] per-tile column sums, behind the staging tile
+    const int et = threadIdx.x - 128;                   // 0..255 within the epilogue warps
+    if (e.colsum) s_colsum[et] = 0.0f;
     asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps only
-    if (!(e.debug & 1)) epilogue_rows<H>(e, cs, CS_LD, (warp - 4) * 16, 16, BN, m0, n0, lane);
+    if (!(e.debug & 1)) epilogue_rows<H>(e, cs, CS_LD, s_colsum, (warp - 4) * 16, 16, BN, m0, n0, lane);
+    if (e.colsum && !e.accumulate) {
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (n0 + et < e.N) atomicAdd(e.colsum + n0 + et, s_colsum[et]);
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -984,12 +1016,12 @@ void PlaneRegistry::add(const float* base, int64_t capacity, float* hi, float* l
   if (n >= MAX) return;
   PlaneBuf& x = b[n++];
   x.base = base; x.capacity = capacity; x.hi = hi; x.lo = lo; x.plane_capacity = plane_capacity;
-  x.ld = 0; x.rows = x.cols = 0; x.ldp = 0; x.valid = false; x.scale_ptr = nullptr; x.amax_site = -1; x.is_static = false;
+  x.ld = 0; x.rows = x.cols = 0; x.ldp = 0; x.valid = false; x.scale_ptr = nullptr; x.amax_site = -1; x.is_static = false; x.fp32_stale = false;
 }
 PlaneBuf* PlaneRegistry::declare(const float* base, int64_t ld, int rows, int cols) {
   PlaneBuf* x = find(base);
   if (!x || x->base != base) return nullptr;
-  x->amax_site = -1; x->is_static = false;
+  x->amax_site = -1; x->is_static = false; x->fp32_stale = false;
   const int64_t ldp = f16 ? (cols + 7) / 8 * 8 : (cols + 3) / 4 * 4;
   if ((int64_t)rows * ldp > (f16 ? 2 : 1) * x->plane_capacity) { x->valid = false; return nullptr; }
   x->ld = ld; x->rows = rows; x->cols = cols; x->ldp = ldp; x->valid = true;
@@ -1001,9 +1033,9 @@ void* PlaneRegistry::plane(const PlaneBuf* x, bool lo, int64_t r0, int64_t c0) c
   const int64_t off = r0 * x->ldp + c0;
   return f16 ? (void*)((__half*)p + off) : (void*)(p + off);
 }
-void PlaneRegistry::invalidate(const float* p) { if (PlaneBuf* x = find(p)) { x->valid = false; x->amax_site = -1; x->is_static = false; } }
+void PlaneRegistry::invalidate(const float* p) { if (PlaneBuf* x = find(p)) { x->valid = false; x->amax_site = -1; x->is_static = false; x->fp32_stale = false; } }
 void PlaneRegistry::invalidate_range(const float* lo_, const float* hi_) {
-  for (int i = 0; i < n; ++i) if (b[i].base >= lo_ && b[i].base < hi_) { b[i].valid = false; b[i].amax_site = -1; b[i].is_static = false; }
+  for (int i = 0; i < n; ++i) if (b[i].base >= lo_ && b[i].base < hi_) { b[i].valid = false; b[i].amax_site = -1; b[i].is_static = false; b[i].fp32_stale = false; }
 }
 int PlaneRegistry::begin_call(cudaStream_t st, int base) {
   call_base = base; gemm_index = 0;
@@ -1038,6 +1070,7 @@ static int resolve_operand(PlaneRegistry* reg, const float* ptr, int64_t ld, int
   const bool H = reg->f16;
   const int pal = H ? 8 : 4;                 // plane leading dimensions / column offsets: 16-byte granules
   if (!x->valid) {
+    if (x->fp32_stale) { set_error("tcgen05 GEMM: a planes-only tensor lost its planes before it was consumed"); return ASE_ERR_INVALID; }
     // adopt the reader's geometry if it starts at the buffer base (inputs written by non-GEMM kernels, weights)
     if (ptr != x->base) return ASE_OK;
     if (!H) {
@@ -1103,6 +1136,13 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   if (H && reg) { if (site_c < 0) { set_error("tcgen05 FP16 GEMM: more GEMMs in one call than scale sites"); return ASE_ERR_WORKSPACE; } reg->gemm_index++; }
   if ((rc = resolve_operand(reg, p.A, p.lda, a_rows, a_cols, &va, site_a, st))) return rc;
   if ((rc = resolve_operand(reg, p.B, p.ldb, b_rows, b_cols, &vb, site_b, st))) return rc;
+  if (reg) {      // a planes-only tensor (fp32 store elided) can only be consumed through its planes / activity bits: anything else is a bug, not a fallback
+    auto stale = [&](const float* ptr) { PlaneBuf* x = ptr ? reg->find(ptr) : nullptr; return x && x->fp32_stale; };
+    if ((!va.ok && stale(p.A)) || (!vb.ok && stale(p.B)) || (p.mask_src && p.mask_mode && !(p.mask_mode == 1 && p.mask_bits) && stale(p.mask_src))) {
+      set_error("tcgen05 GEMM %dx%dx%d: an operand's fp32 copy was elided (c_planes_only) but it is not consumed through its planes", p.M, p.N, p.K);
+      return ASE_ERR_INVALID;
+    }
+  }
   CUtensorMap ah, al, bh, bl;
   char* ws = (char*)p.workspace;
   if (!va.ok || !vb.ok) { if ((rc = gemm_tc_check_workspace(p))) return rc; }
@@ -1155,6 +1195,7 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   e.Chi = e.Clo = nullptr; e.ldp = 0; e.colsum = p.colsum_out;
   e.a_inv = (H && va.scale) ? va.scale + 1 : nullptr; e.b_inv = (H && vb.scale) ? vb.scale + 1 : nullptr;
   e.c_scale = nullptr; e.c_amax = nullptr; e.flag = nullptr;
+  e.relu_bits = p.relu_bits_out; e.ldrb = p.ldrb; e.mask_bits = (e.mask_mode == 1) ? p.mask_bits : nullptr; e.ldmb = p.ldmb; e.skip_c = 0;
   // ---- output planes: a full write at the base of a registered buffer (re)declares its geometry; a partial write
   // keeps planes in sync only if they are currently valid with the same leading dimension; accumulation invalidates
   if (reg && !H) {
@@ -1175,6 +1216,8 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
     // scale.  A tanh-bounded partial write into statically scaled planes (the style columns behind the normalised
     // observations) keeps them in sync.  Anything else leaves the buffer without planes.
     if (PlaneBuf* x = reg->find(p.C)) {
+      if (x->fp32_stale && p.accumulate) { set_error("tcgen05 GEMM: accumulating into a planes-only tensor"); return ASE_ERR_INVALID; }
+      x->fp32_stale = false;
       const bool full = !p.accumulate && p.C == x->base && (int64_t)p.M * pad_to(p.N, 8) <= 2 * x->plane_capacity && (int64_t)(p.M - 1) * p.ldc + p.N <= x->capacity &&
                         !(x->valid && x->is_static && x->ld == p.ldc && (x->rows > p.M || x->cols > p.N));
       if (full) {
@@ -1183,6 +1226,7 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
         if (reg->known[site_c]) {
           x->valid = true; x->amax_site = -1; x->scale_ptr = reg->scale + 2 * site_c;
           e.Chi = x->hi; e.Clo = x->lo; e.ldp = x->ldp; e.c_scale = x->scale_ptr; e.flag = reg->flag;
+          if (p.c_planes_only) { e.skip_c = 1; x->fp32_stale = true; }
         } else { x->valid = false; x->amax_site = site_c; }
       } else if (!p.accumulate && x->valid && x->is_static && x->ld == p.ldc && p.act == 2 && !p.mask_src) {
         const int64_t off = p.C - x->base, r0 = off / x->ld, c0 = off - r0 * x->ld;

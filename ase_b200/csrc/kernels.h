@@ -32,6 +32,7 @@ struct PlaneBuf {
   const float* scale_ptr;                       // device [scale, 1/scale] the current planes were written with
   int amax_site;                                // site whose amax slot holds max |x| of the current fp32 contents (tracked by the GEMM that wrote them), -1 = unknown
   bool is_static;                               // planes written with the registry's static scale by a bounded non-GEMM writer
+  bool fp32_stale;                              // the last producer skipped the fp32 store (c_planes_only): only the planes are current
 };
 // FP16 format (backend 2): every tensor is multiplied by a power of two before the hi/lo split.  Scales live in device memory,
 // one slot per SITE = (GEMM index within the top-level call, operand A / B / output C): the static kernel schedule of the learner

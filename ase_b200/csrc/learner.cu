@@ -83,6 +83,8 @@ struct AseLearner {
   float *Xa, *Xc, *Zc, *S[ASE_MAX_LAYERS], *H[ASE_MAX_LAYERS], *MU, *C[ASE_MAX_LAYERS], *V;
   float *Xd, *D[ASE_MAX_LAYERS], *LOGIT, *E;
   float *dMU, *dV, *dLOGIT, *dE, *G0, *G1, *U[ASE_MAX_LAYERS], *Gx;
+  // ReLU activity bits of the stored activations (1 bit per element, row stride = ceil(cols / 32) words): the backward masks
+  uint32_t *Sb[ASE_MAX_LAYERS], *Hb[ASE_MAX_LAYERS], *Cb[ASE_MAX_LAYERS], *Db[ASE_MAX_LAYERS];
   double* acc;
   void *rms_obs_scratch, *rms_amp_scratch;
   void* tc_ws; int64_t tc_ws_bytes;
@@ -105,6 +107,8 @@ struct Carver {
     return p;
   }
 };
+
+static inline int64_t bits_ld(int cols) { return (cols + 31) / 32; }
 
 static int64_t tc_ws_need(const AseLearner& L) {
   if (L.cfg.gemm_backend < 1) return 0;
@@ -159,6 +163,9 @@ static void carve(AseLearner& L, void* ws, int64_t* total) {
   L.G0 = cv.take<float>(gsz);
   L.G1 = cv.take<float>(gsz);
   L.acc = cv.take<double>(ACC_COUNT);
+  for (int k = 0; k < c.n_style_units && L.ase; ++k) L.Sb[k] = cv.take<uint32_t>(Ra * bits_ld(c.style_units[k]));
+  for (int k = 0; k < c.n_units; ++k) { L.Hb[k] = cv.take<uint32_t>(Ra * bits_ld(c.units[k])); L.Cb[k] = cv.take<uint32_t>(B * bits_ld(c.units[k])); }
+  for (int k = 0; k < c.n_disc_units && L.amp; ++k) L.Db[k] = cv.take<uint32_t>(3 * Ba * bits_ld(c.disc_units[k]));
   L.rms_obs_scratch = cv.take<char>(rms_scratch_bytes(c.obs_dim, L.B, 1));
   L.rms_amp_scratch = L.amp ? cv.take<char>(rms_scratch_bytes(c.amp_dim, L.Ba, 3)) : nullptr;
   L.tc_ws_bytes = tc_ws_need(L);
@@ -260,20 +267,24 @@ struct G {
     p.alpha = 1.0f; p.backend = L.cfg.gemm_backend; p.workspace = L.tc_ws; p.workspace_bytes = L.tc_ws_bytes;
     return p;
   }
-  // Y[M,N] (ldc) = act(X[M,K] (lda) . W^T + b),  W = layer weight [N,K]
-  int fwd(const float* X, int64_t lda, int M, const Layer& l, float* Y, int64_t ldc, int act) const {
+  // Y[M,N] (ldc) = act(X[M,K] (lda) . W^T + b),  W = layer weight [N,K].  bits: ReLU activity of Y for the backward pass;
+  // planes_only: Y is consumed only as a GEMM operand / through bits (its fp32 store may be elided)
+  int fwd(const float* X, int64_t lda, int M, const Layer& l, float* Y, int64_t ldc, int act, uint32_t* bits = nullptr, bool planes_only = false) const {
     AseGemmParams p = base();
     p.A = X; p.lda = lda; p.B = P + l.w; p.ldb = l.in; p.C = Y; p.ldc = ldc; p.M = M; p.N = l.out; p.K = l.in;
     p.bias = P + l.b; p.act = act;
+    p.relu_bits_out = bits; p.ldrb = bits_ld(l.out); p.c_planes_only = planes_only ? 1 : 0;
     return gemm_dispatch(p, st, reg());
   }
-  // dX[M,ncols] (ldc) = (dZ[M,l.out] . W[:, col0:col0+ncols]) (*) mask
+  // dX[M,ncols] (ldc) = (dZ[M,l.out] . W[:, col0:col0+ncols]) (*) mask;  mask_bits (row stride bits_ld(ncols)) replaces mask_src on the
+  // tcgen05 backends for mask_mode 1
   int dx(const float* dZ, int64_t ldz, int M, const Layer& l, int col0, int ncols, float* dX, int64_t ldc,
-         const float* mask_src, int64_t ldm, int mask_mode, float* colsum = nullptr) const {
+         const float* mask_src, int64_t ldm, int mask_mode, float* colsum = nullptr, const uint32_t* mask_bits = nullptr, bool planes_only = false) const {
     AseGemmParams p = base();
     p.colsum_out = colsum;
     p.A = dZ; p.lda = ldz; p.B = P + l.w + col0; p.ldb = l.in; p.b_trans = 1; p.C = dX; p.ldc = ldc; p.M = M; p.N = ncols; p.K = l.out;
     p.mask_src = mask_src; p.ldm = ldm; p.mask_mode = mask_src ? mask_mode : 0;
+    p.mask_bits = (mask_mode == 1) ? mask_bits : nullptr; p.ldmb = bits_ld(ncols); p.c_planes_only = planes_only ? 1 : 0;
     return gemm_dispatch(p, st, reg());
   }
   // dW[l.out, l.in] += dZ[M,l.out]^T . X[M,l.in]
@@ -295,17 +306,19 @@ struct G {
   }
   int db(const float* dZ, int64_t ldz, int M, const Layer& l) const { return launch_colsum(dZ, ldz, M, l.out, GR + l.b, st); }
   // Y = X . W^T (no bias), masked: used by the gradient-penalty backward chain
-  int nt_masked(const float* X, int64_t lda, int M, const Layer& l, float* Y, const float* mask_src, int64_t ldm) const {
+  int nt_masked(const float* X, int64_t lda, int M, const Layer& l, float* Y, const float* mask_src, int64_t ldm, const uint32_t* mask_bits,
+                float* colsum = nullptr) const {
     AseGemmParams p = base();
     p.A = X; p.lda = lda; p.B = P + l.w; p.ldb = l.in; p.C = Y; p.ldc = l.out; p.M = M; p.N = l.out; p.K = l.in;
-    p.mask_src = mask_src; p.ldm = ldm; p.mask_mode = 1;
+    p.mask_src = mask_src; p.ldm = ldm; p.mask_mode = 1; p.mask_bits = mask_bits; p.ldmb = bits_ld(l.out);
+    p.colsum_out = colsum; p.c_planes_only = 1;       // consumed by the next dW / masked GEMM only (the last one by its fused column sum)
     return gemm_dispatch(p, st, reg());
   }
 };
 
 // Backward through a ReLU MLP trunk.  On entry *cur holds dZ of the LAST layer (already masked), [M, out_last].
 // acts[k] = stored post-activation outputs, X0 (ld ldx0) = trunk input.  On exit *cur holds dZ of layer 0.
-static int trunk_backward(const G& g, const Layer* layers, int n, float* const* acts, const float* X0, int64_t ldx0, int M,
+static int trunk_backward(const G& g, const Layer* layers, int n, float* const* acts, uint32_t* const* bits, const float* X0, int64_t ldx0, int M,
                           float** cur, float** other, bool have_db = false) {
   for (int k = n - 1; k >= 0; --k) {
     const Layer& l = layers[k];
@@ -314,8 +327,8 @@ static int trunk_backward(const G& g, const Layer* layers, int n, float* const* 
     RC(g.dw(*cur, l.out, M, l, Xin, ldin));
     if (!have_db) RC(g.db(*cur, l.out, M, l));
     if (k > 0) {
-      // the dX GEMM that produces dZ of layer k-1 also column-sums it into that layer's bias gradient
-      RC(g.dx(*cur, l.out, M, l, 0, l.in, *other, l.in, acts[k - 1], layers[k - 1].out, 1, g.GR + layers[k - 1].b));
+      // the dX GEMM that produces dZ of layer k-1 also column-sums it into that layer's bias gradient; dZ is consumed by GEMMs only
+      RC(g.dx(*cur, l.out, M, l, 0, l.in, *other, l.in, acts[k - 1], layers[k - 1].out, 1, g.GR + layers[k - 1].b, bits[k - 1], true));
       have_db = true;
       float* t = *cur; *cur = *other; *other = t;
     }
@@ -333,17 +346,17 @@ static int forward_actor_critic(const G& g, int rows_a, int rows_c) {
   AseLearner& L = g.L; const Net& n = L.net; const AseLearnerConfig& c = L.cfg;
   if (L.ase && rows_a > 0) {   // style branch: tanh(dense(relu-mlp(z))) written next to the normalised obs (ase_network_builder.py:305-324)
     const float* x = L.Zc; int64_t ld = c.latent_dim;
-    for (int k = 0; k < n.n_style; ++k) { RC(g.fwd(x, ld, rows_a, n.style[k], L.S[k], n.style[k].out, 1)); x = L.S[k]; ld = n.style[k].out; }
+    for (int k = 0; k < n.n_style; ++k) { RC(g.fwd(x, ld, rows_a, n.style[k], L.S[k], n.style[k].out, 1, L.Sb[k], true)); x = L.S[k]; ld = n.style[k].out; }
     RC(g.fwd(x, ld, rows_a, n.style_dense, L.Xa + c.obs_dim, L.ldx, 2));
   }
   if (rows_a > 0) {
     const float* x = L.Xa; int64_t ld = L.ldx;
-    for (int k = 0; k < n.n_actor; ++k) { RC(g.fwd(x, ld, rows_a, n.actor[k], L.H[k], n.actor[k].out, 1)); x = L.H[k]; ld = n.actor[k].out; }
+    for (int k = 0; k < n.n_actor; ++k) { RC(g.fwd(x, ld, rows_a, n.actor[k], L.H[k], n.actor[k].out, 1, L.Hb[k], true)); x = L.H[k]; ld = n.actor[k].out; }
     RC(g.fwd(x, ld, rows_a, n.mu, L.MU, c.act_dim, c.mu_activation == 2 ? 2 : 0));
   }
   if (rows_c > 0) {
     const float* x = L.Xc; int64_t ld = L.ldx;
-    for (int k = 0; k < n.n_critic; ++k) { RC(g.fwd(x, ld, rows_c, n.critic[k], L.C[k], n.critic[k].out, 1)); x = L.C[k]; ld = n.critic[k].out; }
+    for (int k = 0; k < n.n_critic; ++k) { RC(g.fwd(x, ld, rows_c, n.critic[k], L.C[k], n.critic[k].out, 1, L.Cb[k], true)); x = L.C[k]; ld = n.critic[k].out; }
     RC(g.fwd(x, ld, rows_c, n.value, L.V, 1, 0));
   }
   return ASE_OK;
@@ -352,7 +365,8 @@ static int forward_actor_critic(const G& g, int rows_a, int rows_c) {
 static int forward_disc(const G& g, int rows, int enc_rows) {
   AseLearner& L = g.L; const Net& n = L.net; const AseLearnerConfig& c = L.cfg;
   const float* x = L.Xd; int64_t ld = L.amp_ld;
-  for (int k = 0; k < n.n_disc; ++k) { RC(g.fwd(x, ld, rows, n.disc[k], L.D[k], n.disc[k].out, 1)); x = L.D[k]; ld = n.disc[k].out; }
+  // (the top disc layer keeps its fp32 copy: gp_u_last / relu_mask_inplace read it)
+  for (int k = 0; k < n.n_disc; ++k) { RC(g.fwd(x, ld, rows, n.disc[k], L.D[k], n.disc[k].out, 1, L.Db[k], k < n.n_disc - 1)); x = L.D[k]; ld = n.disc[k].out; }
   RC(g.fwd(x, ld, rows, n.logit, L.LOGIT, 1, 0));
   if (L.ase && enc_rows > 0) RC(g.fwd(x, ld, enc_rows, n.enc, L.E, c.latent_dim, 0));
   return ASE_OK;
@@ -523,18 +537,18 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
     const Layer& last = n.actor[n.n_actor - 1];
     RC(g.dw(L.dMU, A, Ra, n.mu, L.H[n.n_actor - 1], last.out));
     RC(g.db(L.dMU, A, Ra, n.mu));
-    RC(g.dx(L.dMU, A, Ra, n.mu, 0, last.out, cur, last.out, L.H[n.n_actor - 1], last.out, 1, s->grads + last.b));
-    RC(trunk_backward(g, n.actor, n.n_actor, L.H, L.Xa, L.ldx, Ra, &cur, &oth, true));
+    RC(g.dx(L.dMU, A, Ra, n.mu, 0, last.out, cur, last.out, L.H[n.n_actor - 1], last.out, 1, s->grads + last.b, L.Hb[n.n_actor - 1], true));
+    RC(trunk_backward(g, n.actor, n.n_actor, L.H, L.Hb, L.Xa, L.ldx, Ra, &cur, &oth, true));
     if (L.ase) {
       // d(style pre-activation) = (dZ0 . W0[:, obs:obs+Z]) * (1 - style^2)
       const Layer& l0 = n.actor[0];
-      RC(g.dx(cur, l0.out, Ra, l0, c.obs_dim, Z, oth, Z, L.Xa + c.obs_dim, L.ldx, 2, s->grads + n.style_dense.b));
+      RC(g.dx(cur, l0.out, Ra, l0, c.obs_dim, Z, oth, Z, L.Xa + c.obs_dim, L.ldx, 2, s->grads + n.style_dense.b, nullptr, true));
       { float* t = cur; cur = oth; oth = t; }
       const Layer& sd = n.style_dense; const Layer& sl = n.style[n.n_style - 1];
       RC(g.dw(cur, Z, Ra, sd, L.S[n.n_style - 1], sl.out));
-      RC(g.dx(cur, Z, Ra, sd, 0, sl.out, oth, sl.out, L.S[n.n_style - 1], sl.out, 1, s->grads + sl.b));
+      RC(g.dx(cur, Z, Ra, sd, 0, sl.out, oth, sl.out, L.S[n.n_style - 1], sl.out, 1, s->grads + sl.b, L.Sb[n.n_style - 1], true));
       { float* t = cur; cur = oth; oth = t; }
-      RC(trunk_backward(g, n.style, n.n_style, L.S, L.Zc, Z, Ra, &cur, &oth, true));
+      RC(trunk_backward(g, n.style, n.n_style, L.S, L.Sb, L.Zc, Z, Ra, &cur, &oth, true));
     }
   }
   // ---- backward: critic ---------------------------------------------------------------------------------
@@ -542,8 +556,8 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
     const Layer& last = n.critic[n.n_critic - 1];
     RC(g.dw(L.dV, 1, B, n.value, L.C[n.n_critic - 1], last.out));
     RC(g.db(L.dV, 1, B, n.value));
-    RC(g.dx(L.dV, 1, B, n.value, 0, last.out, cur, last.out, L.C[n.n_critic - 1], last.out, 1, s->grads + last.b));
-    RC(trunk_backward(g, n.critic, n.n_critic, L.C, L.Xc, L.ldx, B, &cur, &oth, true));
+    RC(g.dx(L.dV, 1, B, n.value, 0, last.out, cur, last.out, L.C[n.n_critic - 1], last.out, 1, s->grads + last.b, L.Cb[n.n_critic - 1], true));
+    RC(trunk_backward(g, n.critic, n.n_critic, L.C, L.Cb, L.Xc, L.ldx, B, &cur, &oth, true));
   }
   // ---- backward: discriminator (+ encoder through the shared trunk) -------------------------------------
   if (L.amp) {
@@ -566,9 +580,9 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
       ASE_LAUNCH_OK();
       g.inval(cur);
     } else {
-      RC(g.dx(L.dLOGIT, 1, R3, n.logit, 0, last.out, cur, last.out, L.D[nd - 1], last.out, 1, s->grads + last.b));
+      RC(g.dx(L.dLOGIT, 1, R3, n.logit, 0, last.out, cur, last.out, L.D[nd - 1], last.out, 1, s->grads + last.b, L.Db[nd - 1], true));
     }
-    RC(trunk_backward(g, n.disc, nd, L.D, L.Xd, L.amp_ld, R3, &cur, &oth, !L.ase));
+    RC(trunk_backward(g, n.disc, nd, L.D, L.Db, L.Xd, L.amp_ld, R3, &cur, &oth, !L.ase));
 
     // ---- gradient penalty on the demo rows: analytic double backward (amp_agent.py:454-459) -------------
     const int64_t demo = (int64_t)2 * Ba;
@@ -577,19 +591,21 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
     g.inval(L.U[nd - 1]);
     for (int k = nd - 1; k >= 1; --k)   // U_{k-1} = D_{k-1} (*) (U_k . W_k)
       RC(g.dx(L.U[k], n.disc[k].out, Ba, n.disc[k], 0, n.disc[k].in, L.U[k - 1], n.disc[k].in,
-              L.D[k - 1] + demo * n.disc[k - 1].out, n.disc[k - 1].out, 1));
+              L.D[k - 1] + demo * n.disc[k - 1].out, n.disc[k - 1].out, 1, nullptr, L.Db[k - 1] + demo * bits_ld(n.disc[k - 1].out), true));
     RC(g.dx(L.U[0], n.disc[0].out, Ba, n.disc[0], 0, c.amp_dim, L.Gx, L.amp_ld, nullptr, 0, 0));     // G = U_0 . W_0
     // (padding columns of Gx are zero: they are never written)
     RC(launch_gp_scale(L.Gx, (int64_t)Ba * L.amp_ld, c.disc_coef * c.disc_grad_penalty * 2.0f / (float)Ba, L.acc, st));
     g.inval(L.Gx);
     RC(g.dw(L.U[0], n.disc[0].out, Ba, n.disc[0], L.Gx, L.amp_ld));                                   // dW_0 += U_0^T Gbar
-    RC(g.nt_masked(L.Gx, L.amp_ld, Ba, n.disc[0], cur, L.D[0] + demo * n.disc[0].out, n.disc[0].out)); // Ubar_0
+    // (the last masked GEMM of the chain column-sums its output into d w_logit: d w_logit += sum_rows Ubar_last)
+    RC(g.nt_masked(L.Gx, L.amp_ld, Ba, n.disc[0], cur, L.D[0] + demo * n.disc[0].out, n.disc[0].out, L.Db[0] + demo * bits_ld(n.disc[0].out),
+                   nd == 1 ? s->grads + n.logit.w : nullptr));                                       // Ubar_0
     for (int k = 1; k < nd; ++k) {
       RC(g.dw(L.U[k], n.disc[k].out, Ba, n.disc[k], cur, n.disc[k].in));                              // dW_k += U_k^T Ubar_{k-1}
-      RC(g.nt_masked(cur, n.disc[k].in, Ba, n.disc[k], oth, L.D[k] + demo * n.disc[k].out, n.disc[k].out));
+      RC(g.nt_masked(cur, n.disc[k].in, Ba, n.disc[k], oth, L.D[k] + demo * n.disc[k].out, n.disc[k].out, L.Db[k] + demo * bits_ld(n.disc[k].out),
+                     k == nd - 1 ? s->grads + n.logit.w : nullptr));
       { float* t = cur; cur = oth; oth = t; }
     }
-    RC(launch_colsum(cur, last.out, Ba, last.out, s->grads + n.logit.w, st));                          // d w_logit += sum_rows Ubar_last
 
     // ---- logit-weight regulariser + weight decay (amp_agent.py:448-466) ---------------------------------
     for (int k = 0; k < nd; ++k)

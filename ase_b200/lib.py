@@ -42,7 +42,8 @@ class GemmParams(C.Structure):
     _fields_ = [('A', vp), ('lda', i64), ('a_trans', i32), ('B', vp), ('ldb', i64), ('b_trans', i32),
                 ('C', vp), ('ldc', i64), ('M', i32), ('N', i32), ('K', i32), ('alpha', f32), ('bias', vp), ('act', i32),
                 ('mask_src', vp), ('ldm', i64), ('mask_mode', i32), ('accumulate', i32), ('split_k', i32), ('backend', i32),
-                ('workspace', vp), ('workspace_bytes', i64), ('colsum_out', vp)]
+                ('workspace', vp), ('workspace_bytes', i64), ('colsum_out', vp),
+                ('relu_bits_out', vp), ('ldrb', i64), ('mask_bits', vp), ('ldmb', i64), ('c_planes_only', i32)]
 
 
 class LearnerConfig(C.Structure):

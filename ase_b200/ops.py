@@ -184,7 +184,7 @@ def calc_advs(returns, values, mask=None):
 
 
 def gemm(A, B, a_trans=False, b_trans=False, bias=None, act=0, mask_src=None, mask_mode=0, out=None, accumulate=False,
-         split_k=0, alpha=1.0, backend=0, colsum_out=None):
+         split_k=0, alpha=1.0, backend=0, colsum_out=None, relu_bits_out=None, mask_bits=None):
     """C = epi(alpha * op(A) . op(B)); see include/ase_b200.h (AseGemmParams)."""
     M = A.shape[1] if a_trans else A.shape[0]
     K = A.shape[0] if a_trans else A.shape[1]
@@ -201,6 +201,7 @@ def gemm(A, B, a_trans=False, b_trans=False, bias=None, act=0, mask_src=None, ma
         ws = ws[off:off + wsb]
     p = L.GemmParams(_p(A), A.stride(0), int(a_trans), _p(B), B.stride(0), int(b_trans), _p(out), out.stride(0), M, N, K, alpha,
                      _p(bias), act, _p(mask_src), 0 if mask_src is None else mask_src.stride(0), mask_mode, int(accumulate),
-                     split_k, backend, _p(ws), wsb, _p(colsum_out))
+                     split_k, backend, _p(ws), wsb, _p(colsum_out), _p(relu_bits_out), 0 if relu_bits_out is None else relu_bits_out.stride(0),
+                     _p(mask_bits), 0 if mask_bits is None else mask_bits.stride(0), 0)
     check(lib.ase_gemm(C.byref(p), _stream()), 'ase_gemm')
     return out

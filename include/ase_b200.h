@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define ASE_ABI_VERSION 1
+#define ASE_ABI_VERSION 2
 #define ASE_MAX_LAYERS 4
 
 typedef enum {
@@ -174,6 +174,14 @@ typedef struct {
   int backend;
   void* workspace; int64_t workspace_bytes;   /* backends 1, 2: >= ase_gemm_tc_workspace_bytes(), 1024-byte aligned */
   float* colsum_out;        /* optional [N]: colsum_out[n] += sum_m C[m,n] (not with accumulate) */
+  /* tcgen05 backends, optional (NULL / 0 = unused; the SIMT backend ignores them):
+   *  relu_bits_out [M, ldrb words]: bit n%32 of word n/32 of row m := (C[m,n] > 0) -- the ReLU activity of a forward layer,
+   *    1 bit instead of 32 for the backward pass;  mask_bits [M, ldmb words]: used INSTEAD of mask_src for mask_mode 1;
+   *  c_planes_only: the caller promises that C is only ever consumed as a GEMM operand (through the learner's operand
+   *    planes) or through relu_bits_out, so the fp32 store may be skipped whenever the planes are written. */
+  uint32_t* relu_bits_out; int64_t ldrb;
+  const uint32_t* mask_bits; int64_t ldmb;
+  int c_planes_only;
 } AseGemmParams;
 int ase_gemm(const AseGemmParams* p, void* stream);
 int64_t ase_gemm_tc_workspace_bytes(int M, int N, int K);

@@ -123,6 +123,29 @@ def test_tc_epilogues_and_split_k(tc):
     _run(256, 256, 2048, False, False, tc, alpha=0.25, tol=2e-5)      # > STAGES k-blocks: ring wrap-around + phase flips
 
 
+@pytest.mark.parametrize('tc', TC_BACKENDS)
+@pytest.mark.parametrize('M,N,K', [(300, 512, 96), (256, 96, 64), (200, 40, 50), (1000, 1024, 128)])
+def test_tc_relu_activity_bits_roundtrip(tc, M, N, K):
+    """relu_bits_out packs (C > 0) into 1 bit per element (word n / 32, bit n % 32); a masked GEMM given those bits instead of the
+    fp32 activation must produce exactly what it produces from the fp32 mask (the backward pass reads 1 bit instead of 32)."""
+    from ase_b200 import ops
+    g = torch.Generator().manual_seed(M + N)
+    A = torch.randn(M, K, generator=g).cuda(); W = torch.randn(N, K, generator=g).cuda(); bias = torch.randn(N, generator=g).cuda()
+    ldb = (N + 31) // 32
+    bits = torch.zeros(M, ldb, dtype=torch.int32, device='cuda')
+    Y = ops.gemm(A, W, bias=bias, act=1, backend=tc, relu_bits_out=bits)
+    torch.cuda.synchronize()
+    cols = torch.arange(N, device='cuda')
+    unpacked = ((bits[:, cols // 32] >> (cols % 32)) & 1).bool()
+    assert torch.equal(unpacked, Y > 0)
+    if N % 32:
+        assert int((bits[:, -1].long() & 0xFFFFFFFF >> (N % 32) << (N % 32)).abs().max()) == 0      # padding bits stay clear
+    dZ = torch.randn(M, 70, generator=torch.Generator().manual_seed(1)).cuda(); W2 = torch.randn(70, N, generator=g).cuda()
+    a = ops.gemm(dZ, W2, b_trans=True, mask_src=Y, mask_mode=1, backend=tc)
+    b = ops.gemm(dZ, W2, b_trans=True, mask_src=Y, mask_mode=1, backend=tc, mask_bits=bits)
+    assert torch.equal(a, b)
+
+
 def test_tc_fp16_planes_dynamic_range():
     """Backend 2 scales every tensor by a power of two before the FP16 hi/lo split: gradient-sized (1e-9) and large (1e+6)
     operands, and a tensor whose entries span 7 decades, must come out as accurately as O(1) ones."""
