@@ -304,6 +304,128 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* cs, i
   }
 }
 
+// Fast store phase of the 128x256 kernel for interior, aligned tiles (the generic epilogue_rows above handles everything else).
+// The generic loop spends ~500 issue slots per (row, 4-column) item on predicates, 64-bit address arithmetic and scalar tails
+// (ncu r01b: 43 % of the kernel's lifetime, issue-bound, not memory-bound).  Here a lane owns 8 consecutive columns of each of the
+// warp's 16 rows: two LDS.128 from the staged tile, one 16-byte store per half plane, pointers advanced by the row strides, the
+// rows' activity-mask words prefetched before the loop, no bounds checks.
+__device__ __forceinline__ bool epilogue_fast256_ok(const TcEpi& e, int m0, int n0, bool H) {
+  if (e.accumulate || m0 + TC_BM > e.M || n0 + 256 > e.N) return false;
+  if ((e.ldc & 3) || (reinterpret_cast<uintptr_t>(e.C) & 15)) return false;
+  if (e.bias && (reinterpret_cast<uintptr_t>(e.bias) & 15)) return false;
+  if (e.Chi && (!H || (e.ldp & 7) || (reinterpret_cast<uintptr_t>(e.Chi) & 15) || (reinterpret_cast<uintptr_t>(e.Clo) & 15))) return false;
+  if (e.mask_mode && !(e.mask_mode == 1 && e.mask_bits) && ((e.ldm & 3) || (reinterpret_cast<uintptr_t>(e.mask_src) & 15))) return false;
+  return true;
+}
+
+template <bool H>
+__device__ __forceinline__ void epilogue_fast256(const TcEpi& e, const float* cs, int cs_ld, float* s_colsum, int row0, int m0, int n0, int lane) {
+  constexpr int NR = 16;
+  const int c8 = lane * 8, n = n0 + c8;
+  const int64_t m = m0 + row0;
+  float bv[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  if (e.bias) {
+    const float4 b0 = *reinterpret_cast<const float4*>(e.bias + n), b1 = *reinterpret_cast<const float4*>(e.bias + n + 4);
+    bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+  }
+  const float cscale = (H && e.Chi && e.c_scale) ? *e.c_scale : 1.0f;
+  const bool use_bits = e.mask_mode == 1 && e.mask_bits != nullptr;
+  const int sh = 8 * (lane & 3);                       // this lane's byte of the 32-column activity word
+  // activity-mask words: 4 rows per group, the next group's words are in flight while the current one is processed
+  const uint32_t* mb = use_bits ? e.mask_bits + m * e.ldmb + (n >> 5) : nullptr;
+  uint32_t mw[4] = {0, 0, 0, 0}, mwn[4] = {0, 0, 0, 0};
+  if (use_bits) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) mw[r] = __ldg(mb + (int64_t)r * e.ldmb);
+  }
+  float* cp = e.C + m * e.ldc + n;
+  __half* hp = e.Chi ? (__half*)e.Chi + m * e.ldp + n : nullptr;
+  __half* lp = e.Chi ? (__half*)e.Clo + m * e.ldp + n : nullptr;
+  uint32_t* rb = e.relu_bits ? e.relu_bits + m * e.ldrb + (n >> 5) : nullptr;
+  const float* mp = (e.mask_mode && !use_bits) ? e.mask_src + m * e.ldm + n : nullptr;
+  const float* sp = cs + row0 * cs_ld + c8;
+  float cs8[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  float amax = 0.0f;
+#pragma unroll 1
+  for (int g = 0; g < NR / 4; ++g) {
+  if (use_bits && g + 1 < NR / 4) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) mwn[r] = __ldg(mb + (int64_t)(4 * (g + 1) + r) * e.ldmb);
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const float4 t0 = *reinterpret_cast<const float4*>(sp), t1 = *reinterpret_cast<const float4*>(sp + 4);
+    float x[8] = {t0.x + bv[0], t0.y + bv[1], t0.z + bv[2], t0.w + bv[3], t1.x + bv[4], t1.y + bv[5], t1.z + bv[6], t1.w + bv[7]};
+    if (e.act == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.0f);
+    } else if (e.act == 2) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = tanhf(x[j]);
+    }
+    if (rb) {
+      uint32_t w = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) w |= (x[j] > 0.0f) ? (1u << j) : 0u;
+      w <<= sh;
+      w |= __shfl_xor_sync(0xffffffffu, w, 1); w |= __shfl_xor_sync(0xffffffffu, w, 2);
+      if ((lane & 3) == 0) *rb = w;
+      rb += e.ldrb;
+    }
+    if (use_bits) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = ((mw[r] >> (sh + j)) & 1u) ? x[j] : 0.0f;
+    } else if (mp) {
+      const float4 q0 = *reinterpret_cast<const float4*>(mp), q1 = *reinterpret_cast<const float4*>(mp + 4);
+      const float mv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+      if (e.mask_mode == 1) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (mv[j] > 0.0f) ? x[j] : 0.0f;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] *= (1.0f - mv[j] * mv[j]);
+      }
+      mp += e.ldm;
+    }
+    if (!e.skip_c) {
+      *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
+      *reinterpret_cast<float4*>(cp + 4) = make_float4(x[4], x[5], x[6], x[7]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { cs8[j] += x[j]; amax = fmaxf(amax, fabsf(x[j])); }
+    if (H && hp) {
+      uint32_t hw[4], lw[4];
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        __half h0, l0, h1, l1;
+        split_f16(x[j] * cscale, h0, l0); split_f16(x[j + 1] * cscale, h1, l1);
+        hw[j >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+        lw[j >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+      }
+      *reinterpret_cast<uint4*>(hp) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+      *reinterpret_cast<uint4*>(lp) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+      hp += e.ldp; lp += e.ldp;
+    }
+    cp += e.ldc; sp += cs_ld;
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) mw[r] = mwn[r];
+  }
+  if (e.colsum) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(s_colsum + c8 + j, cs8[j]);
+  }
+  if (e.c_amax || (H && e.Chi && e.flag)) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if (lane == 0 && amax > 0.0f) {
+      if (e.c_amax) atomicMax(e.c_amax, __float_as_uint(amax));
+      if (H && e.Chi && e.flag && !(amax * cscale <= 60000.0f)) atomicOr(e.flag, 1u);
+      if (H && e.Chi && e.flag && cscale == 0.0f) atomicOr(e.flag, 2u);
+    }
+  }
+}
+
 template <int BN, int STAGES>
 struct TcSmem {
   static constexpr int A_BYTES = TC_BM * 128;                // 16 KB per plane: one 128-byte k-block row per operand row
@@ -666,7 +788,10 @@ gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
     const int et = threadIdx.x - 128;                   // 0..255 within the epilogue warps
     if (e.colsum) s_colsum[et] = 0.0f;
     asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps only
-    if (!(e.debug & 1)) epilogue_rows<H>(e, cs, CS_LD, s_colsum, (warp - 4) * 16, 16, BN, m0, n0, lane);
+    if (!(e.debug & 1)) {
+      if (epilogue_fast256_ok(e, m0, n0, H) && !(e.debug & 256)) epilogue_fast256<H>(e, cs, CS_LD, s_colsum, (warp - 4) * 16, m0, n0, lane);
+      else epilogue_rows<H>(e, cs, CS_LD, s_colsum, (warp - 4) * 16, 16, BN, m0, n0, lane);
+    }
     if (e.colsum && !e.accumulate) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (n0 + et < e.N) atomicAdd(e.colsum + n0 + et, s_colsum[et]);

@@ -5,7 +5,7 @@
 #                                      gpurun_out/ncu_<tag>_dw.ncu-rep  (a split-K dW GEMM)
 tag=${1:-r01}
 common="--set full --import-source on --clock-control none --kernel-name-base demangled"
-ncu $common --kernel-name "regex:gemm_tc256_kernel<0, 0, 1>" --launch-skip 28 --launch-count 1 -f -o gpurun_out/ncu_${tag}_fwd python tools/profile_minibatch.py 3 2 > gpurun_out/ncu_${tag}_fwd.log 2>&1
-ncu $common --kernel-name "regex:gemm_tc256_kernel<0, 1, 1>" --launch-skip 30 --launch-count 1 -f -o gpurun_out/ncu_${tag}_dx python tools/profile_minibatch.py 3 2 > gpurun_out/ncu_${tag}_dx.log 2>&1
-ncu $common --kernel-name "regex:gemm_tc256_kernel<1, 1, 1>" --launch-skip 32 --launch-count 1 -f -o gpurun_out/ncu_${tag}_dw python tools/profile_minibatch.py 3 2 > gpurun_out/ncu_${tag}_dw.log 2>&1
+ncu $common --kernel-name "regex:gemm_tc256_kernel<.bool.0, .bool.0, .bool.1>" --launch-skip 28 --launch-count 1 -f -o gpurun_out/ncu_${tag}_fwd python tools/profile_minibatch.py 3 2 > gpurun_out/ncu_${tag}_fwd.log 2>&1
+ncu $common --kernel-name "regex:gemm_tc256_kernel<.bool.0, .bool.1, .bool.1>" --launch-skip 30 --launch-count 1 -f -o gpurun_out/ncu_${tag}_dx python tools/profile_minibatch.py 3 2 > gpurun_out/ncu_${tag}_dx.log 2>&1
+ncu $common --kernel-name "regex:gemm_tc256_kernel<.bool.1, .bool.1, .bool.1>" --launch-skip 32 --launch-count 1 -f -o gpurun_out/ncu_${tag}_dw python tools/profile_minibatch.py 3 2 > gpurun_out/ncu_${tag}_dw.log 2>&1
 ls -la gpurun_out/*.ncu-rep
