@@ -81,6 +81,14 @@ __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+// Programmatic dependent launch: the GEMMs are launched with programmatic stream serialization, so a CTA of the NEXT kernel may
+// be scheduled (on an SM the previous kernel no longer needs) and run its prologue -- barrier init, TMEM allocation, descriptor
+// fetch -- while the previous kernel's last wave is still computing.  launch_dependents lets our own successor do the same;
+// wait blocks until the predecessor grid has completed and its writes are visible: nothing before it touches global memory.
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
@@ -309,8 +317,8 @@ __device__ __forceinline__ void epilogue_rows(const TcEpi& e, const float* cs, i
 // (ncu r01b: 43 % of the kernel's lifetime, issue-bound, not memory-bound).  Here a lane owns 8 consecutive columns of each of the
 // warp's 16 rows: two LDS.128 from the staged tile, one 16-byte store per half plane, pointers advanced by the row strides, the
 // rows' activity-mask words prefetched before the loop, no bounds checks.
-__device__ __forceinline__ bool epilogue_fast256_ok(const TcEpi& e, int m0, int n0, bool H) {
-  if (e.accumulate || m0 + TC_BM > e.M || n0 + 256 > e.N) return false;
+__device__ __forceinline__ bool epilogue_fast_ok(const TcEpi& e, int m0, int n0, int bn, bool H) {
+  if (e.accumulate || m0 + TC_BM > e.M || n0 + bn > e.N) return false;
   if ((e.ldc & 3) || (reinterpret_cast<uintptr_t>(e.C) & 15)) return false;
   if (e.bias && (reinterpret_cast<uintptr_t>(e.bias) & 15)) return false;
   if (e.Chi && (!H || (e.ldp & 7) || (reinterpret_cast<uintptr_t>(e.Chi) & 15) || (reinterpret_cast<uintptr_t>(e.Clo) & 15))) return false;
@@ -318,19 +326,26 @@ __device__ __forceinline__ bool epilogue_fast256_ok(const TcEpi& e, int m0, int 
   return true;
 }
 
-template <bool H>
-__device__ __forceinline__ void epilogue_fast256(const TcEpi& e, const float* cs, int cs_ld, float* s_colsum, int row0, int m0, int n0, int lane) {
-  constexpr int NR = 16;
-  const int c8 = lane * 8, n = n0 + c8;
+// CPL = columns per lane (8: 256-wide tile, 4: 128-wide tile), NR = rows per warp (a multiple of 4)
+template <bool H, int CPL, int NR>
+__device__ __forceinline__ void epilogue_fast(const TcEpi& e, const float* cs, int cs_ld, float* s_colsum, int row0, int m0, int n0, int lane) {
+  static_assert(CPL == 4 || CPL == 8, "columns per lane");
+  constexpr int LPW = 32 / CPL;                        // lanes per 32-column activity word
+  const int c8 = lane * CPL, n = n0 + c8;
   const int64_t m = m0 + row0;
-  float bv[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  float bv[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) bv[j] = 0.0f;
   if (e.bias) {
-    const float4 b0 = *reinterpret_cast<const float4*>(e.bias + n), b1 = *reinterpret_cast<const float4*>(e.bias + n + 4);
-    bv[0] = b0.x; bv[1] = b0.y; bv[2] = b0.z; bv[3] = b0.w; bv[4] = b1.x; bv[5] = b1.y; bv[6] = b1.z; bv[7] = b1.w;
+#pragma unroll
+    for (int j = 0; j < CPL; j += 4) {
+      const float4 b0 = *reinterpret_cast<const float4*>(e.bias + n + j);
+      bv[j] = b0.x; bv[j + 1] = b0.y; bv[j + 2] = b0.z; bv[j + 3] = b0.w;
+    }
   }
   const float cscale = (H && e.Chi && e.c_scale) ? *e.c_scale : 1.0f;
   const bool use_bits = e.mask_mode == 1 && e.mask_bits != nullptr;
-  const int sh = 8 * (lane & 3);                       // this lane's byte of the 32-column activity word
+  const int sh = CPL * (lane & (LPW - 1));             // this lane's bits of the 32-column activity word
   // activity-mask words: 4 rows per group, the next group's words are in flight while the current one is processed
   const uint32_t* mb = use_bits ? e.mask_bits + m * e.ldmb + (n >> 5) : nullptr;
   uint32_t mw[4] = {0, 0, 0, 0}, mwn[4] = {0, 0, 0, 0};
@@ -344,76 +359,92 @@ __device__ __forceinline__ void epilogue_fast256(const TcEpi& e, const float* cs
   uint32_t* rb = e.relu_bits ? e.relu_bits + m * e.ldrb + (n >> 5) : nullptr;
   const float* mp = (e.mask_mode && !use_bits) ? e.mask_src + m * e.ldm + n : nullptr;
   const float* sp = cs + row0 * cs_ld + c8;
-  float cs8[8] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  float csum[CPL];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j) csum[j] = 0.0f;
   float amax = 0.0f;
 #pragma unroll 1
   for (int g = 0; g < NR / 4; ++g) {
-  if (use_bits && g + 1 < NR / 4) {
+    if (use_bits && g + 1 < NR / 4) {
 #pragma unroll
-    for (int r = 0; r < 4; ++r) mwn[r] = __ldg(mb + (int64_t)(4 * (g + 1) + r) * e.ldmb);
-  }
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const float4 t0 = *reinterpret_cast<const float4*>(sp), t1 = *reinterpret_cast<const float4*>(sp + 4);
-    float x[8] = {t0.x + bv[0], t0.y + bv[1], t0.z + bv[2], t0.w + bv[3], t1.x + bv[4], t1.y + bv[5], t1.z + bv[6], t1.w + bv[7]};
-    if (e.act == 1) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = fmaxf(x[j], 0.0f);
-    } else if (e.act == 2) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = tanhf(x[j]);
+      for (int r = 0; r < 4; ++r) mwn[r] = __ldg(mb + (int64_t)(4 * (g + 1) + r) * e.ldmb);
     }
-    if (rb) {
-      uint32_t w = 0;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) w |= (x[j] > 0.0f) ? (1u << j) : 0u;
-      w <<= sh;
-      w |= __shfl_xor_sync(0xffffffffu, w, 1); w |= __shfl_xor_sync(0xffffffffu, w, 2);
-      if ((lane & 3) == 0) *rb = w;
-      rb += e.ldrb;
-    }
-    if (use_bits) {
+    for (int r = 0; r < 4; ++r) {
+      float x[CPL];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = ((mw[r] >> (sh + j)) & 1u) ? x[j] : 0.0f;
-    } else if (mp) {
-      const float4 q0 = *reinterpret_cast<const float4*>(mp), q1 = *reinterpret_cast<const float4*>(mp + 4);
-      const float mv[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-      if (e.mask_mode == 1) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = (mv[j] > 0.0f) ? x[j] : 0.0f;
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] *= (1.0f - mv[j] * mv[j]);
+      for (int j = 0; j < CPL; j += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(sp + j);
+        x[j] = t.x + bv[j]; x[j + 1] = t.y + bv[j + 1]; x[j + 2] = t.z + bv[j + 2]; x[j + 3] = t.w + bv[j + 3];
       }
-      mp += e.ldm;
-    }
-    if (!e.skip_c) {
-      *reinterpret_cast<float4*>(cp) = make_float4(x[0], x[1], x[2], x[3]);
-      *reinterpret_cast<float4*>(cp + 4) = make_float4(x[4], x[5], x[6], x[7]);
-    }
+      if (e.act == 1) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { cs8[j] += x[j]; amax = fmaxf(amax, fabsf(x[j])); }
-    if (H && hp) {
-      uint32_t hw[4], lw[4];
+        for (int j = 0; j < CPL; ++j) x[j] = fmaxf(x[j], 0.0f);
+      } else if (e.act == 2) {
 #pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        __half h0, l0, h1, l1;
-        split_f16(x[j] * cscale, h0, l0); split_f16(x[j + 1] * cscale, h1, l1);
-        hw[j >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-        lw[j >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        for (int j = 0; j < CPL; ++j) x[j] = tanhf(x[j]);
       }
-      *reinterpret_cast<uint4*>(hp) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-      *reinterpret_cast<uint4*>(lp) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-      hp += e.ldp; lp += e.ldp;
-    }
-    cp += e.ldc; sp += cs_ld;
-  }
+      if (rb) {
+        uint32_t w = 0;
 #pragma unroll
-  for (int r = 0; r < 4; ++r) mw[r] = mwn[r];
+        for (int j = 0; j < CPL; ++j) w |= (x[j] > 0.0f) ? (1u << j) : 0u;
+        w <<= sh;
+#pragma unroll
+        for (int o = 1; o < LPW; o <<= 1) w |= __shfl_xor_sync(0xffffffffu, w, o);
+        if ((lane & (LPW - 1)) == 0) *rb = w;
+        rb += e.ldrb;
+      }
+      if (use_bits) {
+#pragma unroll
+        for (int j = 0; j < CPL; ++j) x[j] = ((mw[r] >> (sh + j)) & 1u) ? x[j] : 0.0f;
+      } else if (mp) {
+        float mv[CPL];
+#pragma unroll
+        for (int j = 0; j < CPL; j += 4) {
+          const float4 q = *reinterpret_cast<const float4*>(mp + j);
+          mv[j] = q.x; mv[j + 1] = q.y; mv[j + 2] = q.z; mv[j + 3] = q.w;
+        }
+        if (e.mask_mode == 1) {
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) x[j] = (mv[j] > 0.0f) ? x[j] : 0.0f;
+        } else {
+#pragma unroll
+          for (int j = 0; j < CPL; ++j) x[j] *= (1.0f - mv[j] * mv[j]);
+        }
+        mp += e.ldm;
+      }
+      if (!e.skip_c) {
+#pragma unroll
+        for (int j = 0; j < CPL; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(x[j], x[j + 1], x[j + 2], x[j + 3]);
+      }
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) { csum[j] += x[j]; amax = fmaxf(amax, fabsf(x[j])); }
+      if (H && hp) {
+        uint32_t hw[CPL / 2], lw[CPL / 2];
+#pragma unroll
+        for (int j = 0; j < CPL; j += 2) {
+          __half h0, l0, h1, l1;
+          split_f16(x[j] * cscale, h0, l0); split_f16(x[j + 1] * cscale, h1, l1);
+          hw[j >> 1] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+          lw[j >> 1] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+        }
+        if (CPL == 8) {
+          *reinterpret_cast<uint4*>(hp) = make_uint4(hw[0], hw[1], hw[CPL / 2 - 2], hw[CPL / 2 - 1]);
+          *reinterpret_cast<uint4*>(lp) = make_uint4(lw[0], lw[1], lw[CPL / 2 - 2], lw[CPL / 2 - 1]);
+        } else {
+          *reinterpret_cast<uint2*>(hp) = make_uint2(hw[0], hw[1]);
+          *reinterpret_cast<uint2*>(lp) = make_uint2(lw[0], lw[1]);
+        }
+        hp += e.ldp; lp += e.ldp;
+      }
+      cp += e.ldc; sp += cs_ld;
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) mw[r] = mwn[r];
   }
   if (e.colsum) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) atomicAdd(s_colsum + c8 + j, cs8[j]);
+    for (int j = 0; j < CPL; ++j) atomicAdd(s_colsum + c8 + j, csum[j]);
   }
   if (e.c_amax || (H && e.Chi && e.flag)) {
 #pragma unroll
@@ -484,6 +515,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   if (CL > 1) cluster_sync_all();        // peers' barriers are initialised before any multicast / remote arrive
+  pdl_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_corr = tmem_base + 2 * BN;
   const uint32_t crank = (CL > 1) ? cluster_rank() : 0u;
@@ -618,7 +650,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
     if (e.colsum) for (int c = (lg * 32 + lane); c < BN; c += 128) s_colsum[c] = 0.0f;
     asm volatile("bar.sync 1, 128;" ::: "memory");      // the 4 epilogue warps only
     // Phase 2: coalesced epilogue -- warp w owns rows [32w, 32w+32)
-    if (!(e.debug & 1)) epilogue_rows<H>(e, cs, CS_LD, s_colsum, lg * 32, 32, BN, m0, n0, lane);
+    if (!(e.debug & 1)) {
+      if (BN == 128 && epilogue_fast_ok(e, m0, n0, BN, H) && !(e.debug & 256)) epilogue_fast<H, 4, 32>(e, cs, CS_LD, s_colsum, lg * 32, m0, n0, lane);
+      else epilogue_rows<H>(e, cs, CS_LD, s_colsum, lg * 32, 32, BN, m0, n0, lane);
+    }
     if (e.colsum && !e.accumulate) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       for (int c = (lg * 32 + lane); c < BN; c += 128) if (n0 + c < e.N) atomicAdd(e.colsum + n0 + c, s_colsum[c]);
@@ -645,6 +680,45 @@ constexpr int TC256_THREADS = 384;       // WG0: warp 0 TMA, warp 1 MMA (+2 idle
 constexpr int TC256_BN = 256;
 constexpr int TC256_STAGES = 2;
 
+// One k-block of operand planes into stage kb % STAGES of the 128x256 kernel's ring (producer thread only); it is
+// called from two places (before and after the CTA-wide setup barrier).
+template <bool AMN, bool BMN, bool H>
+__device__ __forceinline__ void tc256_issue_kb(const CUtensorMap* tmAhi, const CUtensorMap* tmAlo, const CUtensorMap* tmBhi, const CUtensorMap* tmBlo,
+                                            uint8_t* smem, uint64_t* full, uint64_t* empty, int kb, int kb_begin, int m0, int n0) {
+  constexpr int BN = 256, STAGES = 2;
+  using SM = TcSmem<BN, STAGES>;
+  using F = TcFmt<H>;
+  const int s = kb % STAGES;
+  const uint32_t ph = (kb / STAGES) & 1;
+  mbar_wait(&empty[s], ph ^ 1);
+  mbar_expect_tx(&full[s], SM::STAGE_BYTES);
+  uint8_t* st = smem + s * SM::STAGE_BYTES;
+  const int k0 = (kb_begin + kb) * F::BK;
+  if (!AMN) {
+    tma_load_2d(st, tmAhi, &full[s], k0, m0);
+    tma_load_2d(st + SM::A_BYTES, tmAlo, &full[s], k0, m0);
+  } else {
+#pragma unroll
+    for (int b = 0; b < TC_BM / F::MN_BOX; ++b) {
+      tma_load_2d(st + b * F::MN_BOX_BYTES, tmAhi, &full[s], m0 + b * F::MN_BOX, k0);
+      tma_load_2d(st + SM::A_BYTES + b * F::MN_BOX_BYTES, tmAlo, &full[s], m0 + b * F::MN_BOX, k0);
+    }
+  }
+  if (!BMN) {        // the B maps have 128-row boxes: two per plane
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      tma_load_2d(st + 2 * SM::A_BYTES + h * 16384, tmBhi, &full[s], k0, n0 + h * 128);
+      tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES + h * 16384, tmBlo, &full[s], k0, n0 + h * 128);
+    }
+  } else {
+#pragma unroll
+    for (int b = 0; b < BN / F::MN_BOX; ++b) {
+      tma_load_2d(st + 2 * SM::A_BYTES + b * F::MN_BOX_BYTES, tmBhi, &full[s], n0 + b * F::MN_BOX, k0);
+      tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES + b * F::MN_BOX_BYTES, tmBlo, &full[s], n0 + b * F::MN_BOX, k0);
+    }
+  }
+}
+
 template <bool AMN, bool BMN, bool H>
 __global__ void __launch_bounds__(TC256_THREADS, 1)
 gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
@@ -667,10 +741,21 @@ gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
   const int kb_begin = blockIdx.z * e.kb_per_split;
   const int nkb = min(e.kb_per_split, e.kb_total - kb_begin);
 
+  auto issue_kb = [&](int kb) {
+    tc256_issue_kb<AMN, BMN, H>(&tmAhi, &tmAlo, &tmBhi, &tmBlo, smem, full, empty, kb, kb_begin, m0, n0);
+  };
+  const int kb_early = min(STAGES, nkb);      // k-blocks whose loads are issued before the CTA-wide setup barrier
   if (threadIdx.x == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAhi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAlo)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBhi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBlo)) : "memory");
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(main_full, 1); mbar_init(main_empty, 8); mbar_init(corr_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // the first stages' loads fly while TMEM is allocated and the CTA synchronises (they only need the producer's own barriers)
+    pdl_sync();
+    for (int kb = 0; kb < kb_early; ++kb) issue_kb(kb);
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
@@ -679,43 +764,14 @@ gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_corr = tmem_base + BN;
 
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0 && lane == 0) {
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty[s], ph ^ 1);
-        mbar_expect_tx(&full[s], SM::STAGE_BYTES);
-        uint8_t* st = smem + s * SM::STAGE_BYTES;
-        const int k0 = (kb_begin + kb) * F::BK;
-        if (!AMN) {
-          tma_load_2d(st, &tmAhi, &full[s], k0, m0);
-          tma_load_2d(st + SM::A_BYTES, &tmAlo, &full[s], k0, m0);
-        } else {
-#pragma unroll
-          for (int b = 0; b < TC_BM / F::MN_BOX; ++b) {
-            tma_load_2d(st + b * F::MN_BOX_BYTES, &tmAhi, &full[s], m0 + b * F::MN_BOX, k0);
-            tma_load_2d(st + SM::A_BYTES + b * F::MN_BOX_BYTES, &tmAlo, &full[s], m0 + b * F::MN_BOX, k0);
-          }
-        }
-        if (!BMN) {        // the B maps have 128-row boxes: two per plane
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            tma_load_2d(st + 2 * SM::A_BYTES + h * 16384, &tmBhi, &full[s], k0, n0 + h * 128);
-            tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES + h * 16384, &tmBlo, &full[s], k0, n0 + h * 128);
-          }
-        } else {
-#pragma unroll
-          for (int b = 0; b < BN / F::MN_BOX; ++b) {
-            tma_load_2d(st + 2 * SM::A_BYTES + b * F::MN_BOX_BYTES, &tmBhi, &full[s], n0 + b * F::MN_BOX, k0);
-            tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES + b * F::MN_BOX_BYTES, &tmBlo, &full[s], n0 + b * F::MN_BOX, k0);
-          }
-        }
-      }
+      for (int kb = kb_early; kb < nkb; ++kb) issue_kb(kb);
     } else if (warp == 1 && lane == 0) {
       const uint32_t idesc = tc_idesc<H>(AMN, BMN, BN);
       auto adesc = [](uint32_t base, int k) { return tc_desc<H, AMN>(base, k); };
@@ -789,7 +845,7 @@ gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
     if (e.colsum) s_colsum[et] = 0.0f;
     asm volatile("bar.sync 1, 256;" ::: "memory");      // the 8 epilogue warps only
     if (!(e.debug & 1)) {
-      if (epilogue_fast256_ok(e, m0, n0, H) && !(e.debug & 256)) epilogue_fast256<H>(e, cs, CS_LD, s_colsum, (warp - 4) * 16, m0, n0, lane);
+      if (epilogue_fast_ok(e, m0, n0, BN, H) && !(e.debug & 256)) epilogue_fast<H, 8, 16>(e, cs, CS_LD, s_colsum, (warp - 4) * 16, m0, n0, lane);
       else epilogue_rows<H>(e, cs, CS_LD, s_colsum, (warp - 4) * 16, 16, BN, m0, n0, lane);
     }
     if (e.colsum && !e.accumulate) {
@@ -1050,6 +1106,12 @@ static void prof_mark(cudaStream_t st) {
   cudaEventRecord(g_prof.ev[g_prof.used++], st);
 }
 
+static int tc_pdl() {   // env ASE_TC_PDL=0 launches the GEMMs fully stream-serialised
+  static int v = -1;
+  if (v < 0) { const char* d = getenv("ASE_TC_PDL"); v = d ? (atoi(d) != 0) : 1; }
+  return v;
+}
+
 template <int BN, int STAGES, bool AMN, bool BMN, int CL, bool H>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcEpi& e,
                      int splits, cudaStream_t st) {
@@ -1065,10 +1127,12 @@ static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtenso
   if (prof) prof_mark(st);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = tc_pdl();
+  cfg.attrs = attr; cfg.numAttrs = 2;
   ASE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, AMN, BMN, CL, H>, ah, al, bh, bl, e));
   if (prof) { prof_mark(st); g_prof.flops += 2.0 * (double)e.M * (double)e.N * (double)e.K; }
   ASE_LAUNCH_OK();
@@ -1099,7 +1163,13 @@ static int launch_tc256(const CUtensorMap& ah, const CUtensorMap& al, const CUte
   dim3 grid(ceil_div(e.N, TC256_BN), ceil_div(e.M, TC_BM), splits);
   const bool prof = g_prof.on;
   if (prof) prof_mark(st);
-  gemm_tc256_kernel<AMN, BMN, H><<<grid, TC256_THREADS, SM::TOTAL, st>>>(ah, al, bh, bl, e);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(TC256_THREADS); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = tc_pdl();
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  ASE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc256_kernel<AMN, BMN, H>, ah, al, bh, bl, e));
   if (prof) { prof_mark(st); g_prof.flops += 2.0 * (double)e.M * (double)e.N * (double)e.K; }
   ASE_LAUNCH_OK();
   return ASE_OK;

@@ -217,6 +217,23 @@ colsum_kernel(const float* __restrict__ dz, int64_t ld, int rows, int cols, int 
   atomicAdd(&db[c], s);
 }
 
+// Narrow matrices (head gradients: 31 / 1 / 64 columns, contiguous rows): the column of a thread is fixed by making the grid stride a
+// multiple of cols, every thread streams the flat array (fully coalesced), per-column partial sums meet in shared memory.
+__global__ void __launch_bounds__(256)
+colsum_narrow_kernel(const float* __restrict__ dz, int64_t total, int cols, int64_t stride, float* __restrict__ db) {
+  __shared__ float sm[64];
+  if (threadIdx.x < 64) sm[threadIdx.x] = 0.0f;
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < stride) {
+    float s = 0.0f;
+    for (int64_t i = t; i < total; i += stride) s += dz[i];
+    atomicAdd(&sm[(int)(t % cols)], s);
+  }
+  __syncthreads();
+  if (threadIdx.x < cols) atomicAdd(&db[threadIdx.x], sm[threadIdx.x]);
+}
+
 // grads += coef * w ; acc[idx] += sum w^2   (logit-weight regulariser and disc weight decay, amp_agent.py:448-466)
 __global__ void __launch_bounds__(256)
 weight_reg_kernel(const float* __restrict__ w, float* __restrict__ g, int64_t n, float coef, double* __restrict__ acc, int idx, int idx2) {
@@ -305,6 +322,13 @@ int launch_gp_scale(float* g, int64_t total, float scale, double* acc, cudaStrea
   ASE_LAUNCH_OK(); return ASE_OK;
 }
 int launch_colsum(const float* dz, int64_t ld, int rows, int cols, float* db, cudaStream_t st) {
+  if (cols <= 64 && ld == cols) {
+    const int64_t total = (int64_t)rows * cols;
+    const int blocks = (int)imin64((total + 256 * 8 - 1) / (256 * 8), 148 * 4);
+    const int64_t stride = (int64_t)blocks * 256 / cols * cols;        // a multiple of cols: thread t always sees column t % cols
+    colsum_narrow_kernel<<<blocks, 256, 0, st>>>(dz, total, cols, stride, db);
+    ASE_LAUNCH_OK(); return ASE_OK;
+  }
   const int rpb = 256;
   dim3 grid(ceil_div(cols, 128), ceil_div(rows, rpb));
   colsum_kernel<<<grid, 128, 0, st>>>(dz, ld, rows, cols, rpb, db);

@@ -31,36 +31,51 @@ rms_colstats_kernel(RmsBatchList bl, int cols, int chunks, double2* __restrict__
   partial[((int64_t)batch * chunks + chunk) * cols + col] = make_double2(s, ss);
 }
 
-// One thread per column: reduce the chunk partials, merge batch after batch, emit fp32 mean / std per batch.
-__global__ void rms_finalize_kernel(const double2* __restrict__ partial, int cols, int chunks, int nbatch, int rows,
-                                    double* __restrict__ mean, double* __restrict__ var, const double* __restrict__ count,
-                                    float eps, float* __restrict__ meanf, float* __restrict__ stdf, int update) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= cols) return;
-  double m = mean[col], v = var[col], c = count[0];
+// Reduce the chunk partials, merge batch after batch, emit fp32 mean / std per batch.  Block = 32 columns x 8 chunk lanes: the
+// chunk sums of a column are split over 8 threads (coalesced along the columns) and meet in shared memory; lane 0 does the merge.
+__global__ void __launch_bounds__(256)
+rms_finalize_kernel(const double2* __restrict__ partial, int cols, int chunks, int nbatch, int rows,
+                    double* __restrict__ mean, double* __restrict__ var, const double* __restrict__ count,
+                    float eps, float* __restrict__ meanf, float* __restrict__ stdf, int update) {
+  __shared__ double ssum[8][33], ssq[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  const bool ok = col < cols;
+  double m = 0.0, v = 0.0, c = 0.0;
+  if (ok && ty == 0) { m = mean[col]; v = var[col]; c = count[0]; }
   for (int b = 0; b < nbatch; ++b) {
     if (update) {
       double s = 0.0, ss = 0.0;
-      for (int k = 0; k < chunks; ++k) {
+      if (ok) for (int k = ty; k < chunks; k += 8) {
         const double2 p = partial[((int64_t)b * chunks + k) * cols + col];
         s += p.x; ss += p.y;
       }
-      const double n = (double)rows;
-      // the reference's batch moments are fp32 tensors (input.mean(0), input.var(0)): round like it does
-      const double bm = (double)(float)(s / n);
-      double bvar = (ss - s * s / n) / (n - 1.0);
-      if (bvar < 0.0) bvar = 0.0;
-      bvar = (double)(float)bvar;
-      const double delta = bm - m, tot = c + n;
-      const double m2 = v * c + bvar * n + delta * delta * c * n / tot;
-      m = m + delta * n / tot;
-      v = m2 / tot;
-      c = tot;
+      ssum[ty][tx] = s; ssq[ty][tx] = ss;
+      __syncthreads();
+      if (ok && ty == 0) {
+        s = 0.0; ss = 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s += ssum[k][tx]; ss += ssq[k][tx]; }
+        const double n = (double)rows;
+        // the reference's batch moments are fp32 tensors (input.mean(0), input.var(0)): round like it does
+        const double bm = (double)(float)(s / n);
+        double bvar = (ss - s * s / n) / (n - 1.0);
+        if (bvar < 0.0) bvar = 0.0;
+        bvar = (double)(float)bvar;
+        const double delta = bm - m, tot = c + n;
+        const double m2 = v * c + bvar * n + delta * delta * c * n / tot;
+        m = m + delta * n / tot;
+        v = m2 / tot;
+        c = tot;
+      }
+      __syncthreads();
     }
-    meanf[b * cols + col] = (float)m;
-    stdf[b * cols + col] = sqrtf((float)v + eps);
+    if (ok && ty == 0) {
+      meanf[b * cols + col] = (float)m;
+      stdf[b * cols + col] = sqrtf((float)v + eps);
+    }
   }
-  if (update) { mean[col] = m; var[col] = v; }
+  if (update && ok && ty == 0) { mean[col] = m; var[col] = v; }
 }
 
 __global__ void rms_count_add_kernel(double* count, double inc) { count[0] += inc; }
@@ -74,20 +89,26 @@ __device__ __forceinline__ void split_tf32_rms(float x, float& hi, float& lo) { 
   lo = __uint_as_float(l);
 }
 
-// y = clamp((x-mean)/std, -5, 5) written to up to 3 destinations (unnorm: std*clamp(x,+-5)+mean)
-__global__ void __launch_bounds__(256)
+// y = clamp((x-mean)/std, -5, 5) written to up to 3 destinations (unnorm: std*clamp(x,+-5)+mean).
+// Threads map to columns (coalesced rows, the column's mean / std loaded once), blockIdx.y walks chunks of rows.
+constexpr int NORM_ROWS_PER_BLOCK = 32;
+__global__ void __launch_bounds__(128)
 rms_normalize_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols,
                      const float* __restrict__ meanf, const float* __restrict__ stdf, int unnorm, RmsDst dst) {
-  const int64_t total = (int64_t)rows * cols;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= cols) return;
+  const float mu = meanf[c], sd = stdf[c];
+  const bool planes = dst.hi[0] || dst.hi[1] || dst.hi[2];
+  const int r0 = blockIdx.y * NORM_ROWS_PER_BLOCK, r1 = min(rows, r0 + NORM_ROWS_PER_BLOCK);
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r) {
     const float v = x[(int64_t)r * ldx + c];
     float y;
-    if (unnorm) y = stdf[c] * fminf(fmaxf(v, -5.0f), 5.0f) + meanf[c];
-    else y = fminf(fmaxf((v - meanf[c]) / stdf[c], -5.0f), 5.0f);
+    if (unnorm) y = sd * fminf(fmaxf(v, -5.0f), 5.0f) + mu;
+    else y = fminf(fmaxf((v - mu) / sd, -5.0f), 5.0f);
     float h = 0.0f, l = 0.0f;
     __half hh = __float2half_rn(0.0f), hl = hh;
-    if (dst.hi[0] || dst.hi[1] || dst.hi[2]) {
+    if (planes) {
       if (!dst.half) split_tf32_rms(y, h, l);
       else { const float ys = y * dst.pscale; hh = __float2half_rn(ys); hl = __float2half_rn(ys - __half2float(hh)); }
     }
@@ -146,7 +167,7 @@ int rms_update_batches(const RmsBatchList& bl, int nbatch, int cols, double* mea
     rms_colstats_kernel<<<grid, RMS_COLS_PER_BLOCK, 0, st>>>(bl, cols, chunks, partial);
     ASE_LAUNCH_OK();
   }
-  rms_finalize_kernel<<<ceil_div(cols, 128), 128, 0, st>>>(partial, cols, chunks, nbatch, rows, mean, var, count, eps, meanf, stdf, update);
+  rms_finalize_kernel<<<ceil_div(cols, 32), 256, 0, st>>>(partial, cols, chunks, nbatch, rows, mean, var, count, eps, meanf, stdf, update);
   ASE_LAUNCH_OK();
   if (update) {
     rms_count_add_kernel<<<1, 1, 0, st>>>(count, (double)rows * nbatch);
@@ -158,9 +179,9 @@ int rms_update_batches(const RmsBatchList& bl, int nbatch, int cols, double* mea
 
 int rms_normalize(const float* x, int64_t ldx, int rows, int cols, const float* meanf, const float* stdf, int unnorm,
                   const RmsDst& dst, cudaStream_t st) {
-  const int64_t total = (int64_t)rows * cols;
-  const int blocks = (int)imin64((total + 255) / 256, 148 * 16);
-  rms_normalize_kernel<<<blocks, 256, 0, st>>>(x, ldx, rows, cols, meanf, stdf, unnorm, dst);
+  if (rows <= 0 || cols <= 0) return ASE_OK;
+  dim3 grid(ceil_div(cols, 128), ceil_div(rows, NORM_ROWS_PER_BLOCK));
+  rms_normalize_kernel<<<grid, 128, 0, st>>>(x, ldx, rows, cols, meanf, stdf, unnorm, dst);
   ASE_LAUNCH_OK();
   return ASE_OK;
 }
