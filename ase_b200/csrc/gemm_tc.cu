@@ -947,6 +947,59 @@ tc_prep_h_kernel(const float* __restrict__ src, int64_t ld, int rows, int cols, 
   }
 }
 
+// FP16 format: all weight tensors of the learner in ONE launch (they are re-split after every optimizer step; one launch
+// per tensor cost ~7 us each for a few MB of work).  blockIdx.y = tensor, blockIdx.x = slice of it.
+__global__ void __launch_bounds__(256)
+tc_amax_batch_kernel(TcPrepBatch b, unsigned* __restrict__ amax) {
+  const TcPrepItem it = b.item[blockIdx.y];
+  const int64_t total = (int64_t)it.rows * it.cols;
+  float m = 0.0f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) m = fmaxf(m, fabsf(it.src[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0f) atomicMax(amax + it.site, __float_as_uint(m));
+}
+__global__ void __launch_bounds__(256)
+tc_prep_h_batch_kernel(TcPrepBatch b, unsigned* __restrict__ amax, float* __restrict__ scale, float* __restrict__ bscale, int exact,
+                       unsigned* __restrict__ flag) {
+  const TcPrepItem it = b.item[blockIdx.y];
+  float s;
+  if (exact) {
+    s = scale_from_amax(__uint_as_float(amax[it.site]), TOP_SITE);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { scale[2 * it.site] = s; scale[2 * it.site + 1] = 1.0f / s; }
+  } else s = scale[2 * it.site];
+  if (blockIdx.x == 0 && threadIdx.x == 0) { bscale[2 * it.buf] = s; bscale[2 * it.buf + 1] = (s != 0.0f) ? 1.0f / s : 0.0f; }
+  __half* hi = (__half*)it.hi; __half* lo = (__half*)it.lo;
+  const int c4n = it.ldp >> 2;
+  const int64_t total = (int64_t)it.rows * c4n;
+  const bool vec = (it.cols & 3) == 0;         // weight rows are contiguous (ld = cols) and the arena offsets 128-byte aligned
+  float m = 0.0f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / c4n), c = (int)(i - (int64_t)r * c4n) * 4;
+    float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    const float* sp = it.src + (int64_t)r * it.cols + c;
+    if (vec && c + 4 <= it.cols) { const float4 t = *reinterpret_cast<const float4*>(sp); x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w; }
+    else for (int j = 0; j < 4; ++j) if (c + j < it.cols) x[j] = sp[j];
+    __half h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { m = fmaxf(m, fabsf(x[j])); split_f16(x[j] * s, h[j], l[j]); }
+    uint2 hv, lv;
+    hv.x = (uint32_t)__half_as_ushort(h[0]) | ((uint32_t)__half_as_ushort(h[1]) << 16); hv.y = (uint32_t)__half_as_ushort(h[2]) | ((uint32_t)__half_as_ushort(h[3]) << 16);
+    lv.x = (uint32_t)__half_as_ushort(l[0]) | ((uint32_t)__half_as_ushort(l[1]) << 16); lv.y = (uint32_t)__half_as_ushort(l[2]) | ((uint32_t)__half_as_ushort(l[3]) << 16);
+    *reinterpret_cast<uint2*>(hi + (int64_t)r * it.ldp + c) = hv;
+    *reinterpret_cast<uint2*>(lo + (int64_t)r * it.ldp + c) = lv;
+  }
+  if (!exact) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0f) {
+      atomicMax(amax + it.site, __float_as_uint(m));
+      if (!(m * s <= 60000.0f)) atomicOr(flag, 1u);
+      if (s == 0.0f) atomicOr(flag, 2u);
+    }
+  }
+}
+
 // FP16 format, start of every top-level call: fold the maxima tracked during the previous call into the sites' scales (the
 // prediction for this call), check that the previous prediction did not lose precision, and clear the maxima.
 __global__ void __launch_bounds__(256)
@@ -1252,6 +1305,36 @@ int PlaneRegistry::begin_call(cudaStream_t st, int base) {
   return ASE_OK;
 }
 
+// (Re)split every listed weight tensor [rows, cols] (contiguous) into its registered planes: one launch (two on the first call
+// after the parameters were announced: exact maxima first).  Sites are fixed per tensor (WEIGHT_SITE0 + i).
+int PlaneRegistry::prep_weights(const float* const* src, const int* rows, const int* cols, int count, cudaStream_t st) {
+  if (!f16 || count <= 0) return ASE_OK;
+  TcPrepBatch batch; int nb = 0; bool all_known = true;
+  for (int i = 0; i < count && nb < TcPrepBatch::MAX; ++i) {
+    PlaneBuf* x = find(src[i]);
+    if (!x || x->base != src[i]) continue;
+    const int64_t ldp = (cols[i] + 7) / 8 * 8;
+    if ((int64_t)rows[i] * ldp > 2 * x->plane_capacity) continue;
+    const int site = WEIGHT_SITE0 + i;
+    if (site >= SITES) break;
+    TcPrepItem& it = batch.item[nb++];
+    it.src = src[i]; it.hi = x->hi; it.lo = x->lo; it.rows = rows[i]; it.cols = cols[i]; it.ldp = (int)ldp; it.site = site; it.buf = (int)(x - b);
+    x->ld = cols[i]; x->rows = rows[i]; x->cols = cols[i]; x->ldp = ldp; x->valid = true; x->is_static = false; x->amax_site = -1; x->fp32_stale = false;
+    x->scale_ptr = bscale + 2 * it.buf;
+    all_known = all_known && known[site];
+    touched[site] = true;
+  }
+  if (nb == 0) return ASE_OK;
+  dim3 grid(16, nb);
+  if (!all_known) {
+    tc_amax_batch_kernel<<<grid, 256, 0, st>>>(batch, amax);
+    ASE_LAUNCH_OK();
+  }
+  tc_prep_h_batch_kernel<<<grid, 256, 0, st>>>(batch, amax, scale, bscale, all_known ? 0 : 1, flag);
+  ASE_LAUNCH_OK();
+  return ASE_OK;
+}
+
 struct OpView { const void* hi; const void* lo; int64_t ldp; bool ok; const float* scale; };
 
 // View [nat_rows, nat_cols] (ld) at `ptr` as planes.  Geometry of a registered buffer is whatever its last full
@@ -1440,7 +1523,7 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   if (H) {
     if (use256) return launch_tc256_major<true>(amn, bmn, ah, al, bh, bl, e, splits, st);
     if (BN == 128) return launch_tc_major<128, 3, 1, true>(amn, bmn, ah, al, bh, bl, e, splits, st);
-    return launch_tc_major<64, 4, 1, true>(amn, bmn, ah, al, bh, bl, e, splits, st);
+    return launch_tc_major<64, 2, 1, true>(amn, bmn, ah, al, bh, bl, e, splits, st);      // 2 stages = 97 KB: two CTAs per SM hide each other's latencies
   }
   if (use256) return launch_tc256_major<false>(amn, bmn, ah, al, bh, bl, e, splits, st);
   if (BN == 128 && CL == 4) return launch_tc_major<128, 3, 4, false>(amn, bmn, ah, al, bh, bl, e, splits, st);

@@ -40,8 +40,11 @@ struct PlaneBuf {
 // (or from the max the producing GEMM tracked); afterwards the scale predicted from the previous call's max is used, which lets the
 // producing GEMM's epilogue write the planes itself.  The prediction leaves 2^9 of headroom above and 2^12 below; leaving that
 // window between two consecutive calls raises a sticky device flag (ase_learner_plane_status), never a silent wrong result.
+struct TcPrepItem { const float* src; void* hi; void* lo; int rows, cols, ldp, site, buf; };
+struct TcPrepBatch { static constexpr int MAX = 40; TcPrepItem item[MAX]; };
 struct PlaneRegistry {
   static constexpr int MAX = 160;
+  static constexpr int WEIGHT_SITE0 = 960;      // fixed scale sites of the weight tensors (prep_weights)
   static constexpr int SITES = 1024;
   static constexpr float STATIC_SCALE = 64.0f;  // bounded writers (normalised observations clamp at 5, tanh outputs, unit latents)
   PlaneBuf b[MAX]; int n = 0;
@@ -59,6 +62,7 @@ struct PlaneRegistry {
     amax = (unsigned*)mem; scale = (float*)((char*)mem + SITES * 4); bscale = scale + 2 * SITES; static_scale = bscale + 2 * MAX; flag = (unsigned*)(static_scale + 2);
     for (int i = 0; i < SITES; ++i) known[i] = touched[i] = false;
   }
+  int prep_weights(const float* const* src, const int* rows, const int* cols, int count, cudaStream_t st);
   int begin_call(cudaStream_t st, int base);    // start of one stream-ordered sequence of GEMMs (calc_gradients / eval_*)
   int site(int which) const { const int s = call_base + 3 * gemm_index + which; return s < SITES ? s : -1; }
   bool reset_pending = false;     // forget_sites(): the device slots are cleared at the next begin_call (stream-ordered)

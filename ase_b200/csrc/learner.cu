@@ -94,6 +94,7 @@ struct AseLearner {
   float* w_planes; int64_t w_plane_floats;         // carved region for weight planes
   const float* reg_params;                         // parameter arena the weight entries currently point at
   void* reg_dev;                                   // FP16 format: device amax / scale slots of the registry
+  bool weights_split;                              // FP16 format: the weight planes are current (one batched split per optimizer step)
 };
 
 namespace ase {
@@ -236,6 +237,22 @@ static void register_planes(AseLearner& L, const float* params) {
     woff += cap;
   }
   L.reg_params = params;
+  L.weights_split = false;
+}
+
+// FP16 format: (re)split all weight matrices in one launch if the parameters changed since the last split.
+// (desc[] alternates weight, bias per layer: even entries are the GEMM operands)
+static int split_weights(AseLearner& L, const float* params, cudaStream_t st) {
+  if (!L.reg || !L.reg->f16 || L.weights_split) return ASE_OK;
+  const float* src[TcPrepBatch::MAX]; int rows[TcPrepBatch::MAX], cols[TcPrepBatch::MAX]; int n = 0;
+  for (int i = 0; i < L.net.n_tensors && n < TcPrepBatch::MAX; i += 2) {
+    const TensorDesc& d = L.net.desc[i];
+    src[n] = params + d.off; rows[n] = d.rows; cols[n] = d.cols; ++n;
+  }
+  int rc = L.reg->prep_weights(src, rows, cols, n, st);
+  if (rc) return rc;
+  L.weights_split = true;
+  return ASE_OK;
 }
 
 static int init_learner(AseLearner& L, const AseLearnerConfig& cfg) {
@@ -424,6 +441,7 @@ extern "C" void ase_learner_destroy(AseLearner* l) { if (l) { delete l->reg; del
 extern "C" int ase_learner_params_changed(AseLearner* l) {
   ASE_CHECK_ARG(l != nullptr, "ase_learner_params_changed: null learner");
   if (l->reg && l->reg_params) l->reg->invalidate_range(l->reg_params, l->reg_params + l->net.arena);
+  l->weights_split = false;
   if (l->reg) l->reg->forget_sites();     // new weights: the FP16 format recalibrates every scale exactly on the next call
   return ASE_OK;
 }
@@ -453,7 +471,7 @@ extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState*
   ASE_CHECK_ARG(out->scalars, "calc_gradients: scalars output");
   const int B = L.B, Ba = L.Ba, Ra = L.Ra, Z = c.latent_dim, A = c.act_dim;
   register_planes(L, s->params);
-  if (L.reg) RC(L.reg->begin_call(st, 0));
+  if (L.reg) { RC(L.reg->begin_call(st, 0)); RC(split_weights(L, s->params, st)); }
   G g{L, st, s->params, s->grads};
 
   ASE_CUDA_OK(cudaMemsetAsync(L.acc, 0, ACC_COUNT * sizeof(double), st));
@@ -633,6 +651,7 @@ extern "C" int ase_learner_adam_step(AseLearner* lp, const AseLearnerState* s, i
   ASE_CHECK_ARG(lp && s && s->params && s->grads && s->exp_avg && s->exp_avg_sq && step >= 1, "adam_step: bad argument");
   const AseLearnerConfig& c = lp->cfg;
   if (lp->reg) lp->reg->invalidate_range(s->params, s->params + lp->net.arena);   // weight planes are stale after the update
+  lp->weights_split = false;
   return launch_adam(s->params, s->grads, s->exp_avg, s->exp_avg_sq, lp->net.arena, grad_scale, c.beta1, c.beta2, c.lr, c.adam_eps, step,
                      (cudaStream_t)stream);
 }
@@ -645,7 +664,7 @@ extern "C" int ase_learner_eval_actor_critic(AseLearner* lp, const AseLearnerSta
   ASE_CHECK_ARG(!L.ase || latents, "eval_actor_critic: latents required");
   cudaStream_t st = (cudaStream_t)stream;
   register_planes(L, s->params);
-  if (L.reg) RC(L.reg->begin_call(st, 600));
+  if (L.reg) { RC(L.reg->begin_call(st, 600)); RC(split_weights(L, s->params, st)); }
   G g{L, st, s->params, s->grads};
   RC(rms_apply(obs, c.obs_dim, rows, c.obs_dim, s->obs_mean, s->obs_var, c.rms_eps, 0, L.Xa, L.ldx, st));
   g.inval(L.Xa); g.inval(L.Xc); g.inval(L.Zc);
@@ -669,7 +688,7 @@ extern "C" int ase_learner_eval_disc_enc(AseLearner* lp, const AseLearnerState* 
   ASE_CHECK_ARG(!enc_pred || L.ase, "eval_disc_enc: enc_pred needs an ASE learner");
   cudaStream_t st = (cudaStream_t)stream;
   register_planes(L, s->params);
-  if (L.reg) RC(L.reg->begin_call(st, 800));
+  if (L.reg) { RC(L.reg->begin_call(st, 800)); RC(split_weights(L, s->params, st)); }
   G g{L, st, s->params, s->grads};
   RC(rms_apply(amp_obs, c.amp_dim, rows, c.amp_dim, s->amp_mean, s->amp_var, c.rms_eps, 0, L.Xd, L.amp_ld, st));
   g.inval(L.Xd);

@@ -91,7 +91,7 @@ __device__ __forceinline__ void split_tf32_rms(float x, float& hi, float& lo) { 
 
 // y = clamp((x-mean)/std, -5, 5) written to up to 3 destinations (unnorm: std*clamp(x,+-5)+mean).
 // Threads map to columns (coalesced rows, the column's mean / std loaded once), blockIdx.y walks chunks of rows.
-constexpr int NORM_ROWS_PER_BLOCK = 32;
+constexpr int NORM_ROWS_PER_BLOCK = 8;       // few rows per thread, all loads in flight at once: the pass is latency-bound otherwise
 __global__ void __launch_bounds__(128)
 rms_normalize_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols,
                      const float* __restrict__ meanf, const float* __restrict__ stdf, int unnorm, RmsDst dst) {
@@ -99,10 +99,15 @@ rms_normalize_kernel(const float* __restrict__ x, int64_t ldx, int rows, int col
   if (c >= cols) return;
   const float mu = meanf[c], sd = stdf[c];
   const bool planes = dst.hi[0] || dst.hi[1] || dst.hi[2];
-  const int r0 = blockIdx.y * NORM_ROWS_PER_BLOCK, r1 = min(rows, r0 + NORM_ROWS_PER_BLOCK);
-#pragma unroll 4
-  for (int r = r0; r < r1; ++r) {
-    const float v = x[(int64_t)r * ldx + c];
+  const int r0 = blockIdx.y * NORM_ROWS_PER_BLOCK;
+  float xv[NORM_ROWS_PER_BLOCK];
+#pragma unroll
+  for (int i = 0; i < NORM_ROWS_PER_BLOCK; ++i) xv[i] = (r0 + i < rows) ? x[(int64_t)(r0 + i) * ldx + c] : 0.0f;
+#pragma unroll
+  for (int i = 0; i < NORM_ROWS_PER_BLOCK; ++i) {
+    const int r = r0 + i;
+    if (r >= rows) break;
+    const float v = xv[i];
     float y;
     if (unnorm) y = sd * fminf(fmaxf(v, -5.0f), 5.0f) + mu;
     else y = fminf(fmaxf((v - mu) / sd, -5.0f), 5.0f);
