@@ -146,6 +146,37 @@ def test_tc_relu_activity_bits_roundtrip(tc, M, N, K):
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize('a_trans,b_trans', [(False, False), (False, True), (True, False), (True, True)])
+def test_tc_persistent_many_tiles_per_cta(a_trans, b_trans):
+    """ASE_TC_PERSIST=1 routes backend 2's non-split GEMMs to the persistent ping-pong kernel (kept as an opt-in experiment: correct,
+    but slower than the 128x256 kernel on B200): with more than 148 output tiles every CTA walks several tiles, alternating between
+    its two TMEM accumulator sets / drain warp sets and handing the staging tile back and forth.  Odd and even k-block counts per
+    tile exercise both parities of every barrier across tile boundaries."""
+    import os
+    from ase_b200 import ops
+    os.environ['ASE_TC_PERSIST'] = '1'
+    try:
+        _persistent_cases(a_trans, b_trans, ops)
+    finally:
+        os.environ['ASE_TC_PERSIST'] = '0'
+
+
+def _persistent_cases(a_trans, b_trans, ops):
+    _run(8192, 1024, 192, a_trans, b_trans, 2, bias=True, act=1, tol=1e-5)       # 512 tiles, 3 k-blocks each
+    _run(4096, 1024, 64, a_trans, b_trans, 2, tol=1e-5)                           # 256 tiles, 1 k-block each
+    _run(5000, 900, 256, a_trans, b_trans, 2, mask_mode=1, tol=1e-5)              # 320 tiles, ragged M and N tails, 4 k-blocks
+    _run(3000, 1400, 130, a_trans, b_trans, 2, lda_pad=3, tol=1e-5)               # 264 tiles, ragged everything, unaligned ld
+    g = torch.Generator().manual_seed(9)
+    A = torch.randn(6016, 320, generator=g).cuda(); B = torch.randn(768, 320, generator=g).cuda()
+    if a_trans or b_trans:
+        return
+    cs = torch.zeros(768, device='cuda')
+    C = ops.gemm(A, B, backend=2, colsum_out=cs)                                    # 282 tiles + fused column sums
+    ref = A.double() @ B.double().t()
+    assert float((C.double() - ref).abs().max() / ref.abs().max()) < 1e-5
+    assert float((cs.double() - ref.sum(0)).abs().max() / ref.sum(0).abs().max()) < 1e-5
+
+
 def test_tc_fp16_planes_dynamic_range():
     """Backend 2 scales every tensor by a power of two before the FP16 hi/lo split: gradient-sized (1e-9) and large (1e+6)
     operands, and a tensor whose entries span 7 decades, must come out as accurately as O(1) ones."""
