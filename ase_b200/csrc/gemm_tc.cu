@@ -1,19 +1,23 @@
-// tcgen05 3xTF32 GEMM for sm_100a: fp32-accurate products on the 5th-gen tensor cores.
+// tcgen05 GEMM for sm_100a with fp32-class accuracy: three tensor-core MMAs per product on hi/lo operand planes.
 //
-//   C[M,N] = epi(alpha * A . B^T),  A = A_hi + A_lo, B = B_hi + B_lo   (each part exactly representable in TF32)
-//   A.B^T ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo       (dropped A_lo.B_lo term is 2^-24 relative)
+//   C[M,N] = epi(alpha * A . B^T),  A = A_hi + A_lo, B = B_hi + B_lo
+//   A.B^T ~= A_hi.B_hi + A_lo.B_hi + A_hi.B_lo       (dropped A_lo.B_lo term is 2^-22 relative)
 //
-// Pipeline (one 128 x BN output tile per CTA, 192 threads):
-//   prep kernels : split (and transpose when the caller's operand is MN-major) each operand into K-major
-//                  hi/lo planes [rows, Kp] in the caller-provided workspace (Kp = K rounded up to 32, zero padded)
-//   warp 0       : TMA producer  -- cp.async.bulk.tensor 2D tiles (128B-swizzled, 32 fp32 = 128 B per row) into a
-//                  3-stage shared-memory ring, completion on mbarriers
-//   warp 1       : MMA issuer    -- one thread issues tcgen05.mma.kind::tf32 (M=128, N=BN, K=8), 3 MMAs per k-slice,
-//                  accumulating in TMEM; tcgen05.commit frees the smem stage / signals the epilogue
-//   warps 2..5   : epilogue      -- tcgen05.ld 32x32b (one accumulator row per thread), fused bias / ReLU / tanh /
-//                  mask / alpha, direct global stores (or fp32 RED for split-K accumulation)
+// Plane formats (template parameter H): scaled FP16 halfs (kind::f16, backend 2, default) or fp32 words holding TF32 values
+// (kind::tf32, backend 1).  Planes are kept in the tensors' natural row-major layout and read K-major or MN-major by TMA / UMMA
+// descriptors -- nothing is transposed -- and are normally WRITTEN by the epilogue of the GEMM that produces the tensor.
+//
+// Kernels (all: warp 0 = TMA producer into a shared-memory ring with mbarrier completion, warp 1 = one thread issuing
+// tcgen05.mma into TMEM, drain / epilogue warps that pull every k-block's A_hi.B_hi partial out of TMEM with tcgen05.ld and
+// accumulate it in fp32 registers with round-to-nearest adds -- the tensor core's own accumulation truncates):
+//   gemm_tc256_kernel  128 x 256 tile, 2-stage ring, 8 drain warps            (N >= 384; the workhorse)
+//   gemm_tc_kernel     128 x 128 / 128 x 64 tile, double-buffered main tile   (narrow N)
+//   gemm_tcp_kernel    persistent 128 x 128 ping-pong kernel                  (opt-in experiment, ASE_TC_PERSIST=1)
+// Store phase: registers -> shared staging tile -> coalesced pass with bias / ReLU / tanh / mask (fp32 or 1-bit), optional
+// fp32 C, half planes (predicted power-of-two scale), ReLU activity bits, max |C|, fused column sums, split-K fp32 RED.
 // Descriptor formats follow the PTX ISA "tcgen05 shared memory descriptor" / "instruction descriptor" tables
-// (cross-checked against cute/arch/mma_sm100_desc.hpp in the image's CUTLASS headers).
+// (cross-checked against cute/arch/mma_sm100_desc.hpp and cute/atom/mma_traits_sm100.hpp in the image's CUTLASS headers).
+// DESIGN.md section 5 has the numerics and the measurements.
 #include <cuda.h>
 #include <cuda_fp16.h>
 #include <vector>
