@@ -315,9 +315,28 @@ class CommonAgent:
              'actions': batch_dict['actions'], 'obs': batch_dict['obses'], 'mu': batch_dict['mus'], 'sigma': batch_dict['sigmas']}
         self.dataset.update_values_dict(d)
 
+    def _gather(self, pairs):
+        """pairs: [(key, source tensor [n, ...], int64 row indices)] -> {key: rows}; fp32 contiguous sources go through ONE fused
+        ase_gather_rows launch into per-key staging buffers (AMPDataset._get_item issues one indexing kernel per tensor)."""
+        bufs = self.__dict__.setdefault('_mb_bufs', {})
+        out, items = {}, []
+        for k, v, idx in pairs:
+            if v.dtype != torch.float32 or not v.is_contiguous() or not v.is_cuda:
+                out[k] = v[idx]
+                continue
+            shape = (idx.shape[0],) + tuple(v.shape[1:])
+            dst = bufs.get(k)
+            if dst is None or tuple(dst.shape) != shape:
+                dst = bufs[k] = torch.empty(shape, dtype=torch.float32, device=v.device)
+            items.append((v, dst, idx))
+            out[k] = dst
+        if items:
+            ops.gather_rows(items)
+        return out
+
     def _minibatch(self, i):
         idx = self.dataset.sample_indices(i)
-        return {k: v[idx] for k, v in self.dataset.values_dict.items() if v is not None}, idx
+        return self._gather([(k, v, idx) for k, v in self.dataset.values_dict.items() if v is not None]), idx
 
     # ------------------------------------------------------------------ update (common_agent.py:353-435)
     def _new_latents(self, n):
@@ -512,11 +531,16 @@ class AMPAgent(CommonAgent):
         self._amp_obs_flat = batch_dict['amp_obs']
 
     def _minibatch(self, i):
-        mb, idx = super()._minibatch(i)
-        a = idx[:self._amp_minibatch_size]          # only amp_minibatch_size rows are consumed (ase_agent.py:172-181)
-        mb['amp_obs'] = self._amp_obs_flat[a]
-        mb['amp_obs_demo'] = self._amp_obs_demo_buffer.rows('amp_obs', self._demo_idx[a])
-        mb['amp_obs_replay'] = mb['amp_obs'] if self._replay_idx is None else self._amp_replay_buffer.rows('amp_obs', self._replay_idx[a])
+        idx = self.dataset.sample_indices(i)
+        a = idx[:self._amp_minibatch_size].contiguous()      # only amp_minibatch_size rows are consumed (ase_agent.py:172-181)
+        pairs = [(k, v, idx) for k, v in self.dataset.values_dict.items() if v is not None]
+        pairs.append(('amp_obs', self._amp_obs_flat, a))
+        pairs.append(('amp_obs_demo', self._amp_obs_demo_buffer._data_buf['amp_obs'], self._demo_idx[a]))
+        if self._replay_idx is not None:
+            pairs.append(('amp_obs_replay', self._amp_replay_buffer._data_buf['amp_obs'], self._replay_idx[a]))
+        mb = self._gather(pairs)
+        if self._replay_idx is None:
+            mb['amp_obs_replay'] = mb['amp_obs']
         return mb, idx
 
     def _post_update(self, batch_dict):

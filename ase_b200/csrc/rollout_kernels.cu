@@ -150,3 +150,49 @@ extern "C" int ase_policy_sample(const float* mu, const float* logstd, const flo
   ASE_LAUNCH_OK();
   return ASE_OK;
 }
+
+// ------------------------------------------------------------------------------------------------------------
+// Minibatch gather (learning/amp_datasets.py:14-27 AMPDataset._get_item + the demo / replay row fetches of
+// amp_agent.py:194-202): dst_i[r, :] = src_i[idx_i[r], :] for up to ASE_GATHER_MAX tensors in ONE launch
+// (the reference issues one advanced-indexing kernel per tensor, 13 per minibatch).  blockIdx.y = tensor.
+// ------------------------------------------------------------------------------------------------------------
+namespace ase {
+__global__ void __launch_bounds__(256)
+gather_rows_kernel(AseGatherBatch b) {
+  const AseGatherItem it = b.item[blockIdx.y];
+  const bool vec = ((it.cols & 3) == 0) && ((it.src_ld & 3) == 0) && ((it.dst_ld & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(it.src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(it.dst) & 15) == 0);
+  if (vec) {
+    const int c4n = it.cols >> 2;
+    const int64_t total = (int64_t)it.rows * c4n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int r = (int)(i / c4n), c = (int)(i - (int64_t)r * c4n) * 4;
+      const int64_t sr = it.idx ? it.idx[r] : r;
+      *reinterpret_cast<float4*>(it.dst + (int64_t)r * it.dst_ld + c) = *reinterpret_cast<const float4*>(it.src + sr * it.src_ld + c);
+    }
+  } else {
+    const int64_t total = (int64_t)it.rows * it.cols;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int r = (int)(i / it.cols), c = (int)(i - (int64_t)r * it.cols);
+      const int64_t sr = it.idx ? it.idx[r] : r;
+      it.dst[(int64_t)r * it.dst_ld + c] = it.src[sr * it.src_ld + c];
+    }
+  }
+}
+}  // namespace ase
+
+extern "C" int ase_gather_rows(const AseGatherBatch* batch, void* stream) {
+  ASE_CHECK_ARG(batch && batch->count >= 0 && batch->count <= ASE_GATHER_MAX, "ase_gather_rows: bad batch");
+  if (batch->count == 0) return ASE_OK;
+  int64_t big = 0;
+  for (int i = 0; i < batch->count; ++i) {
+    const AseGatherItem& it = batch->item[i];
+    ASE_CHECK_ARG(it.src && it.dst && it.rows >= 0 && it.cols > 0 && it.src_ld >= it.cols && it.dst_ld >= it.cols, "ase_gather_rows: item %d", i);
+    big = ase::imax64(big, (int64_t)it.rows * it.cols);
+  }
+  if (big == 0) return ASE_OK;
+  dim3 grid((unsigned)ase::imin64((big / 4 + 255) / 256 + 1, 148 * 4), (unsigned)batch->count);
+  ase::gather_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*batch);
+  ASE_LAUNCH_OK();
+  return ASE_OK;
+}

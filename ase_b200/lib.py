@@ -46,6 +46,17 @@ class GemmParams(C.Structure):
                 ('relu_bits_out', vp), ('ldrb', i64), ('mask_bits', vp), ('ldmb', i64), ('c_planes_only', i32)]
 
 
+ASE_GATHER_MAX = 16
+
+
+class GatherItem(C.Structure):
+    _fields_ = [('src', vp), ('dst', vp), ('idx', vp), ('rows', i32), ('cols', i32), ('src_ld', i64), ('dst_ld', i64)]
+
+
+class GatherBatch(C.Structure):
+    _fields_ = [('count', i32), ('item', GatherItem * ASE_GATHER_MAX)]
+
+
 class LearnerConfig(C.Structure):
     _fields_ = [('kind', i32), ('obs_dim', i32), ('act_dim', i32), ('amp_dim', i32), ('latent_dim', i32),
                 ('n_units', i32), ('units', i32 * ASE_MAX_LAYERS),
@@ -75,7 +86,7 @@ class TrainResult(C.Structure):
 
 # every symbol declared in include/ase_b200.h (tests/test_abi.py checks the two lists agree)
 EXPORTS = ['ase_abi_version', 'ase_last_error', 'ase_launch_count', 'ase_obs_build', 'ase_amp_obs_build',
-           'ase_rms_scratch_bytes', 'ase_rms_update', 'ase_rms_apply', 'ase_gae', 'ase_amp_rewards', 'ase_heading_obs', 'ase_heading_reward', 'ase_motion_state', 'ase_amp_obs_demo', 'ase_policy_sample', 'ase_adv_normalize',
+           'ase_rms_scratch_bytes', 'ase_rms_update', 'ase_rms_apply', 'ase_gae', 'ase_amp_rewards', 'ase_heading_obs', 'ase_heading_reward', 'ase_motion_state', 'ase_amp_obs_demo', 'ase_policy_sample', 'ase_adv_normalize', 'ase_gather_rows',
            'ase_gemm', 'ase_gemm_tc_workspace_bytes', 'ase_gemm_tc_profile', 'ase_gemm_tc_profile_read', 'ase_learner_num_params', 'ase_learner_param_desc',
            'ase_learner_arena_floats', 'ase_learner_workspace_bytes', 'ase_learner_create', 'ase_learner_destroy', 'ase_learner_params_changed', 'ase_learner_plane_status',
            'ase_learner_calc_gradients', 'ase_learner_adam_step', 'ase_learner_eval_actor_critic',
@@ -107,6 +118,7 @@ def _load():
     lib.ase_amp_obs_demo.argtypes = [C.POINTER(MotionLibParams), vp, vp, i32, f32, i32, i32, i32, vp, vp]
     lib.ase_policy_sample.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
     lib.ase_adv_normalize.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    lib.ase_gather_rows.argtypes = [C.POINTER(GatherBatch), vp]
     lib.ase_obs_build.argtypes = [C.POINTER(ObsBuildParams), vp]
     lib.ase_amp_obs_build.argtypes = [C.POINTER(AmpObsBuildParams), vp]
     lib.ase_gemm.argtypes = [C.POINTER(GemmParams), vp]

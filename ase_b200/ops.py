@@ -183,6 +183,24 @@ def calc_advs(returns, values, mask=None):
     return out
 
 
+def gather_rows(items):
+    """items: list of (src [n, ...] contiguous fp32, dst [rows, ...] contiguous fp32, idx int64 [rows] or None): dst[r] = src[idx[r]]
+    for all of them in one launch (AMPDataset._get_item + demo / replay fetches, amp_datasets.py:14-27)."""
+    for s0 in range(0, len(items), L.ASE_GATHER_MAX):
+        chunk = items[s0:s0 + L.ASE_GATHER_MAX]
+        b = L.GatherBatch()
+        b.count = len(chunk)
+        for i, (src, dst, idx) in enumerate(chunk):
+            assert src.dtype == torch.float32 and dst.dtype == torch.float32 and src.is_contiguous() and dst.is_contiguous()
+            assert idx is None or (idx.dtype == torch.int64 and idx.is_contiguous() and idx.numel() == dst.shape[0])
+            cols = 1 if src.dim() == 1 else int(src[0].numel())
+            assert (1 if dst.dim() == 1 else int(dst[0].numel())) == cols
+            it = b.item[i]
+            it.src, it.dst, it.idx = src.data_ptr(), dst.data_ptr(), None if idx is None else idx.data_ptr()
+            it.rows, it.cols, it.src_ld, it.dst_ld = dst.shape[0], cols, cols, cols
+        check(lib.ase_gather_rows(C.byref(b), _stream()), 'ase_gather_rows')
+
+
 def gemm(A, B, a_trans=False, b_trans=False, bias=None, act=0, mask_src=None, mask_mode=0, out=None, accumulate=False,
          split_k=0, alpha=1.0, backend=0, colsum_out=None, relu_bits_out=None, mask_bits=None):
     """C = epi(alpha * op(A) . op(B)); see include/ase_b200.h (AseGemmParams)."""

@@ -149,6 +149,14 @@ int ase_policy_sample(const float* mu, const float* logstd, const float* noise, 
 int ase_adv_normalize(const float* returns, const float* values, const float* mask, int rows,
                       float* advs, void* scratch, void* stream);
 
+/* Minibatch gather: dst_i[r, :] = src_i[idx_i[r], :] (idx NULL = identity) for up to ASE_GATHER_MAX fp32 tensors in one
+ * launch.  Replaces the per-tensor advanced indexing of AMPDataset._get_item (learning/amp_datasets.py:14-27) and the demo /
+ * replay row fetches (amp_agent.py:194-202, replay_buffer.py:27-69); idx are int64 device row indices as torch produces. */
+#define ASE_GATHER_MAX 16
+typedef struct { const float* src; float* dst; const int64_t* idx; int rows, cols; int64_t src_ld, dst_ld; } AseGatherItem;
+typedef struct { int count; AseGatherItem item[ASE_GATHER_MAX]; } AseGatherBatch;
+int ase_gather_rows(const AseGatherBatch* batch, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * GEMM primitives (exposed for tests / profiling; the learner drives them internally).
  *   C[M,N] = epilogue( alpha * op(A) . op(B) )          fp32 in, fp32 accumulate, fp32 out

@@ -159,3 +159,24 @@ def test_motion_lib_state_and_demo_obs_golden():
     # sampler plumbing: shapes, times inside [truncate, len]
     d = ml.fetch_amp_obs_demo(512, 1.0 / 30.0, 10)
     assert d.shape == (512, 1400) and torch.isfinite(d).all()
+
+
+def test_gather_rows_bit_exact():
+    """ase_gather_rows (AMPDataset._get_item, amp_datasets.py:14-27): index work is bit-exact; several tensors per launch, vector and
+    scalar paths (row widths 253 / 31 / 1 / 1400 / 64), identity index, empty batch, more tensors than one launch holds."""
+    from ase_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    n, rows = 5000, 777
+    idx = torch.randint(0, n, (rows,), generator=g).cuda()
+    srcs = [torch.randn(n, c, generator=g).cuda() for c in (253, 31, 1400, 64)] + [torch.randn(n, generator=g).cuda(), torch.randn(n, 1, generator=g).cuda()]
+    dsts = [torch.full((rows,) + tuple(s.shape[1:]), -7.0, device='cuda') for s in srcs]
+    ops.gather_rows([(s, d, idx) for s, d in zip(srcs, dsts)])
+    for s, d in zip(srcs, dsts):
+        assert torch.equal(d, s[idx])
+    ident = torch.empty(rows, 253, device='cuda')
+    ops.gather_rows([(srcs[0], ident, None)])
+    assert torch.equal(ident, srcs[0][:rows])
+    ops.gather_rows([])
+    many = [(srcs[1], torch.empty(rows, 31, device='cuda'), idx) for _ in range(19)]       # > ASE_GATHER_MAX: split over two launches
+    ops.gather_rows(many)
+    assert all(torch.equal(d, srcs[1][idx]) for _, d, _ in many)

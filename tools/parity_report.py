@@ -1,4 +1,4 @@
-"""Prints the parity table (GPU engine vs the reference's golden outputs) for both GEMM backends.
+"""Prints the parity table (GPU engine vs the reference's golden outputs) for the three GEMM backends.
 Usage (on the GPU box): python tools/parity_report.py > profiles/parity_rNN.txt"""
 import os
 import sys
@@ -19,7 +19,7 @@ def report(name, backend):
     ln = _make_learner(kind, meta, P, backend)
     st = O.LearnerState(P, 253, 1400, kind)
     cfg = meta['cfg']
-    print(f"== {name}  backend={'tcgen05-3xTF32' if backend else 'SIMT-fp32'}  B={meta['B']} Ba={meta['Ba']}")
+    print(f"== {name}  backend={('SIMT-fp32', 'tcgen05-3xTF32', 'tcgen05-3xFP16-scaled')[backend]}  B={meta['B']} Ba={meta['Ba']}")
     for s, rec in enumerate(steps):
         d, nz = synth.minibatch(st, cfg, meta['B'], meta['Ba'], seed=meta['seed'] * 100 + s, kind=kind)
         out = ln.calc_gradients(_cuda(d), None if nz is None else nz.cuda())
@@ -49,5 +49,5 @@ def report(name, backend):
 
 if __name__ == '__main__':
     for name in ('calc_grad_ase_cfg1.pt', 'calc_grad_amp_cfg.pt'):
-        for backend in (0, 1):
+        for backend in (0, 1, 2):
             report(name, backend)
