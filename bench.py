@@ -187,7 +187,10 @@ def run_ours(args):
         "data": "synthetic",
         "config": _workload_config(world),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_secs * 1e3 / args.steps},
+                "ms_per_step": e2e_secs * 1e3 / args.steps,
+                "note": "separate timed run through the agent API: every sim step's rigid-body state arrives from pinned host memory (H2D inside "
+                        "the timed region, overlapping compute on the copy engine), the epoch's train_result series is read back (D2H); it can "
+                        "come out slightly ahead of `value`, whose synthetic env refreshes its state with device-to-device copies on the compute stream"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "roofline": {"bound": "tensor", "kernel": "gemm_tc256_kernel / gemm_tc_kernel (tcgen05.mma kind::f16, 3 MMAs per product on scaled FP16 hi/lo planes)" if GEMM_BACKEND == 2
