@@ -92,6 +92,7 @@ class CommonAgent:
         self.max_epochs = config.get('max_epochs', 1e6)
         self.save_freq = config.get('save_frequency', 0)
         self.print_stats = config.get('print_stats', True)
+        self.writer = config.get('writer', None)          # optional tensorboardX-like object with add_scalar(tag, value, step)
         self.clip_actions = config.get('clip_actions', True)
         self.multi_gpu = config.get('multi_gpu', False)
         self.rank, self.rank_size = 0, 1
@@ -426,19 +427,51 @@ class CommonAgent:
             broadcast_state([self.model.params, self.model.exp_avg, self.model.exp_avg_sq])
             self.model.params_changed()
         self._init_train()
+        # no per-epoch host sync -- the epoch's scalars and event timings come back through a pinned ring
+        from .async_log import AsyncEpochLog
+        from .lib import TR_NAMES
+        log = AsyncEpochLog(TR_NAMES, depth=4)
+        self.epoch_log = []                       # [{'epoch', 'frames', 'scalars', 'play_time', 'update_time'}], an epoch or two behind
         total_time = 0.0
+
+        def consume(recs):
+            nonlocal total_time
+            for r in recs:
+                r.pop('series', None)
+                total_time += r.get('play_time', 0.0) + r.get('update_time', 0.0)
+                self.epoch_log.append(r)
+                if self.rank == 0 and self.print_stats and 'play_time' in r:
+                    tot = r['play_time'] + r['update_time']
+                    print(f"epoch {r['epoch']}: fps step: {r['frames'] / r['play_time']:.1f} fps total: {r['frames'] / tot:.1f}")
+                if self.writer is not None:       # performance/* and losses/* scalars of common_agent.py:119-152,551-564
+                    self._write_stats(r)
+
         while True:
             epoch_num = self.update_epoch()
             self.train_epoch()
-            play_time, update_time, sum_time = self.epoch_times()
-            total_time += sum_time
             if self.multi_gpu:
                 self._sync_stats()
             self.frame += self.curr_frames * self.rank_size
-            if self.rank == 0 and self.print_stats:
-                print(f'fps step: {self.curr_frames / play_time:.1f} fps total: {self.curr_frames / sum_time:.1f}')
+            consume(log.push(epoch_num, self._tr_buf, frames=self.curr_frames, events=tuple(self._events)))
+            consume(log.poll())
             if epoch_num >= self.max_epochs:
+                consume(log.flush())
+                if self.model.cfg.gemm_backend == 2:
+                    self.model.plane_status()     # raises if an FP16 operand-plane scale was missed anywhere in the run
+                self.total_time = total_time
                 return -100500, epoch_num
+
+    def _write_stats(self, r):
+        """TensorBoard emission (common_agent.py:119-152, amp_agent.py:244-262) from an AsyncEpochLog record."""
+        w, frame = self.writer, r['epoch'] * self.batch_size * self.rank_size
+        if 'play_time' in r:
+            tot = r['play_time'] + r['update_time']
+            w.add_scalar('performance/total_fps', r['frames'] * self.rank_size / tot, frame)
+            w.add_scalar('performance/step_fps', r['frames'] * self.rank_size / r['play_time'], frame)
+            w.add_scalar('performance/update_time', r['update_time'], frame)
+            w.add_scalar('performance/play_time', r['play_time'], frame)
+        for k, v in r['scalars'].items():
+            w.add_scalar(('info/' if k in ('kl', 'last_lr', 'lr_mul', 'e_clip') else 'losses/') + k, v, frame)
 
 
 class AMPAgent(CommonAgent):

@@ -62,3 +62,21 @@ def test_param_names_match_reference_state_dict():
     assert ['sigma'] + param_names('ase', 3, 3, 2) == list(O.ase_param_shapes().keys())
     assert ['sigma'] + param_names('amp', 2, 2, 0) == list(O.amp_param_shapes().keys())
     assert ['sigma'] + param_names('ppo', 2, 0, 0) == list(O.amp_param_shapes(amp=0).keys())
+
+
+def test_async_epoch_log_ring_cpu():
+    """AsyncEpochLog on CPU tensors: order, means, ring overflow drains the oldest epoch first."""
+    import torch
+    from ase_b200.async_log import AsyncEpochLog
+    log = AsyncEpochLog(['a', 'b'], depth=2)
+    got = []
+    for e in range(1, 6):
+        series = torch.tensor([[float(e), 2.0 * e], [float(e) + 2, 2.0 * e]])
+        got += log.push(e, series, frames=10 * e)
+        if e == 3:
+            got += log.poll()
+    got += log.flush()
+    assert [r['epoch'] for r in got] == [1, 2, 3, 4, 5]
+    assert [r['frames'] for r in got] == [10, 20, 30, 40, 50]
+    assert all(abs(r['scalars']['a'] - (r['epoch'] + 1)) < 1e-6 and abs(r['scalars']['b'] - 2 * r['epoch']) < 1e-6 for r in got)
+    assert log.poll() == [] and log.flush() == []

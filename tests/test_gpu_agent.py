@@ -93,6 +93,25 @@ def test_train_epochs_run_and_stay_finite_and_checkpoint_roundtrip():
     assert torch.equal(agent2.model.exp_avg, agent.model.exp_avg) and agent2.model.step == agent.model.step
 
 
+def test_train_loop_logs_through_the_async_ring():
+    """agent.train() (common_agent.py:82-155) never reads a device scalar inside the loop: the epochs' train_result series and event
+    timings come back through AsyncEpochLog (pinned ring) -- all epochs accounted for, in order, finite."""
+    torch.manual_seed(2)
+    agent, env = _small_agent('ase')
+    agent.max_epochs = 5
+    tags = []
+    class W:
+        def add_scalar(self, tag, value, step):
+            tags.append(tag)
+    agent.writer = W()
+    agent.train()
+    assert [r['epoch'] for r in agent.epoch_log] == [1, 2, 3, 4, 5]
+    for r in agent.epoch_log:
+        assert r['play_time'] > 0 and r['update_time'] > 0 and r['frames'] == 64 * 8
+        assert all(v == v and abs(v) < 1e9 for v in r['scalars'].values())
+    assert 'performance/total_fps' in tags and 'losses/disc_loss' in tags and 'info/kl' in tags
+
+
 def test_hrl_agent_epoch_config5_shapes():
     """BASELINE config 5 (HumanoidHeading task-train over a frozen ASE LLC): play_steps + update run end to end; the
     combined reward, LLC stepping and tanh-mu HLC learner are checked against the oracle on the stored buffers."""
