@@ -160,6 +160,19 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
 __device__ __forceinline__ uint64_t make_smem_desc_mn_h(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
+// FP16 format, 32-wide k sub-blocks (the 4-deep ring of the 128x256 kernel).  K-major rows are 64 bytes: SWIZZLE_64B (layout type 4,
+// ((8,n),2):((4,SBO),1) in 16-byte units: 8-row x 64 B atoms, SBO = 512).  MN-major boxes are [32 k-rows x 64 mn]: the same SWIZZLE_128B
+// layout as above with LBO = 4096 (one box per 64-wide MN block).
+__device__ __forceinline__ uint64_t make_smem_desc_k64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+__device__ __forceinline__ uint64_t make_smem_desc_mn_h32(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+template <bool MN>
+__device__ __forceinline__ uint64_t tc_desc_sub(uint32_t base, int k) {      // k = 0, 1: the two K=16 MMAs of a 32-wide sub-block
+  return MN ? make_smem_desc_mn_h32(base + k * 2048) : make_smem_desc_k64(base + k * 32);
+}
 template <bool H, bool MN>
 __device__ __forceinline__ uint64_t tc_desc(uint32_t base, int k) {
   if (!MN) return make_smem_desc(base + k * 32);                       // K-major: 32 bytes along the swizzled row per MMA
@@ -699,55 +712,65 @@ constexpr int TC256_THREADS = 384;       // WG0: warp 0 TMA, warp 1 MMA (+2 idle
 constexpr int TC256_BN = 256;
 constexpr int TC256_STAGES = 2;
 
-// One k-block of operand planes into stage kb % STAGES of the 128x256 kernel's ring (producer thread only); it is
+// One k-block (SUB: one 32-wide k sub-block) of operand planes into the 128x256 kernel's ring (producer thread only); it is
 // called from two places (before and after the CTA-wide setup barrier).
-template <bool AMN, bool BMN, bool H>
+//   SUB = false: 2 stages x 96 KB, 64-wide k-blocks (default).
+//   SUB = true : 4 stages x 48 KB, 32-wide sub-blocks released one by one, so loads are issued 14-16 MMA slots ahead instead of 12.
+//                Built to test whether the mainloop (74 % of the MMA rate) waits on load LATENCY: it does not -- same slope, 3 % slower
+//                overall -- so the limit is the L2 -> SM operand bandwidth (1.6 GB per 32768x1024x1024 GEMM at ~13 TB/s).  Opt-in.
+template <bool AMN, bool BMN, bool H, bool SUB>
 __device__ __forceinline__ void tc256_issue_kb(const CUtensorMap* tmAhi, const CUtensorMap* tmAlo, const CUtensorMap* tmBhi, const CUtensorMap* tmBlo,
-                                            uint8_t* smem, uint64_t* full, uint64_t* empty, int kb, int kb_begin, int m0, int n0) {
-  constexpr int BN = 256, STAGES = 2;
-  using SM = TcSmem<BN, STAGES>;
+                                               uint8_t* smem, uint64_t* full, uint64_t* empty, int kb, int kb_begin, int m0, int n0) {
+  constexpr int BN = 256, STAGES = SUB ? 4 : 2;
   using F = TcFmt<H>;
+  constexpr int KW = SUB ? 32 : F::BK;                       // k elements per ring slot
+  constexpr int ROWB = SUB ? 64 : 128;                        // bytes per K-major operand row in a slot
+  constexpr int A_BYTES = TC_BM * ROWB, B_BYTES = BN * ROWB, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  constexpr int MN_BOX_BYTES = SUB ? 4096 : F::MN_BOX_BYTES;  // [KW k-rows x 64 mn] halfs
   const int s = kb % STAGES;
   const uint32_t ph = (kb / STAGES) & 1;
   mbar_wait(&empty[s], ph ^ 1);
-  mbar_expect_tx(&full[s], SM::STAGE_BYTES);
-  uint8_t* st = smem + s * SM::STAGE_BYTES;
-  const int k0 = (kb_begin + kb) * F::BK;
+  mbar_expect_tx(&full[s], STAGE_BYTES);
+  uint8_t* st = smem + s * STAGE_BYTES;
+  const int k0 = (SUB ? 2 * kb_begin + kb : kb_begin + kb) * KW;
   if (!AMN) {
     tma_load_2d(st, tmAhi, &full[s], k0, m0);
-    tma_load_2d(st + SM::A_BYTES, tmAlo, &full[s], k0, m0);
+    tma_load_2d(st + A_BYTES, tmAlo, &full[s], k0, m0);
   } else {
 #pragma unroll
     for (int b = 0; b < TC_BM / F::MN_BOX; ++b) {
-      tma_load_2d(st + b * F::MN_BOX_BYTES, tmAhi, &full[s], m0 + b * F::MN_BOX, k0);
-      tma_load_2d(st + SM::A_BYTES + b * F::MN_BOX_BYTES, tmAlo, &full[s], m0 + b * F::MN_BOX, k0);
+      tma_load_2d(st + b * MN_BOX_BYTES, tmAhi, &full[s], m0 + b * F::MN_BOX, k0);
+      tma_load_2d(st + A_BYTES + b * MN_BOX_BYTES, tmAlo, &full[s], m0 + b * F::MN_BOX, k0);
     }
   }
   if (!BMN) {        // the B maps have 128-row boxes: two per plane
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      tma_load_2d(st + 2 * SM::A_BYTES + h * 16384, tmBhi, &full[s], k0, n0 + h * 128);
-      tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES + h * 16384, tmBlo, &full[s], k0, n0 + h * 128);
+      tma_load_2d(st + 2 * A_BYTES + h * (128 * ROWB), tmBhi, &full[s], k0, n0 + h * 128);
+      tma_load_2d(st + 2 * A_BYTES + B_BYTES + h * (128 * ROWB), tmBlo, &full[s], k0, n0 + h * 128);
     }
   } else {
 #pragma unroll
     for (int b = 0; b < BN / F::MN_BOX; ++b) {
-      tma_load_2d(st + 2 * SM::A_BYTES + b * F::MN_BOX_BYTES, tmBhi, &full[s], n0 + b * F::MN_BOX, k0);
-      tma_load_2d(st + 2 * SM::A_BYTES + SM::B_BYTES + b * F::MN_BOX_BYTES, tmBlo, &full[s], n0 + b * F::MN_BOX, k0);
+      tma_load_2d(st + 2 * A_BYTES + b * MN_BOX_BYTES, tmBhi, &full[s], n0 + b * F::MN_BOX, k0);
+      tma_load_2d(st + 2 * A_BYTES + B_BYTES + b * MN_BOX_BYTES, tmBlo, &full[s], n0 + b * F::MN_BOX, k0);
     }
   }
 }
 
-template <bool AMN, bool BMN, bool H>
+template <bool AMN, bool BMN, bool H, bool SUB>
 __global__ void __launch_bounds__(TC256_THREADS, 1)
 gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                   const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const TcEpi e) {
-  constexpr int BN = TC256_BN, STAGES = TC256_STAGES;
-  using SM = TcSmem<BN, STAGES>;
+  static_assert(!SUB || H, "32-wide k sub-blocks exist for the FP16 format only");
+  constexpr int BN = TC256_BN, STAGES = SUB ? 4 : TC256_STAGES;
+  using SM = TcSmem<BN, TC256_STAGES>;                      // total bytes are the same: 2 x 96 KB or 4 x 48 KB
+  constexpr int SLOT_BYTES = SM::STAGE_BYTES / (SUB ? 2 : 1);
+  constexpr int SA_BYTES = SM::A_BYTES / (SUB ? 2 : 1), SB_BYTES = SM::B_BYTES / (SUB ? 2 : 1);
   using F = TcFmt<H>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * SM::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + TC256_STAGES * SM::STAGE_BYTES);
   uint64_t* full = bars;
   uint64_t* empty = bars + STAGES;
   uint64_t* main_full = bars + 2 * STAGES;
@@ -761,9 +784,10 @@ gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
   const int nkb = min(e.kb_per_split, e.kb_total - kb_begin);
 
   auto issue_kb = [&](int kb) {
-    tc256_issue_kb<AMN, BMN, H>(&tmAhi, &tmAlo, &tmBhi, &tmBlo, smem, full, empty, kb, kb_begin, m0, n0);
+    tc256_issue_kb<AMN, BMN, H, SUB>(&tmAhi, &tmAlo, &tmBhi, &tmBlo, smem, full, empty, kb, kb_begin, m0, n0);
   };
-  const int kb_early = min(STAGES, nkb);      // k-blocks whose loads are issued before the CTA-wide setup barrier
+  const int nslots = SUB ? 2 * nkb : nkb;     // ring slots this CTA streams (32-wide sub-blocks / 64-wide k-blocks)
+  const int kb_early = min(STAGES, nslots);   // slots whose loads are issued before the CTA-wide setup barrier
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAhi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAlo)) : "memory");
@@ -790,30 +814,63 @@ gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
   if (warp < 4) {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == 0 && lane == 0) {
-      for (int kb = kb_early; kb < nkb; ++kb) issue_kb(kb);
+      for (int kb = kb_early; kb < nslots; ++kb) issue_kb(kb);
     } else if (warp == 1 && lane == 0) {
       const uint32_t idesc = tc_idesc<H>(AMN, BMN, BN);
       auto adesc = [](uint32_t base, int k) { return tc_desc<H, AMN>(base, k); };
       auto bdesc = [](uint32_t base, int k) { return tc_desc<H, BMN>(base, k); };
       for (int kb = 0; kb < nkb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full[s], ph);
-        mbar_wait(main_empty, (uint32_t)((kb & 1) ^ 1));       // drain of k-block kb-1 (runs under its correction MMAs)
-        tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
-        const uint32_t a_hi = sa, a_lo = sa + SM::A_BYTES, b_hi = sa + 2 * SM::A_BYTES, b_lo = b_hi + SM::B_BYTES;
+        if (!SUB) {
+          const int s = kb % STAGES;
+          const uint32_t ph = (kb / STAGES) & 1;
+          mbar_wait(&full[s], ph);
+          mbar_wait(main_empty, (uint32_t)((kb & 1) ^ 1));       // drain of k-block kb-1 (runs under its correction MMAs)
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
+          const uint32_t a_hi = sa, a_lo = sa + SM::A_BYTES, b_hi = sa + 2 * SM::A_BYTES, b_lo = b_hi + SM::B_BYTES;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          tc_mma<H>(tmem_base, adesc(a_hi, k), bdesc(b_hi, k), idesc, k > 0 ? 1u : 0u);
-        tc_commit(main_full);
-        if (!(e.debug & 4))
+          for (int k = 0; k < 4; ++k)
+            tc_mma<H>(tmem_base, adesc(a_hi, k), bdesc(b_hi, k), idesc, k > 0 ? 1u : 0u);
+          tc_commit(main_full);
+          if (!(e.debug & 4))
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          tc_mma<H>(tmem_corr, adesc(a_lo, k), bdesc(b_hi, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          tc_mma<H>(tmem_corr, adesc(a_hi, k), bdesc(b_lo, k), idesc, 1u);
+          for (int k = 0; k < 4; ++k) {
+            tc_mma<H>(tmem_corr, adesc(a_lo, k), bdesc(b_hi, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            tc_mma<H>(tmem_corr, adesc(a_hi, k), bdesc(b_lo, k), idesc, 1u);
+          }
+          tc_commit(&empty[s]);
+        } else {
+          // two 32-wide sub-blocks per 64-wide k-block: main MMAs of both (the drain granularity stays 64), then each
+          // sub-block's correction MMAs followed by the release of its ring slot
+          const int g0 = 2 * kb, g1 = 2 * kb + 1;
+          const int s0 = g0 % STAGES, s1 = g1 % STAGES;
+          mbar_wait(&full[s0], (uint32_t)((g0 / STAGES) & 1));
+          mbar_wait(&full[s1], (uint32_t)((g1 / STAGES) & 1));
+          mbar_wait(main_empty, (uint32_t)((kb & 1) ^ 1));
+          tc_fence_after();
+          const uint32_t base0 = smem_u32(smem + s0 * SLOT_BYTES), base1 = smem_u32(smem + s1 * SLOT_BYTES);
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            const uint32_t sa = x ? base1 : base0;
+            const uint32_t a_hi = sa, b_hi = sa + 2 * SA_BYTES;
+#pragma unroll
+            for (int k = 0; k < 2; ++k)
+              tc_mma<H>(tmem_base, tc_desc_sub<AMN>(a_hi, k), tc_desc_sub<BMN>(b_hi, k), idesc, (x > 0 || k > 0) ? 1u : 0u);
+          }
+          tc_commit(main_full);
+#pragma unroll
+          for (int x = 0; x < 2; ++x) {
+            const uint32_t sa = x ? base1 : base0;
+            const uint32_t a_hi = sa, a_lo = sa + SA_BYTES, b_hi = sa + 2 * SA_BYTES, b_lo = b_hi + SB_BYTES;
+            if (!(e.debug & 4))
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              tc_mma<H>(tmem_corr, tc_desc_sub<AMN>(a_lo, k), tc_desc_sub<BMN>(b_hi, k), idesc, (kb > 0 || x > 0 || k > 0) ? 1u : 0u);
+              tc_mma<H>(tmem_corr, tc_desc_sub<AMN>(a_hi, k), tc_desc_sub<BMN>(b_lo, k), idesc, 1u);
+            }
+            tc_commit(&empty[x ? s1 : s0]);
+          }
         }
-        tc_commit(&empty[s]);
       }
       tc_commit(corr_full);
     }
@@ -1277,8 +1334,10 @@ static std::unordered_map<MapKey, CUtensorMap, MapKeyHash>& map_cache() { static
 
 // 2D map over [rows, cols] elements (cols contiguous, row stride ld elements); the box is one 128-byte row chunk
 // (32 fp32 words / 64 halfs) x box_rows
-static int encode_cached(CUtensorMap* tm, const void* base, int rows, int cols, int64_t ld, int box_rows, bool mn_major, bool half = false) {
-  MapKey k{base, rows, cols, ld, box_rows, (mn_major ? 1 : 0) | (half ? 2 : 0)};
+// sub (halfs only): maps for the 32-wide k sub-block ring -- K-major boxes are 32 elements (64 bytes, SWIZZLE_64B) wide, MN-major boxes 32 k-rows tall
+static int encode_cached(CUtensorMap* tm, const void* base, int rows, int cols, int64_t ld, int box_rows, bool mn_major, bool half = false, bool sub = false) {
+  if (sub && mn_major) box_rows = 32;
+  MapKey k{base, rows, cols, ld, box_rows, (mn_major ? 1 : 0) | (half ? 2 : 0) | (sub ? 4 : 0)};
   auto& c = map_cache();
   auto it = c.find(k);
   if (it != c.end()) { memcpy(tm, &it->second, sizeof(CUtensorMap)); return ASE_OK; }
@@ -1286,11 +1345,12 @@ static int encode_cached(CUtensorMap* tm, const void* base, int rows, int cols, 
   if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return ASE_ERR_UNSUPPORTED; }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * (half ? 2 : 4)};
-  cuuint32_t box[2] = {half ? 64u : 32u, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {half ? ((sub && !mn_major) ? 32u : 64u) : 32u, (cuuint32_t)box_rows};
+  const bool sw64 = half && sub && !mn_major;
   cuuint32_t estr[2] = {1, 1};
   // MN-major: fp32 words need the 32-byte-atom flavour of the 128B swizzle, halfs the plain one (see the smem descriptors)
   CUresult r = enc(tm, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, (mn_major && !half) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : ((mn_major && !half) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(%d x %d, ld %lld, box %d) failed with CUresult %d", rows, cols, (long long)ld, box_rows, (int)r); return ASE_ERR_CUDA; }
   if (c.size() > 8192) c.clear();
@@ -1299,8 +1359,8 @@ static int encode_cached(CUtensorMap* tm, const void* base, int rows, int cols, 
 }
 
 // 2D tensor map over a zero-padded plane [rows_p, cols_p] (cols contiguous); box = [box_rows x 32 cols], 128B swizzle
-static int make_map(CUtensorMap* tm, const void* base, int rows_p, int cols_p, int box_rows, bool mn_major = false, bool half = false) {
-  return encode_cached(tm, base, rows_p, cols_p, cols_p, box_rows, mn_major, half);
+static int make_map(CUtensorMap* tm, const void* base, int rows_p, int cols_p, int box_rows, bool mn_major = false, bool half = false, bool sub = false) {
+  return encode_cached(tm, base, rows_p, cols_p, cols_p, box_rows, mn_major, half, sub);
 }
 
 static inline int pad_to(int x, int m) { return (x + m - 1) / m * m; }
@@ -1427,13 +1487,13 @@ static int launch_tc_major(bool amn, bool bmn, const CUtensorMap& ah, const CUte
 // A-multicast clusters are OFF by default: measured on B200 (profiles/experiments_r01.md) they do not help -- the
 // mainloop is bound by the per-SM ingest port (~64 B/clk), which multicast does not relieve.  ASE_TC_CLUSTER=2|4 enables them
 // (TF32 format only).
-template <bool AMN, bool BMN, bool H>
+template <bool AMN, bool BMN, bool H, bool SUB>
 static int launch_tc256(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcEpi& e,
                         int splits, cudaStream_t st) {
   using SM = TcSmem<TC256_BN, TC256_STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    ASE_CUDA_OK(cudaFuncSetAttribute(gemm_tc256_kernel<AMN, BMN, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    ASE_CUDA_OK(cudaFuncSetAttribute(gemm_tc256_kernel<AMN, BMN, H, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr_set = true;
   }
   dim3 grid(ceil_div(e.N, TC256_BN), ceil_div(e.M, TC_BM), splits);
@@ -1445,18 +1505,22 @@ static int launch_tc256(const CUtensorMap& ah, const CUtensorMap& al, const CUte
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = tc_pdl();
   cfg.attrs = attr; cfg.numAttrs = 1;
-  ASE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc256_kernel<AMN, BMN, H>, ah, al, bh, bl, e));
+  ASE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc256_kernel<AMN, BMN, H, SUB>, ah, al, bh, bl, e));
   if (prof) { prof_mark(st); g_prof.flops += 2.0 * (double)e.M * (double)e.N * (double)e.K; }
   ASE_LAUNCH_OK();
   return ASE_OK;
 }
-template <bool H>
+template <bool H, bool SUB>
 static int launch_tc256_major(bool amn, bool bmn, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                               const TcEpi& e, int splits, cudaStream_t st) {
-  if (!amn && !bmn) return launch_tc256<false, false, H>(ah, al, bh, bl, e, splits, st);
-  if (!amn && bmn) return launch_tc256<false, true, H>(ah, al, bh, bl, e, splits, st);
-  if (amn && !bmn) return launch_tc256<true, false, H>(ah, al, bh, bl, e, splits, st);
-  return launch_tc256<true, true, H>(ah, al, bh, bl, e, splits, st);
+  if (!amn && !bmn) return launch_tc256<false, false, H, SUB>(ah, al, bh, bl, e, splits, st);
+  if (!amn && bmn) return launch_tc256<false, true, H, SUB>(ah, al, bh, bl, e, splits, st);
+  if (amn && !bmn) return launch_tc256<true, false, H, SUB>(ah, al, bh, bl, e, splits, st);
+  return launch_tc256<true, true, H, SUB>(ah, al, bh, bl, e, splits, st);
+}
+static int tc_sub() {   // env ASE_TC_SUB=1: 4 x 48 KB ring of 32-wide k sub-blocks instead of the 2 x 96 KB ring of 64-wide k-blocks (FP16 format).
+  const char* d = getenv("ASE_TC_SUB");     // OFF by default: measured 3 % slower (profiles/experiments_r01.md) -- the mainloop is bound by the
+  return d ? (atoi(d) != 0) : 0;            // L2 -> SM operand bandwidth, not by load latency.  Read per call so that the tests can cover both rings.
 }
 template <bool AMN, bool BMN, bool H>
 static int launch_tcp(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcEpi& e, cudaStream_t st) {
@@ -1647,8 +1711,8 @@ static int resolve_operand(PlaneRegistry* reg, const float* ptr, int64_t ld, int
 }
 
 // tensor map over a (sub-)view of a plane with TRUE extents: TMA zero-fills everything outside [rows, cols]
-static int make_view_map(CUtensorMap* tm, const void* base, int rows, int cols, int64_t ldp, int box_rows, bool mn_major, bool half) {
-  return encode_cached(tm, base, rows, cols, ldp, box_rows, mn_major, half);
+static int make_view_map(CUtensorMap* tm, const void* base, int rows, int cols, int64_t ldp, int box_rows, bool mn_major, bool half, bool sub) {
+  return encode_cached(tm, base, rows, cols, ldp, box_rows, mn_major, half, sub);
 }
 
 int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
@@ -1657,6 +1721,8 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   const int BK = H ? 64 : 32, MNB = H ? 64 : 32;
   const int BN = (p.N > 64) ? 128 : 64;
   const bool use256 = tc_tile256() && p.N >= 384;               // 128x256 tiles (B maps keep 128-row boxes: two per stage)
+  const bool persist = H && tc_persist() && !p.accumulate && !(p.split_k > 1) && BN == 128;
+  const bool sub = H && use256 && !persist && tc_sub();          // 4 x 48 KB ring of 32-wide k sub-blocks
   int CL = (!H && BN == 128 && p.N > 128 && !use256) ? tc_cluster() : 1;       // A-multicast groups need >= 2 N tiles
   if (CL == 4 && p.N <= 384) CL = 2;
   const int a_box = TC_BM / CL;
@@ -1697,8 +1763,8 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   unsigned* oflag = (H && reg) ? reg->flag : nullptr;
   char* wsp = ws + TC_WS_HEAD;
   if (va.ok) {
-    if ((rc = make_view_map(&ah, va.hi, a_rows, a_cols, va.ldp, p.a_trans ? BK : a_box, p.a_trans != 0, H)) ||
-        (rc = make_view_map(&al, va.lo, a_rows, a_cols, va.ldp, p.a_trans ? BK : a_box, p.a_trans != 0, H))) return rc;
+    if ((rc = make_view_map(&ah, va.hi, a_rows, a_cols, va.ldp, p.a_trans ? BK : a_box, p.a_trans != 0, H, sub)) ||
+        (rc = make_view_map(&al, va.lo, a_rows, a_cols, va.ldp, p.a_trans ? BK : a_box, p.a_trans != 0, H, sub))) return rc;
   } else {
     float* Ahi = (float*)wsp; float* Alo = (float*)(wsp + align_up((int64_t)Mp * Kp * 4, 1024));
     if (!H) { if ((rc = prep_operand(p.A, p.lda, p.a_trans, p.M, p.K, Mp, Kp, Ahi, Alo, st))) return rc; }
@@ -1706,12 +1772,12 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
       if ((rc = materialize_h(p.A, p.lda, a_rows, a_cols, p.a_trans ? Kp : Mp, p.a_trans ? Mp : Kp, Ahi, Alo, t_amax[0], t_scale[0], nullptr, t_pred[0], oflag, st, reg ? TOP_SITE : TOP_EXACT))) return rc;
       va.scale = t_scale[0];
     }
-    if (!p.a_trans) { if ((rc = make_map(&ah, Ahi, Mp, Kp, a_box, false, H)) || (rc = make_map(&al, Alo, Mp, Kp, a_box, false, H))) return rc; }
-    else            { if ((rc = make_map(&ah, Ahi, Kp, Mp, BK, true, H)) || (rc = make_map(&al, Alo, Kp, Mp, BK, true, H))) return rc; }
+    if (!p.a_trans) { if ((rc = make_map(&ah, Ahi, Mp, Kp, a_box, false, H, sub)) || (rc = make_map(&al, Alo, Mp, Kp, a_box, false, H, sub))) return rc; }
+    else            { if ((rc = make_map(&ah, Ahi, Kp, Mp, BK, true, H, sub)) || (rc = make_map(&al, Alo, Kp, Mp, BK, true, H, sub))) return rc; }
   }
   if (vb.ok) {
-    if ((rc = make_view_map(&bh, vb.hi, b_rows, b_cols, vb.ldp, p.b_trans ? BK : BN, p.b_trans != 0, H)) ||
-        (rc = make_view_map(&bl, vb.lo, b_rows, b_cols, vb.ldp, p.b_trans ? BK : BN, p.b_trans != 0, H))) return rc;
+    if ((rc = make_view_map(&bh, vb.hi, b_rows, b_cols, vb.ldp, p.b_trans ? BK : BN, p.b_trans != 0, H, sub)) ||
+        (rc = make_view_map(&bl, vb.lo, b_rows, b_cols, vb.ldp, p.b_trans ? BK : BN, p.b_trans != 0, H, sub))) return rc;
   } else {
     char* wb = wsp + 2 * align_up((int64_t)Mp * Kp * 4, 1024);
     float* Bhi = (float*)wb; float* Blo = (float*)(wb + align_up((int64_t)Np * Kp * 4, 1024));
@@ -1720,8 +1786,8 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
       if ((rc = materialize_h(p.B, p.ldb, b_rows, b_cols, p.b_trans ? Kp : Np, p.b_trans ? Np : Kp, Bhi, Blo, t_amax[1], t_scale[1], nullptr, t_pred[1], oflag, st, reg ? TOP_SITE : TOP_EXACT))) return rc;
       vb.scale = t_scale[1];
     }
-    if (!p.b_trans) { if ((rc = make_map(&bh, Bhi, Np, Kp, BN, false, H)) || (rc = make_map(&bl, Blo, Np, Kp, BN, false, H))) return rc; }
-    else            { if ((rc = make_map(&bh, Bhi, Kp, Np, BK, true, H)) || (rc = make_map(&bl, Blo, Kp, Np, BK, true, H))) return rc; }
+    if (!p.b_trans) { if ((rc = make_map(&bh, Bhi, Np, Kp, BN, false, H, sub)) || (rc = make_map(&bl, Blo, Np, Kp, BN, false, H, sub))) return rc; }
+    else            { if ((rc = make_map(&bh, Bhi, Kp, Np, BK, true, H, sub)) || (rc = make_map(&bl, Blo, Kp, Np, BK, true, H, sub))) return rc; }
   }
   (void)MNB;
   TcEpi e;
@@ -1779,12 +1845,13 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   const bool amn = p.a_trans != 0, bmn = p.b_trans != 0;
   if (H) {
     // non-split GEMMs with N > 64: persistent ping-pong kernel (128x128 tiles; the B maps already have 128-row boxes)
-    if (tc_persist() && !p.accumulate && splits == 1 && BN == 128) return launch_tcp_major(amn, bmn, ah, al, bh, bl, e, st);
-    if (use256) return launch_tc256_major<true>(amn, bmn, ah, al, bh, bl, e, splits, st);
+    if (persist) return launch_tcp_major(amn, bmn, ah, al, bh, bl, e, st);
+    if (use256 && sub) return launch_tc256_major<true, true>(amn, bmn, ah, al, bh, bl, e, splits, st);
+    if (use256) return launch_tc256_major<true, false>(amn, bmn, ah, al, bh, bl, e, splits, st);
     if (BN == 128) return launch_tc_major<128, 3, 1, true>(amn, bmn, ah, al, bh, bl, e, splits, st);
     return launch_tc_major<64, 2, 1, true>(amn, bmn, ah, al, bh, bl, e, splits, st);      // 2 stages = 97 KB: two CTAs per SM hide each other's latencies
   }
-  if (use256) return launch_tc256_major<false>(amn, bmn, ah, al, bh, bl, e, splits, st);
+  if (use256) return launch_tc256_major<false, false>(amn, bmn, ah, al, bh, bl, e, splits, st);
   if (BN == 128 && CL == 4) return launch_tc_major<128, 3, 4, false>(amn, bmn, ah, al, bh, bl, e, splits, st);
   if (BN == 128 && CL == 2) return launch_tc_major<128, 3, 2, false>(amn, bmn, ah, al, bh, bl, e, splits, st);
   if (BN == 128) return launch_tc_major<128, 3, 1, false>(amn, bmn, ah, al, bh, bl, e, splits, st);

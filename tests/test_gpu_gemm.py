@@ -177,6 +177,20 @@ def _persistent_cases(a_trans, b_trans, ops):
     assert float((cs.double() - ref.sum(0)).abs().max() / ref.sum(0).abs().max()) < 1e-5
 
 
+@pytest.mark.parametrize('a_trans,b_trans', [(False, False), (False, True), (True, False), (True, True)])
+def test_tc_wide_tiles_sub_block_ring(a_trans, b_trans):
+    """ASE_TC_SUB=1 makes the 128x256 FP16 kernel stream 32-wide k sub-blocks through a 4 x 48 KB ring (K-major SWIZZLE_64B rows,
+    MN-major 32-row boxes) instead of 64-wide k-blocks through 2 x 96 KB (an opt-in experiment: correct, not faster)."""
+    import os
+    os.environ['ASE_TC_SUB'] = '1'
+    try:
+        _run(300, 1400, 317, a_trans, b_trans, 2, lda_pad=3, tol=1e-5)
+        _run(512, 1024, 2048, a_trans, b_trans, 2, mask_mode=1, tol=1e-5)
+        _run(1024, 512, 4096, True, True, 2, accumulate=True, split_k=5, tol=3e-5)
+    finally:
+        del os.environ['ASE_TC_SUB']
+
+
 def test_tc_fp16_planes_dynamic_range():
     """Backend 2 scales every tensor by a power of two before the FP16 hi/lo split: gradient-sized (1e-9) and large (1e+6)
     operands, and a tensor whose entries span 7 decades, must come out as accurately as O(1) ones."""
