@@ -97,6 +97,18 @@ def _make_agent(torch, rank, world, state_source, seed):
     return agent, env
 
 
+def _plane_flags(agent):
+    """gemm_backend 2: sticky scale-miss flags of the learner (0 = fine); a miss is reported in the JSON line and on stderr."""
+    import ctypes as C
+    from ase_b200 import lib as L
+    f = C.c_int(0)
+    import torch
+    L.check(L.lib.ase_learner_plane_status(agent.model._h, C.byref(f), torch.cuda.current_stream().cuda_stream), 'ase_learner_plane_status')
+    if f.value:
+        sys.stderr.write(f"WARNING: FP16 operand-plane scale miss (flags {f.value}) -- the flagged updates are not fp32-accurate\n")
+    return int(f.value)
+
+
 def _timed_epochs(torch, agent, steps, world, d2h=False):
     """barrier + synchronize on both sides, CUDA events on the launching (current) stream, max over ranks."""
     import torch.distributed as dist
@@ -146,6 +158,7 @@ def run_ours(args):
     L.lib.ase_gemm_tc_profile(0)
     launches = L.launch_count() - launches0
     play_t, upd_t, _ = agent.epoch_times()
+    plane_flags = _plane_flags(agent)      # FP16 operand-plane scale misses during the warm-up / timed epochs (read outside the timed region)
     tr = {k: float(v) for k, v in zip(L.TR_NAMES, agent._tr_buf[-1].tolist())}
     env_steps = args.steps * NUM_ENVS * HORIZON * world
     value = env_steps / secs
@@ -158,6 +171,7 @@ def run_ours(args):
         agent.update_epoch(); agent.train_epoch()
     e2e_secs, host = _timed_epochs(torch, agent, args.steps, world, d2h=True)
     e2e_value = env_steps / e2e_secs
+    plane_flags |= _plane_flags(agent)
     h2d = env.h2d_bytes_per_step * HORIZON
     d2h = host[0].numel() * 4 if host else 0
     del agent, env
@@ -203,6 +217,7 @@ def run_ours(args):
                              "(backend 2), 1/6 with TF32 planes (backend 1)",
                      "learner_tflops_algorithmic": nmb * FLOP_PER_MINIBATCH / 1e12 / (upd_t * args.steps) if upd_t > 0 else None},
         "split": {"play_time_s_last_step": play_t, "update_time_s_last_step": upd_t},
+        "plane_status": plane_flags,      # ase_learner_plane_status after both runs: 0 = every FP16 plane scale prediction held
         "train_result_last": tr,
     }
     if world == 1:
