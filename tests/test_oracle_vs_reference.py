@@ -81,3 +81,42 @@ def test_calc_gradients_live_ase():
                 continue
             assert torch.allclose(prm.grad, grads[k], rtol=1e-4, atol=1e-7), k
             assert torch.allclose(prm.detach(), st.p[k], rtol=1e-6, atol=1e-7), k
+
+
+def test_dataset_and_replay_buffer_host_logic_matches_reference_classes():
+    """SURVEY 8f row 1 host logic, live against the reference's own classes on CPU: learning/amp_datasets.py AMPDataset (global
+    permutation, contiguous slices, reshuffle when exhausted) and learning/replay_buffer.py ReplayBuffer (ring store with wrap-around,
+    permutation sampling, modulo while the buffer is not full) produce the SAME row sequences as ase_b200's mirrors under one seed."""
+    import ref_harness as rh
+    rh._setup_path()
+    from learning.amp_datasets import AMPDataset as RefDataset
+    from learning.replay_buffer import ReplayBuffer as RefReplay
+    from ase_b200.agent import AMPDataset
+    from ase_b200.replay_buffer import ReplayBuffer
+    B, mb = 96, 32
+    x = torch.arange(B, dtype=torch.float32)
+    torch.manual_seed(5)
+    ref = RefDataset(B, mb, False, False, 'cpu', 4)
+    ref.update_values_dict({'x': x})
+    ref_seq = [ref._get_item(i)['x'].clone() for _ in range(3) for i in range(len(ref))]
+    torch.manual_seed(5)
+    mine = AMPDataset(B, mb, 'cpu')
+    mine.update_values_dict({'x': x})
+    my_seq = [x[mine.sample_indices(i)] for _ in range(3) for i in range(len(mine))]
+    assert len(ref) == len(mine) == 3 and all(torch.equal(a, b) for a, b in zip(ref_seq, my_seq))
+
+    torch.manual_seed(9)
+    r = RefReplay(50, 'cpu')
+    ref_out = []
+    g = torch.Generator().manual_seed(1)
+    chunks = [torch.randn(n, 3, generator=g) for n in (20, 20, 20, 7, 50, 13)]       # fills, wraps around, exact-size store
+    for c in chunks:
+        r.store({'amp_obs': c})
+        ref_out.append(r.sample(16)['amp_obs'].clone())
+    torch.manual_seed(9)
+    m = ReplayBuffer(50, 'cpu')
+    for c, ro in zip(chunks, ref_out):
+        m.store({'amp_obs': c})
+        idx = m.sample_indices(16)
+        assert torch.equal(m.rows('amp_obs', idx), ro)
+    assert m.get_total_count() == r.get_total_count() and m.get_buffer_size() == r.get_buffer_size()
