@@ -1718,7 +1718,7 @@ static int make_view_map(CUtensorMap* tm, const void* base, int rows, int cols, 
 int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   const bool H = p.backend == 2;             // scaled FP16 hi/lo planes instead of TF32 ones
   if (reg && reg->f16 != H) { set_error("tcgen05 GEMM: plane registry format does not match backend %d", p.backend); return ASE_ERR_INVALID; }
-  const int BK = H ? 64 : 32, MNB = H ? 64 : 32;
+  const int BK = H ? 64 : 32;
   const int BN = (p.N > 64) ? 128 : 64;
   const bool use256 = tc_tile256() && p.N >= 384;               // 128x256 tiles (B maps keep 128-row boxes: two per stage)
   const bool persist = H && tc_persist() && !p.accumulate && !(p.split_k > 1) && BN == 128;
@@ -1789,7 +1789,6 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
     if (!p.b_trans) { if ((rc = make_map(&bh, Bhi, Np, Kp, BN, false, H, sub)) || (rc = make_map(&bl, Blo, Np, Kp, BN, false, H, sub))) return rc; }
     else            { if ((rc = make_map(&bh, Bhi, Kp, Np, BK, true, H, sub)) || (rc = make_map(&bl, Blo, Kp, Np, BK, true, H, sub))) return rc; }
   }
-  (void)MNB;
   TcEpi e;
   e.C = p.C; e.ldc = p.ldc; e.M = p.M; e.N = p.N; e.K = p.K; e.alpha = p.alpha; e.bias = p.bias; e.act = p.act;
   e.mask_src = p.mask_src; e.ldm = p.ldm; e.mask_mode = p.mask_src ? p.mask_mode : 0; e.accumulate = p.accumulate;
