@@ -124,6 +124,18 @@ def gen_calc_gradients():
     print('calc_grad_amp_cfg', r['steps'][-1]['scalars'])
 
 
+def gen_calc_gradients_full():
+    """BASELINE configs 3 and 2 at the benchmarked size (B = 16384, B_amp = 4096, full networks): two consecutive calls of the
+    reference's own ASEAgent / AMPAgent.calc_gradients (SURVEY.md 8c "... and at full size").  Sampled gradients / parameters,
+    full gradient norms, all scalars and the RMS state are stored (a few hundred kB)."""
+    r = _run_steps('ase', {}, {}, B=16384, Ba=4096, nsteps=2, seed=17, full=False)
+    torch.save(r, os.path.join(OUT, 'calc_grad_ase_full.pt'))
+    print('calc_grad_ase_full', r['steps'][-1]['scalars'])
+    r = _run_steps('amp', {}, {}, B=16384, Ba=4096, nsteps=2, seed=19, full=False)
+    torch.save(r, os.path.join(OUT, 'calc_grad_amp_full.pt'))
+    print('calc_grad_amp_full', r['steps'][-1]['scalars'])
+
+
 def gen_motion_lib():
     """The reference's own MotionLib.get_motion_state + build_amp_observations on synthetic clip tables (the object is
     assembled field by field so no .npy clip has to travel; the real loader only fills these same tensors)."""
@@ -232,6 +244,10 @@ def gen_rollout_math():
 if __name__ == '__main__':
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1:           # python oracle/gen_golden.py gen_calc_gradients_full gen_rollout ...
+        for name in sys.argv[1:]:
+            globals()[name]()
+        sys.exit(0)
     gen_obs()
     gen_motion_lib()
     gen_heading()

@@ -34,7 +34,8 @@ def test_rollout_math_matches_reference_golden():
     assert torch.allclose(0.5 * fx['disc_r'] + 0.5 * fx['enc_r'], fx['combined'], rtol=1e-6, atol=1e-7)
 
 
-@pytest.mark.parametrize('name', ['calc_grad_ase_small.pt', 'calc_grad_ase_cfg1.pt', 'calc_grad_amp_cfg.pt'])
+@pytest.mark.parametrize('name', ['calc_grad_ase_small.pt', 'calc_grad_ase_cfg1.pt', 'calc_grad_amp_cfg.pt',
+                                  'calc_grad_ase_full.pt', 'calc_grad_amp_full.pt'])     # *_full: B = 16384, B_amp = 4096 (the benchmarked size)
 def test_calc_gradients_matches_reference_golden(name):
     meta, steps, shapes, P = G.calc_grad_case(name)
     st = O.LearnerState(P, 253, 1400, meta['kind'])
