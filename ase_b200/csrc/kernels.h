@@ -80,6 +80,7 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg = nullpt
 bool gemm_tc_supported(const AseGemmParams& p);
 int64_t gemm_tc_workspace_bytes(int M, int N, int K);
 int gemm_tc_tile_n(int N);      // N extent of the output tile the tcgen05 backend will use for this N
+bool gemm_tc_pair_candidate(int backend, int M, int N);   // this [M, N] output goes to the persistent CTA-pair kernel (256 x 256 tiles, 74 pair slots)
 int gemm_dispatch(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg = nullptr);    // picks the backend named in p.backend (falls back to SIMT for shapes tc rejects)
 
 // ------------------------------------------------------------------ loss-side accumulators (doubles)

@@ -310,11 +310,14 @@ struct G {
     p.A = dZ; p.lda = ldz; p.a_trans = 1; p.B = X; p.ldb = ldx; p.b_trans = 1; p.C = GR + l.w; p.ldc = l.in;
     p.M = l.out; p.N = l.in; p.K = M; p.accumulate = 1;
     // split-K so that tiles x splits fills whole waves of the 148 SMs; every extra split adds one RED pass over dW
-    const int tiles = ceil_div(l.out, 128) * ceil_div(l.in, L.cfg.gemm_backend >= 1 ? gemm_tc_tile_n(l.in) : 128);
+    const bool pair = gemm_tc_pair_candidate(L.cfg.gemm_backend, l.out, l.in);     // 256 x 256 tiles on 74 CTA pairs
+    const int tiles = pair ? ceil_div(l.out, 256) * ceil_div(l.in, 256)
+                           : ceil_div(l.out, 128) * ceil_div(l.in, L.cfg.gemm_backend >= 1 ? gemm_tc_tile_n(l.in) : 128);
+    const int slots = pair ? 74 : 148;
     const int smax = max(1, min(16, M / 1024));
     int best = 1; double best_cost = 1e30;
     for (int s = 1; s <= smax; ++s) {
-      const double waves = (double)ceil_div((int64_t)tiles * s, 148);
+      const double waves = (double)ceil_div((int64_t)tiles * s, slots);
       const double cost = waves / s * (1.0 + 0.03 * s);
       if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
     }

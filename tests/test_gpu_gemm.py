@@ -227,3 +227,75 @@ def test_tc_accuracy_is_fp32_class_not_tf32(tc):
     # tensor core accumulating across all of K left a one-sided 0.006 (truncating accumulator); with the k-block partials
     # accumulated outside in fp32 RN the error is a few ulps of 1025 (1.2e-4 each).
     assert float((C.double() - ref).abs().max()) < 1.5e-3
+
+
+# ------------------------------------------------------------------------------------------------ persistent CTA-pair kernel (gemm_tc2.cu)
+def _pair(on):
+    import os
+    os.environ['ASE_TC_PAIR'] = '1' if on else '0'
+
+
+@pytest.mark.parametrize('a_trans,b_trans', [(False, False), (False, True), (True, False), (True, True)])
+def test_tc_pair_kernel_many_items_per_pair(a_trans, b_trans):
+    """Backend 2, N >= 384, M % 128 == 0 runs on the persistent cta_group::2 kernel (256 x 256 tiles, 74 CTA pairs).  More work items than
+    pairs: every pair walks several tiles, so the ring / main / correction barriers cross tile boundaries with both parities (odd and
+    even k-block counts), the last pair-tile of an odd 128-row tile count has an idle peer, N tails are zero-filled by TMA."""
+    _pair(True)
+    _run(8192, 1024, 192, a_trans, b_trans, 2, bias=True, act=1, tol=1e-5)        # 128 items, 3 k-blocks each
+    _run(16384, 512, 64, a_trans, b_trans, 2, tol=1e-5)                            # 128 items, 1 k-block each
+    _run(4992, 1400, 256, a_trans, b_trans, 2, bias=True, tol=1e-5)                # 39 x 128 rows (odd), 6 column tiles with a 120-column tail
+    _run(2944, 904, 130, a_trans, b_trans, 2, lda_pad=3, tol=1e-5)                 # ragged K (zero padded), N % 8 == 0 tail, unaligned operand ld
+    _run(128, 384, 640, a_trans, b_trans, 2, bias=True, act=1, tol=1e-5)                # a single item: peer CTA has no rows
+    _run(32768, 1024, 1024, a_trans, b_trans, 2, tol=1e-5)                         # the benchmarked forward / dX shape
+
+
+def test_tc_pair_kernel_agrees_with_one_tile_kernels():
+    """Both kernel families form the same products; they differ only in where the tensor core's truncating adds happen (the pair kernel
+    drains main + correction terms of every k-block together, the 128x256 kernel keeps the correction terms in TMEM across K): the
+    results must agree to a few fp32 ulps of the output scale -- far inside the distance of either from fp64."""
+    from ase_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    for (M, N, K, bt) in ((1024, 1024, 1024, False), (768, 1400, 320, True), (2048, 512, 4096, False)):
+        A = torch.randn(M, K, generator=g).cuda()
+        B = (torch.randn(K, N, generator=g) if bt else torch.randn(N, K, generator=g)).cuda()
+        bias = torch.randn(N, generator=g).cuda()
+        _pair(True); c1 = ops.gemm(A, B, b_trans=bt, bias=bias, act=1, backend=2)
+        _pair(False); c0 = ops.gemm(A, B, b_trans=bt, bias=bias, act=1, backend=2)
+        _pair(True)
+        torch.cuda.synchronize()
+        ref = torch.relu(A.double() @ (B.double() if bt else B.double().t()) + bias.double())
+        scale = float(ref.abs().max())
+        assert float((c0 - c1).abs().max()) <= 2e-6 * scale, (M, N, K, bt, float((c0 - c1).abs().max()) / scale)
+        e1, e0 = float((c1.double() - ref).abs().max()) / scale, float((c0.double() - ref).abs().max()) / scale
+        assert e1 <= max(2.0 * e0, 2e-6), (M, N, K, bt, e1, e0)
+
+
+def test_tc_pair_kernel_split_k_colsum_bits():
+    from ase_b200 import ops
+    _pair(True)
+    _run(1024, 1024, 32768, True, True, 2, accumulate=True, split_k=9, tol=2e-5)     # the dW shape: 16 pair tiles x 9 splits on 74 pairs
+    _run(512, 1400, 12288, True, True, 2, accumulate=True, split_k=4, tol=2e-5)
+    _run(1024, 512, 4096, True, True, 2, accumulate=True, split_k=1, tol=2e-5)       # accumulate without split
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn(6016, 320, generator=g).cuda(); B = torch.randn(768, 320, generator=g).cuda()
+    cs = torch.zeros(768, device='cuda')
+    C = ops.gemm(A, B, backend=2, colsum_out=cs)                                      # 47 x 128 rows, fused column sums (shuffle butterfly)
+    ref = A.double() @ B.double().t()
+    assert float((C.double() - ref).abs().max() / ref.abs().max()) < 1e-5
+    assert float((cs.double() - ref.sum(0)).abs().max() / ref.sum(0).abs().max()) < 1e-5
+    # activity bits out (thread = row layout: one 16-byte store of 4 words per row) and bits in
+    for (M, N, K) in ((1024, 1024, 128), (640, 1400, 96), (256, 416, 64)):
+        A = torch.randn(M, K, generator=g).cuda(); W = torch.randn(N, K, generator=g).cuda(); bias = torch.randn(N, generator=g).cuda()
+        bits = torch.zeros(M, (N + 31) // 32, dtype=torch.int32, device='cuda')
+        Y = ops.gemm(A, W, bias=bias, act=1, backend=2, relu_bits_out=bits)
+        cols = torch.arange(N, device='cuda')
+        unpacked = ((bits[:, cols // 32] >> (cols % 32)) & 1).bool()
+        assert torch.equal(unpacked, Y > 0), (M, N, K)
+        if N % 32:
+            assert int((bits[:, -1].long() & 0xFFFFFFFF >> (N % 32) << (N % 32)).abs().max()) == 0
+        dZ = torch.randn(M, 512, generator=g).cuda(); W2 = torch.randn(512, N, generator=g).cuda()
+        cs2 = torch.zeros(N, device='cuda')
+        a = ops.gemm(dZ, W2, b_trans=True, mask_src=Y, mask_mode=1, backend=2, mask_bits=bits, colsum_out=cs2)      # pair kernel (bit mask)
+        ref = (dZ.double() @ W2.double()) * (Y > 0).double()
+        assert float((a.double() - ref).abs().max() / ref.abs().max()) < 1e-5, (M, N, K)
+        assert float((cs2.double() - ref.sum(0)).abs().max() / ref.sum(0).abs().max()) < 2e-5, (M, N, K)
