@@ -17,6 +17,7 @@ Differences from the reference that do not change results:
     indices instead of materialising two [batch, 1400] copies per epoch (same rows, same order);
   * the diversity loss' second actor pass is batched with the first (2B rows)."""
 import math
+import os
 import time
 
 import numpy as np
@@ -83,7 +84,7 @@ class CommonAgent:
         self.normalize_input = config['normalize_input']
         self.normalize_value = config.get('normalize_value', False)
         self.normalize_advantage = config['normalize_advantage']
-        assert self.normalize_input and self.normalize_value, "the engine implements the shipped configs (normalize_* True)"
+        assert self.normalize_input and self.normalize_value and self.normalize_advantage, "the engine implements the shipped configs (normalize_* True)"
         self.gamma, self.tau = config['gamma'], config['tau']
         self.e_clip = config['e_clip']
         assert not config.get('clip_value', False) and not config.get('truncate_grads', False), "clip_value/truncate_grads are False in every shipped config"
@@ -91,6 +92,11 @@ class CommonAgent:
         assert config.get('lr_schedule', 'constant') in ('constant', None)
         self.max_epochs = config.get('max_epochs', 1e6)
         self.save_freq = config.get('save_frequency', 0)
+        self._save_intermediate = config.get('save_intermediate', False)
+        # rl_games A2CBase: <train_dir>/<experiment name>/nn/<config name>.pth (common_agent.py:92)
+        self.train_dir = config.get('train_dir', 'runs')
+        self.experiment_name = config.get('full_experiment_name') or (config.get('name', base_name) + time.strftime('_%d-%H-%M-%S'))
+        self.nn_dir = os.path.join(self.train_dir, self.experiment_name, 'nn')
         self.print_stats = config.get('print_stats', True)
         self.writer = config.get('writer', None)          # optional tensorboardX-like object with add_scalar(tag, value, step)
         self.clip_actions = config.get('clip_actions', True)
@@ -110,6 +116,10 @@ class CommonAgent:
         self.has_central_value = False
         self._eval_mode = False
         self._timing = {}
+        # rollout flavour: 'device_rollout' (default True) uses the mask-driven zero-sync step when the env offers reset_done();
+        # 'rollout_graph' (default True) additionally captures the whole rollout in one CUDA graph
+        self._device_rollout = bool(config.get('device_rollout', True))
+        self._rollout_graph_enabled = bool(config.get('rollout_graph', True))
 
     # ------------------------------------------------------------------ construction helpers
     def _load_config_params(self, config):
@@ -172,13 +182,35 @@ class CommonAgent:
         return st
 
     def set_full_state_weights(self, w):
+        """common_agent.py:157-170."""
         self.model.load_state_dict(w['model'])
         self.model.set_stats_weights(w)
         self.epoch_num = w.get('epoch', 0)
         self.frame = w.get('frame', 0)
+        self.last_mean_rewards = w.get('last_mean_rewards', -100500)
         if 'optimizer' in w:
             self._load_optimizer_state_dict(w['optimizer'])
         self.model.params_changed()
+        if hasattr(self.vec_env, 'set_env_state'):
+            self.vec_env.set_env_state(w.get('env_state', None))
+
+    def save(self, fn):
+        """rl_games A2CBase.save -> torch_ext.save_checkpoint(fn, get_full_state_weights()): writes fn + '.pth' (common_agent.py:141-150)."""
+        d = os.path.dirname(fn)
+        if d:
+            os.makedirs(d, exist_ok=True)
+        state = self.get_full_state_weights()
+        state = {k: ({kk: (vv.detach().cpu().clone() if torch.is_tensor(vv) else vv) for kk, vv in v.items()} if isinstance(v, dict) and k != 'optimizer' else v)
+                 for k, v in state.items()}
+        state['optimizer']['state'] = {i: {kk: (vv.cpu() if torch.is_tensor(vv) else vv) for kk, vv in st.items()} for i, st in state['optimizer']['state'].items()}
+        torch.save(state, fn + '.pth')
+        return fn + '.pth'
+
+    def restore(self, fn):
+        """rl_games A2CBase.restore -> set_full_state_weights(torch_ext.load_checkpoint(fn)): what run.py / the Runner call for --checkpoint
+        and what HRLAgent does with the LLC checkpoint (hrl_agent.py:202-213).  Accepts the reference's own .pth files."""
+        w = torch.load(fn, map_location='cpu', weights_only=False)
+        self.set_full_state_weights(w)
 
     def _optimizer_state_dict(self):
         """torch.optim.Adam.state_dict() layout: param index 0 is the frozen sigma (no state), 1.. follow parameters()."""
@@ -222,6 +254,11 @@ class CommonAgent:
         self.current_rewards = torch.zeros(N, 1, device=dev)
         self.current_lengths = torch.zeros(N, device=dev)
         self.dones = torch.ones(N, dtype=torch.uint8, device=dev)
+        self._no_dones = torch.zeros(N, dtype=torch.uint8, device=dev)
+        self._episode_meter = torch.zeros(3, device=dev)       # finished episodes: sum of rewards, sum of lengths, count (game_rewards / game_lengths)
+        # device RNG state of the rollout kernels: {seed, call counter}
+        self._rng = torch.tensor([int(self.config.get('seed', 0) or 0) * 1000003 + 12345 + self.rank, 0], dtype=torch.int64, device=dev)
+        self._rollout_graph, self._rollout_warm = None, 0
 
     def env_reset(self, env_ids=None):
         obs = self.vec_env.reset(env_ids)
@@ -243,11 +280,18 @@ class CommonAgent:
     def _rand_action_probs_tensor(self):
         return None
 
+    # RNG hooks of the reference-order rollout (tests inject the reference's own draws here)
+    def _draw_normal(self, shape):
+        return torch.randn(shape, device=self.ppo_device, dtype=torch.float32)
+
+    def _draw_bernoulli(self, probs):
+        return torch.bernoulli(probs)
+
     def get_action_values(self, obs_dict, latents=None, rand_action_probs=None):
         """ase_agent.py:117-148 / amp_agent.py:139-169 (eval mode): actor+critic forward, sample, eps-greedy mask."""
         mu, v = self.model.eval_actor_critic(obs_dict['obs'], latents)
-        noise = torch.randn(mu.shape, device=mu.device, dtype=torch.float32)
-        mask = None if rand_action_probs is None else torch.bernoulli(rand_action_probs)
+        noise = self._draw_normal(mu.shape)
+        mask = None if rand_action_probs is None else self._draw_bernoulli(rand_action_probs)
         actions, nlp, sig = ops.policy_sample(mu, self.model.sigma, noise, mask)
         values = self.model.value_mean_std(v, unnorm=True)
         res = {'actions': actions, 'neglogpacs': nlp, 'values': values, 'mus': mu, 'sigmas': sig}
@@ -263,16 +307,38 @@ class CommonAgent:
         pass
 
     def play_steps(self):
+        """common_agent.py:244-307 / amp_agent.py:61-137 / ase_agent.py:36-115.  Two implementations of the same step sequence:
+        the DEVICE rollout (no host sync: masks instead of nonzero() index lists, in-kernel Philox draws, optionally one CUDA graph for
+        the whole rollout) when the env offers a mask-driven reset (`reset_done`), else the reference-order rollout (index lists, eager
+        torch draws) that any rl_games vec-env works with."""
         self.set_eval()
+        if self._device_rollout and hasattr(self.vec_env, 'reset_done'):
+            self._play_steps_device()
+        else:
+            self._play_steps_reference()
         eb = self.experience_buffer
-        done_indices = None
+        mb_rewards, extra = self._final_rewards()
+        mb_advs = ops.discount_values(eb['dones'], eb['values'], mb_rewards, eb['next_values'], self.gamma, self.tau)
+        mb_returns = mb_advs + eb['values']
+        batch_dict = {k: swap_and_flatten01(eb[k]) for k in self.tensor_list}
+        batch_dict['returns'] = swap_and_flatten01(mb_returns)
+        batch_dict['played_frames'] = self.batch_size
+        for k, v in extra.items():
+            batch_dict[k] = swap_and_flatten01(v)
+        return batch_dict
+
+    def _play_steps_reference(self):
+        eb = self.experience_buffer
+        # amp_agent.py:64 / ase_agent.py:40 `done_indices = []`: the first step of a rollout resets NOTHING (vec_env.reset(None) would
+        # reset every env, humanoid.py:125-128, and ASEAgent.env_reset(None) every latent)
+        done_indices = torch.empty(0, dtype=torch.long, device=self.ppo_device)
         for n in range(self.horizon_length):
             self.obs = self.env_reset(done_indices)
             eb['obses'][n] = self.obs['obs']
             self._pre_action()
             res = self.get_action_values(self.obs, self._latents(), self._rand_action_probs_tensor())
             for k in self.update_list:
-                eb[k][n] = res[k] if k != 'values' else res[k]
+                eb[k][n] = res[k]
             self.obs, rewards, self.dones, infos = self.env_step(res['actions'])
             eb['rewards'][n] = rewards
             eb['next_obses'][n] = self.obs['obs']
@@ -285,18 +351,75 @@ class CommonAgent:
             self.current_rewards += rewards
             self.current_lengths += 1
             done_indices = self.dones.nonzero(as_tuple=False)[:, 0]      # (host sync, as in the reference: ase_agent.py:78-79)
+            self._episode_meter[0] += self.current_rewards[done_indices].sum(); self._episode_meter[1] += self.current_lengths[done_indices].sum()
+            self._episode_meter[2] += done_indices.numel()
             not_dones = 1.0 - self.dones.float()
             self.current_rewards = self.current_rewards * not_dones.unsqueeze(1)
             self.current_lengths = self.current_lengths * not_dones
-        mb_rewards, extra = self._final_rewards()
-        mb_advs = ops.discount_values(eb['dones'], eb['values'], mb_rewards, eb['next_values'], self.gamma, self.tau)
-        mb_returns = mb_advs + eb['values']
-        batch_dict = {k: swap_and_flatten01(eb[k]) for k in self.tensor_list}
-        batch_dict['returns'] = swap_and_flatten01(mb_returns)
-        batch_dict['played_frames'] = self.batch_size
-        for k, v in extra.items():
-            batch_dict[k] = swap_and_flatten01(v)
-        return batch_dict
+
+    # ------------------------------------------------------------------ device rollout
+    def _device_latent_step(self, done_mask, n):
+        pass
+
+    def _rollout_loop(self):
+        """One rollout as a fixed sequence of device work: nothing here reads a device value on the host."""
+        eb, N = self.experience_buffer, self.num_actors
+        logstd, vrms = self.model.sigma, self.model.value_mean_std
+        probs = self._rand_action_probs_tensor()
+        mask_out = eb.get('rand_action_mask')
+        done_mask = self._no_dones
+        inj = getattr(self, '_inject', None)           # tests: per-env draw tables [H, N, ...] instead of the in-kernel generator
+        for n in range(self.horizon_length):
+            obs = self.vec_env.reset_done(done_mask)                   # step 0 resets nothing (done_indices = [] in the reference)
+            self.obs = {'obs': obs}
+            eb['obses'][n].copy_(obs)
+            self._device_latent_step(done_mask, n)
+            lat = self._latents()
+            mu, v = self.model.eval_actor_critic(obs, lat)
+            eb['mus'][n].copy_(mu)
+            ops.policy_sample_rng(mu, logstd, probs, self._rng, 0, eb['actions'][n], eb['neglogpacs'][n], eb['sigmas'][n],
+                                  None if mask_out is None else mask_out[n], noise=None if inj is None else inj['noise'][n],
+                                  mask=None if (inj is None or probs is None) else inj['mask'][n])
+            vrms(v, unnorm=True, out=eb['values'][n])
+            self.obs, rewards, self.dones, infos = self.env_step(eb['actions'][n])
+            eb['rewards'][n].copy_(rewards)
+            eb['next_obses'][n].copy_(self.obs['obs'])
+            eb['dones'][n].copy_(self.dones)
+            self._extra_buffer_writes_device(n, infos)
+            _, vn = self.model.eval_actor_critic(self.obs['obs'], self._latents(), want_value=True, want_actor=False)
+            ops.rollout_post_step(rewards, eb['dones'][n], infos['terminate'], vn, vrms, eb['next_values'][n], self.current_rewards,
+                                  self.current_lengths, self._episode_meter, self._rng)
+            done_mask = eb['dones'][n]
+
+    def _extra_buffer_writes_device(self, n, infos):
+        pass
+
+    def _play_steps_device(self):
+        if not self._rollout_graph_enabled:
+            self._rollout_loop()
+            return
+        if self._rollout_graph is None:
+            if self._rollout_warm < 2:             # the learner calibrates its FP16 plane scales on its first calls: capture a settled schedule
+                self._rollout_warm += 1
+                self._rollout_loop()
+                return
+            g = torch.cuda.CUDAGraph()
+            try:
+                with torch.cuda.graph(g):
+                    self._rollout_loop()
+            except Exception as ex:     # a vec-env whose step cannot be captured: keep the eager device rollout
+                import sys
+                sys.stderr.write(f"ase_b200: CUDA-graph capture of the rollout failed ({type(ex).__name__}: {ex}); running it eagerly\n")
+                self._rollout_graph_enabled = False
+                torch.cuda.synchronize()
+                self._rollout_loop()
+                return
+            self._rollout_graph = g
+            g.replay()                              # capture does not execute
+            return
+        self._rollout_graph.replay()
+        if hasattr(self.vec_env, 'on_graph_replay'):
+            self.vec_env.on_graph_replay(self.horizon_length)
 
     def _final_rewards(self):
         return self.experience_buffer['rewards'], {}
@@ -352,7 +475,7 @@ class CommonAgent:
             scale = allreduce_grads(self.model.grads)       # one flat NCCL sum per minibatch (Horovod averaged: amp_agent.py:357-363)
         self.model.adam_step(grad_scale=scale)
         row = self._tr_buf[self._tr_i % self._tr_buf.shape[0]]
-        row.copy_(out['scalars'])
+        row[:out['scalars'].shape[0]].copy_(out['scalars'])
         self._tr_i += 1
         from .lib import TR_NAMES
         tr = {name: row[j] for j, name in enumerate(TR_NAMES)}
@@ -386,13 +509,14 @@ class CommonAgent:
         nmb = self.mini_epochs_num * len(self.dataset)
         if getattr(self, '_tr_buf', None) is None or self._tr_buf.shape[0] != nmb:
             from .lib import TR_COUNT
-            self._tr_buf = torch.zeros(nmb, TR_COUNT, device=self.ppo_device)
+            self._tr_buf = torch.zeros(nmb, TR_COUNT + 1, device=self.ppo_device)       # + the learner's plane-scale status
         self._tr_i = 0
         for _ in range(self.mini_epochs_num):
             for i in range(len(self.dataset)):
                 mb, idx = self._minibatch(i)
                 self.train_actor_critic(mb)
         self._post_update(batch_dict)
+        self.model.plane_flag_to(self._tr_buf[:, -1])
         ev[2].record()
         self._events = ev
         from .lib import TR_NAMES
@@ -430,7 +554,8 @@ class CommonAgent:
         # no per-epoch host sync -- the epoch's scalars and event timings come back through a pinned ring
         from .async_log import AsyncEpochLog
         from .lib import TR_NAMES
-        log = AsyncEpochLog(TR_NAMES, depth=4)
+        log = AsyncEpochLog(list(TR_NAMES) + ['plane_status'], depth=4)
+        self.last_mean_rewards = -100500
         self.epoch_log = []                       # [{'epoch', 'frames', 'scalars', 'play_time', 'update_time'}], an epoch or two behind
         total_time = 0.0
 
@@ -438,6 +563,11 @@ class CommonAgent:
             nonlocal total_time
             for r in recs:
                 r.pop('series', None)
+                # FP16 operand-plane scale status of the epoch (rides in the record: no extra sync).  A miss means the flagged updates
+                # were not fp32-accurate: stop right here instead of training on them
+                if r['scalars'].pop('plane_status', 0.0) != 0.0:
+                    raise RuntimeError(f"epoch {r['epoch']}: FP16 operand-plane scale miss -- a tensor's max moved by more than 2^9 up / 2^12 down between "
+                                       "two consecutive calls; rerun with gemm_backend=1 (restore() the last checkpoint)")
                 total_time += r.get('play_time', 0.0) + r.get('update_time', 0.0)
                 self.epoch_log.append(r)
                 if self.rank == 0 and self.print_stats and 'play_time' in r:
@@ -446,6 +576,7 @@ class CommonAgent:
                 if self.writer is not None:       # performance/* and losses/* scalars of common_agent.py:119-152,551-564
                     self._write_stats(r)
 
+        model_output_file = os.path.join(self.nn_dir, self.config.get('name', self.name))
         while True:
             epoch_num = self.update_epoch()
             self.train_epoch()
@@ -454,12 +585,16 @@ class CommonAgent:
             self.frame += self.curr_frames * self.rank_size
             consume(log.push(epoch_num, self._tr_buf, frames=self.curr_frames, events=tuple(self._events)))
             consume(log.poll())
-            if epoch_num >= self.max_epochs:
+            if self.rank == 0 and self.save_freq > 0 and epoch_num % self.save_freq == 0:      # common_agent.py:141-147
+                self.save(model_output_file)
+                if self._save_intermediate:
+                    self.save(model_output_file + '_' + str(epoch_num).zfill(8))
+            if epoch_num > self.max_epochs:                                                      # common_agent.py:149-152
                 consume(log.flush())
-                if self.model.cfg.gemm_backend == 2:
-                    self.model.plane_status()     # raises if an FP16 operand-plane scale was missed anywhere in the run
+                if self.rank == 0:
+                    self.save(model_output_file)
                 self.total_time = total_time
-                return -100500, epoch_num
+                return self.last_mean_rewards, epoch_num
 
     def _write_stats(self, r):
         """TensorBoard emission (common_agent.py:119-152, amp_agent.py:244-262) from an AsyncEpochLog record."""
@@ -524,6 +659,9 @@ class AMPAgent(CommonAgent):
     def _extra_buffer_writes(self, n, res, infos):
         self.experience_buffer['amp_obs'][n] = infos['amp_obs']
         self.experience_buffer['rand_action_mask'][n] = res['rand_action_mask']
+
+    def _extra_buffer_writes_device(self, n, infos):
+        self.experience_buffer['amp_obs'][n].copy_(infos['amp_obs'])       # (rand_action_mask is written by the sampling kernel)
 
     def _calc_amp_rewards(self, amp_obs, latents=None):
         """amp_agent.py:563-577 / ase_agent.py:395-411: disc (+enc) trunk over the whole rollout, then the reward kernels."""
@@ -628,9 +766,11 @@ class ASEAgent(AMPAgent):
     def _reset_latents(self, env_ids):
         self._ase_latents[env_ids] = self._sample_latents(len(env_ids))
 
+    def _draw_latent_steps(self, n):
+        return torch.randint(self._latent_steps_min, self._latent_steps_max, (n,), dtype=torch.int32, device=self.ppo_device)
+
     def _reset_latent_step_count(self, env_ids):
-        self._latent_reset_steps[env_ids] = torch.randint(self._latent_steps_min, self._latent_steps_max, (len(env_ids),),
-                                                          dtype=torch.int32, device=self.ppo_device)
+        self._latent_reset_steps[env_ids] = self._draw_latent_steps(len(env_ids))
 
     def env_reset(self, env_ids=None):
         obs = super().env_reset(env_ids)
@@ -650,12 +790,22 @@ class ASEAgent(AMPAgent):
         ids = new.nonzero(as_tuple=False).flatten()
         if ids.numel() > 0:
             self._reset_latents(ids)
-            self._latent_reset_steps[ids] += torch.randint(self._latent_steps_min, self._latent_steps_max, (ids.numel(),),
-                                                           dtype=torch.int32, device=self.ppo_device)
+            self._latent_reset_steps[ids] += self._draw_latent_steps(ids.numel())
 
     def _extra_buffer_writes(self, n, res, infos):
         super()._extra_buffer_writes(n, res, infos)
         self.experience_buffer['ase_latents'][n] = self._ase_latents
+
+    def _extra_buffer_writes_device(self, n, infos):
+        super()._extra_buffer_writes_device(n, infos)
+        self.experience_buffer['ase_latents'][n].copy_(self._ase_latents)
+
+    def _device_latent_step(self, done_mask, n):
+        """env_reset's latent part + _update_latents in one mask-driven kernel (ase_agent.py:329-381)."""
+        inj = getattr(self, '_inject', None)
+        ops.latent_update(self._ase_latents, self._latent_reset_steps, self.vec_env.env.task.progress_buf, done_mask,
+                          self._latent_steps_min, self._latent_steps_max, self._rng, 2,
+                          z_in=None if inj is None else inj['z'][n], steps_in=None if inj is None else inj['steps'][n])
 
     def _final_rewards(self):
         eb = self.experience_buffer
@@ -743,6 +893,9 @@ class HRLAgent(CommonAgent):
 
     def _extra_buffer_writes(self, n, res, infos):
         self.experience_buffer['disc_rewards'][n] = infos['disc_rewards']
+
+    def _extra_buffer_writes_device(self, n, infos):
+        self.experience_buffer['disc_rewards'][n].copy_(infos['disc_rewards'].reshape(-1, 1))
 
     def _final_rewards(self):
         """hrl_agent.py:150-152,243-249 _combine_rewards."""

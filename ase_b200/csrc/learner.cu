@@ -460,6 +460,26 @@ extern "C" int ase_learner_plane_status(AseLearner* l, int* flags, void* stream)
   return ASE_OK;
 }
 
+namespace ase {
+__global__ void plane_flag_to_kernel(const unsigned* __restrict__ flag, float* __restrict__ dst, int count, int64_t stride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) dst[(int64_t)i * stride] = flag ? (float)(*flag) : 0.0f;
+}
+}  // namespace ase
+extern "C" int ase_learner_plane_flag_to(AseLearner* l, float* dst, int count, int64_t stride, void* stream) {
+  ASE_CHECK_ARG(l && dst && count >= 0, "ase_learner_plane_flag_to: bad argument");
+  if (count == 0) return ASE_OK;
+  const unsigned* f = (l->reg && l->reg->f16) ? l->reg->flag : nullptr;
+  plane_flag_to_kernel<<<ceil_div(count, 128), 128, 0, (cudaStream_t)stream>>>(f, dst, count, stride);
+  ASE_LAUNCH_OK();
+  return ASE_OK;
+}
+extern "C" int ase_learner_plane_flag_clear(AseLearner* l, void* stream) {
+  ASE_CHECK_ARG(l != nullptr, "ase_learner_plane_flag_clear: null learner");
+  if (l->reg && l->reg->f16) ASE_CUDA_OK(cudaMemsetAsync(l->reg->flag, 0, sizeof(unsigned), (cudaStream_t)stream));
+  return ASE_OK;
+}
+
 extern "C" int ase_learner_calc_gradients(AseLearner* lp, const AseLearnerState* s, const AseMinibatch* mb, const AseTrainResult* out,
                                           void* stream) {
   ASE_CHECK_ARG(lp && s && mb && out, "calc_gradients: null argument");

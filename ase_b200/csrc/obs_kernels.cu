@@ -67,6 +67,7 @@ obs_build_kernel(AseObsBuildParams p, int obs_dim) {
   for (int idx = threadIdx.x; idx < ne * obs_dim; idx += OBS_THREADS) {
     const int e = idx / obs_dim, c = idx - e * obs_dim;
     const int env = p.env_ids ? p.env_ids[e0 + e] : (e0 + e);
+    if (p.env_mask && !p.env_mask[env]) continue;          // masked reset path: only the flagged envs are rewritten
     p.obs[(int64_t)env * p.obs_ld + c] = s_out[idx];
   }
 }
@@ -101,6 +102,7 @@ amp_obs_build_kernel(AseAmpObsBuildParams p, AmpTables tb) {
   float* s_new = s_hist + (S - 1) * F;   // [F]
   __shared__ float s_hq[4];
   const int env = p.env_ids ? p.env_ids[blockIdx.x] : blockIdx.x;
+  if (p.env_mask && !p.env_mask[env]) return;              // masked reset path (block-uniform)
   float* buf = p.amp_obs + (int64_t)env * S * F;
   if (p.shift_history) {
     for (int i = threadIdx.x; i < (S - 1) * F; i += AMP_THREADS) s_hist[i] = buf[i];
@@ -151,7 +153,9 @@ amp_obs_build_kernel(AseAmpObsBuildParams p, AmpTables tb) {
   }
   __syncthreads();
   for (int i = threadIdx.x; i < F; i += AMP_THREADS) buf[i] = s_new[i];
-  if (p.shift_history) {
+  if (p.fill_history) {       // reset (humanoid_amp.py:206-218 default-state path): the whole history := the current frame
+    for (int i = threadIdx.x; i < (S - 1) * F; i += AMP_THREADS) buf[F + i] = s_new[i % F];
+  } else if (p.shift_history) {
     for (int i = threadIdx.x; i < (S - 1) * F; i += AMP_THREADS) buf[F + i] = s_hist[i];
   }
 }
@@ -251,6 +255,7 @@ extern "C" int ase_amp_obs_build(const AseAmpObsBuildParams* p, void* stream) {
   ASE_CHECK_ARG(p->step_dim == 13 + 6 * p->num_joints + p->num_dofs + 3 * p->num_key_bodies,
                 "ase_amp_obs_build: step_dim %d inconsistent", p->step_dim);
   ASE_CHECK_ARG(p->hist_steps >= 1, "ase_amp_obs_build: hist_steps");
+  ASE_CHECK_ARG(!(p->fill_history && p->shift_history), "ase_amp_obs_build: fill_history and shift_history exclude each other");
   AmpTables tb;
   for (int j = 0; j <= p->num_joints; ++j) tb.dof_offsets[j] = p->dof_offsets[j];
   for (int j = 0; j < p->num_joints; ++j) {

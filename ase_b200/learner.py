@@ -258,6 +258,13 @@ class Learner:
                              "than 2^9 up / 2^12 down between two consecutive calls; rerun with gemm_backend=1")
         return 0
 
+    def plane_flag_to(self, dst):
+        """Write the sticky FP16 plane-scale status (0 = fine) into every element of the 1-D float view `dst`, on the stream (no sync)."""
+        check(lib.ase_learner_plane_flag_to(self._h, dst.data_ptr(), dst.shape[0], dst.stride(0), _stream()), 'ase_learner_plane_flag_to')
+
+    def plane_flag_clear(self):
+        check(lib.ase_learner_plane_flag_clear(self._h, _stream()), 'ase_learner_plane_flag_clear')
+
     def train_result(self, out):
         """Host-side view of the last train_result with the reference's key names (one D2H copy)."""
         s = out['scalars'].tolist()

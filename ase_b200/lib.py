@@ -19,7 +19,7 @@ vp, i32, i64, f32 = C.c_void_p, C.c_int, C.c_int64, C.c_float
 class ObsBuildParams(C.Structure):
     _fields_ = [('body_state', vp), ('env_stride', i64), ('body_stride', i64), ('num_envs', i32), ('num_bodies', i32),
                 ('local_root_obs', i32), ('root_height_obs', i32), ('env_ids', vp), ('num_env_ids', i32),
-                ('obs', vp), ('obs_ld', i64)]
+                ('obs', vp), ('obs_ld', i64), ('env_mask', vp)]
 
 
 class AmpObsBuildParams(C.Structure):
@@ -28,7 +28,7 @@ class AmpObsBuildParams(C.Structure):
                 ('num_envs', i32), ('num_dofs', i32), ('num_joints', i32), ('dof_offsets', C.POINTER(C.c_int32)),
                 ('num_key_bodies', i32), ('key_body_ids', C.POINTER(C.c_int32)),
                 ('local_root_obs', i32), ('root_height_obs', i32), ('env_ids', vp), ('num_env_ids', i32),
-                ('amp_obs', vp), ('hist_steps', i32), ('step_dim', i32), ('shift_history', i32)]
+                ('amp_obs', vp), ('hist_steps', i32), ('step_dim', i32), ('shift_history', i32), ('env_mask', vp), ('fill_history', i32)]
 
 
 class MotionLibParams(C.Structure):
@@ -86,9 +86,9 @@ class TrainResult(C.Structure):
 
 # every symbol declared in include/ase_b200.h (tests/test_abi.py checks the two lists agree)
 EXPORTS = ['ase_abi_version', 'ase_last_error', 'ase_launch_count', 'ase_obs_build', 'ase_amp_obs_build',
-           'ase_rms_scratch_bytes', 'ase_rms_update', 'ase_rms_apply', 'ase_gae', 'ase_amp_rewards', 'ase_heading_obs', 'ase_heading_reward', 'ase_motion_state', 'ase_amp_obs_demo', 'ase_policy_sample', 'ase_adv_normalize', 'ase_gather_rows',
+           'ase_rms_scratch_bytes', 'ase_rms_update', 'ase_rms_apply', 'ase_gae', 'ase_amp_rewards', 'ase_heading_obs', 'ase_heading_reward', 'ase_motion_state', 'ase_amp_obs_demo', 'ase_policy_sample', 'ase_policy_sample_rng', 'ase_latent_update', 'ase_rollout_post_step', 'ase_humanoid_reset', 'ase_adv_normalize', 'ase_gather_rows',
            'ase_gemm', 'ase_gemm_tc_workspace_bytes', 'ase_gemm_tc_profile', 'ase_gemm_tc_profile_read', 'ase_learner_num_params', 'ase_learner_param_desc',
-           'ase_learner_arena_floats', 'ase_learner_workspace_bytes', 'ase_learner_create', 'ase_learner_destroy', 'ase_learner_params_changed', 'ase_learner_plane_status',
+           'ase_learner_arena_floats', 'ase_learner_workspace_bytes', 'ase_learner_create', 'ase_learner_destroy', 'ase_learner_params_changed', 'ase_learner_plane_status', 'ase_learner_plane_flag_to', 'ase_learner_plane_flag_clear',
            'ase_learner_calc_gradients', 'ase_learner_adam_step', 'ase_learner_eval_actor_critic',
            'ase_learner_eval_disc_enc']
 
@@ -118,6 +118,12 @@ def _load():
     lib.ase_amp_obs_demo.argtypes = [C.POINTER(MotionLibParams), vp, vp, i32, f32, i32, i32, i32, vp, vp]
     lib.ase_policy_sample.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp, vp, vp]
     lib.ase_adv_normalize.argtypes = [vp, vp, vp, i32, vp, vp, vp]
+    lib.ase_policy_sample_rng.argtypes = [vp, vp, vp, i32, i32, vp, i32, vp, vp, vp, vp, vp, vp, vp]
+    lib.ase_latent_update.argtypes = [vp, i32, vp, vp, vp, i32, i32, i32, vp, i32, vp, vp, vp]
+    lib.ase_rollout_post_step.argtypes = [vp, vp, vp, vp, vp, vp, f32, i32, vp, vp, vp, vp, vp, vp]
+    lib.ase_humanoid_reset.argtypes = [vp, vp, i64, i64, vp, i64, i64, i32, vp, vp, f32, i32, i32, vp, vp, vp]
+    lib.ase_learner_plane_flag_to.argtypes = [vp, vp, i32, i64, vp]
+    lib.ase_learner_plane_flag_clear.argtypes = [vp, vp]
     lib.ase_gather_rows.argtypes = [C.POINTER(GatherBatch), vp]
     lib.ase_obs_build.argtypes = [C.POINTER(ObsBuildParams), vp]
     lib.ase_amp_obs_build.argtypes = [C.POINTER(AmpObsBuildParams), vp]

@@ -33,24 +33,26 @@ def _body_strides(body_state):
     return body_state.stride(0), body_state.stride(1)
 
 
-def compute_humanoid_observations_max(body_state, local_root_obs, root_height_obs, out=None, env_ids=None):
+def compute_humanoid_observations_max(body_state, local_root_obs, root_height_obs, out=None, env_ids=None, env_mask=None):
     """env/tasks/humanoid.py:591-635 on the packed rigid-body state [N, J, 13] (pos, quat xyzw, vel, angvel).
-    env_ids (int32 CUDA tensor) restricts the update to a subset of rows (reset path, humanoid.py:395-409)."""
+    env_ids (int32 CUDA tensor) restricts the update to a subset of rows (reset path, humanoid.py:395-409); env_mask (uint8 [N]) does the
+    same without an index list (no host sync)."""
     n, j, _ = body_state.shape
     es, bs = _body_strides(body_state)
     obs_dim = 1 + (j - 1) * 3 + j * 6 + j * 3 + j * 3
     if out is None:
         out = torch.empty(n, obs_dim, device=body_state.device, dtype=torch.float32)
     p = L.ObsBuildParams(_p(body_state), es, bs, n, j, int(bool(local_root_obs)), int(bool(root_height_obs)),
-                         _p(env_ids), 0 if env_ids is None else env_ids.numel(), _p(out), out.stride(0))
+                         _p(env_ids), 0 if env_ids is None else env_ids.numel(), _p(out), out.stride(0), _p(env_mask))
     check(lib.ase_obs_build(C.byref(p), _stream()), 'ase_obs_build')
     return out
 
 
 def build_amp_observations(body_state, dof_pos, dof_vel, amp_obs_buf, local_root_obs, root_height_obs,
                            dof_offsets=DOF_OFFSETS_SWORD_SHIELD, key_body_ids=KEY_BODY_IDS_SWORD_SHIELD,
-                           shift_history=True, env_ids=None):
-    """env/tasks/humanoid_amp.py:248-316: (optionally) shift the [N, S, F] history and write the newest frame at slot 0."""
+                           shift_history=True, env_ids=None, env_mask=None, fill_history=False):
+    """env/tasks/humanoid_amp.py:248-316: (optionally) shift the [N, S, F] history and write the newest frame at slot 0.
+    env_mask (uint8 [N]) restricts the update to flagged envs; fill_history sets every slot to the new frame (reset)."""
     n = body_state.shape[0]
     es, bs = _body_strides(body_state)
     dof_pos = _f32c(dof_pos, 'dof_pos'); dof_vel = _f32c(dof_vel, 'dof_vel')
@@ -62,7 +64,7 @@ def build_amp_observations(body_state, dof_pos, dof_vel, amp_obs_buf, local_root
                             n, dof_pos.shape[1], nj, offs, len(key_body_ids), keys,
                             int(bool(local_root_obs)), int(bool(root_height_obs)), _p(env_ids),
                             0 if env_ids is None else env_ids.numel(), _p(amp_obs_buf), amp_obs_buf.shape[1], amp_obs_buf.shape[2],
-                            int(bool(shift_history)))
+                            int(bool(shift_history)), _p(env_mask), int(bool(fill_history)))
     check(lib.ase_amp_obs_build(C.byref(p), _stream()), 'ase_amp_obs_build')
     return amp_obs_buf
 
@@ -88,10 +90,12 @@ class RunningMeanStd:
     def load_state_dict(self, sd):
         self.running_mean.copy_(sd['running_mean']); self.running_var.copy_(sd['running_var']); self.count.copy_(sd['count'])
 
-    def __call__(self, x, unnorm=False):
+    def __call__(self, x, unnorm=False, out=None):
         shp = x.shape
         x2 = _f32c(x.reshape(-1, self.size), 'x')
-        y = torch.empty_like(x2)
+        if out is not None:
+            assert out.is_contiguous() and out.numel() == x2.numel() and out.dtype == torch.float32
+        y = torch.empty_like(x2) if out is None else out.view(x2.shape)
         if self.training and not unnorm:
             need = lib.ase_rms_scratch_bytes(x2.shape[0], self.size)
             if self._scratch is None or self._scratch.numel() < need:
@@ -104,7 +108,50 @@ class RunningMeanStd:
                 raise NotImplementedError("unnorm in train mode is not on the reference's hot path")
             check(lib.ase_rms_apply(_p(x2), x2.stride(0), x2.shape[0], self.size, _p(self.running_mean), _p(self.running_var),
                                     self.eps, int(bool(unnorm)), _p(y), y.stride(0), _stream()), 'ase_rms_apply')
-        return y.reshape(shp)
+        return y.reshape(shp) if out is None else out
+
+
+def policy_sample_rng(mu, logstd, rand_probs, rng, stream_id, out_actions, out_neglogp, out_sigma, out_mask, noise=None, mask=None):
+    """get_action_values' sampling half with in-kernel Philox draws (or injected noise / mask), written straight into the given
+    experience-buffer slices."""
+    rows, a = mu.shape
+    check(lib.ase_policy_sample_rng(_p(mu), _p(logstd), _p(rand_probs), rows, a, _p(rng), int(stream_id), _p(noise), _p(mask),
+                                    _p(out_actions), _p(out_neglogp), _p(out_sigma), _p(out_mask), _stream()), 'ase_policy_sample_rng')
+
+
+def latent_update(latents, reset_steps, progress, done_mask, steps_min, steps_max, rng, stream_id, z_in=None, steps_in=None):
+    """ASEAgent.env_reset (latent part) + _update_latents, mask driven (ase_agent.py:329-381)."""
+    n, z = latents.shape
+    assert latents.is_contiguous() and reset_steps.dtype == torch.int32 and progress.dtype == torch.int64
+    check(lib.ase_latent_update(_p(latents), z, _p(reset_steps), _p(progress), _p(done_mask), n, int(steps_min), int(steps_max),
+                                _p(rng), int(stream_id), _p(z_in), _p(steps_in), _stream()), 'ase_latent_update')
+
+
+def rollout_post_step(rewards, dones, terminate, v_next_normed, value_rms, next_values_out, cur_rewards, cur_lengths, meter, rng):
+    """ase_agent.py:66-92 after env.step: next_values, episode bookkeeping, RNG call counter."""
+    n = dones.shape[0]
+    check(lib.ase_rollout_post_step(_p(rewards), _p(dones), _p(terminate), _p(v_next_normed),
+                                    _p(value_rms.running_mean) if value_rms is not None else None,
+                                    _p(value_rms.running_var) if value_rms is not None else None,
+                                    value_rms.eps if value_rms is not None else 0.0, n, _p(next_values_out), _p(cur_rewards), _p(cur_lengths),
+                                    _p(meter), _p(rng), _stream()), 'ase_rollout_post_step')
+
+
+def compute_humanoid_reset(progress_buf, contact_buf, is_contact_body, body_state, max_episode_length, enable_early_termination,
+                           termination_heights, reset_out=None, terminate_out=None):
+    """env/tasks/humanoid.py:645-670 -> (reset, terminated) uint8 [N].  contact_buf [N, J, 3]; body_state [N, J, 13];
+    is_contact_body uint8 [J] (1 for the bodies in contact_body_ids)."""
+    n, j, _ = body_state.shape
+    es, bs = _body_strides(body_state)
+    if reset_out is None:
+        reset_out = torch.empty(n, dtype=torch.uint8, device=body_state.device)
+    if terminate_out is None:
+        terminate_out = torch.empty(n, dtype=torch.uint8, device=body_state.device)
+    assert contact_buf.stride(2) == 1
+    check(lib.ase_humanoid_reset(_p(progress_buf), _p(contact_buf), contact_buf.stride(0), contact_buf.stride(1), _p(body_state), es, bs, j,
+                                 _p(is_contact_body), _p(termination_heights), float(max_episode_length), int(bool(enable_early_termination)), n,
+                                 _p(reset_out), _p(terminate_out), _stream()), 'ase_humanoid_reset')
+    return reset_out, terminate_out
 
 
 def discount_values(dones, values, rewards, next_values, gamma, tau, want_returns=False):

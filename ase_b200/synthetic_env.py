@@ -71,6 +71,7 @@ class SyntheticHumanoidEnv:
         self.rew_buf = torch.zeros(n, device=self.device)
         self.reset_buf = torch.zeros(n, dtype=torch.uint8, device=self.device)
         self._terminate_buf = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        self._done_bool = torch.zeros(n, dtype=torch.bool, device=self.device); self._term_bool = torch.zeros(n, dtype=torch.bool, device=self.device)
         self.extras = {}
         # demo AMP observations.  'motion_lib': synthetic clips in MotionLib's table format, sampled and turned into 10-frame AMP
         # observations by the ase_amp_obs_demo kernel every fetch (what HumanoidAMP.fetch_amp_obs_demo does, humanoid_amp.py:64-83);
@@ -136,14 +137,15 @@ class SyntheticHumanoidEnv:
         self._dof.copy_(self._dof_pool[i], non_blocking=True)
         self._t += 1
 
-    def _compute_observations(self, shift, env_ids=None):
+    def _compute_observations(self, shift, env_ids=None, env_mask=None, fill_history=False):
         D = self.NUM_DOFS
-        ops.compute_humanoid_observations_max(self._body, self.local_root_obs, self.root_height_obs, out=self.obs_buf, env_ids=env_ids)
+        ops.compute_humanoid_observations_max(self._body, self.local_root_obs, self.root_height_obs, out=self.obs_buf, env_ids=env_ids,
+                                              env_mask=env_mask)
         if self.heading_task:      # humanoid_amp_task.py:51-64: task obs appended behind the humanoid features
             ops.compute_heading_observations(self._body[:, 0], self._tar_dir, self._tar_speed, self._tar_face_dir, out=self.obs_buf,
                                              col0=self.num_humanoid_obs)
         ops.build_amp_observations(self._body, self._dof[:, :D], self._dof[:, D:], self._amp_obs_buf, self.local_root_obs,
-                                   self.root_height_obs, shift_history=shift, env_ids=env_ids)
+                                   self.root_height_obs, shift_history=shift, env_ids=env_ids, env_mask=env_mask, fill_history=fill_history)
 
     def step(self, actions):
         """base_task.py:119-137: physics (bypassed: next synthetic state) then post_physics_step."""
@@ -155,19 +157,35 @@ class SyntheticHumanoidEnv:
         if self.heading_task:
             self.rew_buf = ops.compute_heading_reward(self._body[:, 0, 0:3], self._prev_root_pos, self._body[:, 0, 3:7], self._tar_dir,
                                                       self._tar_speed, self._tar_face_dir, self.dt)
-        r = torch.rand(self.num_envs, device=self.device, generator=self._gen)
-        self.reset_buf = (r < self.done_prob).to(torch.uint8)
-        self._terminate_buf = (r < 0.5 * self.done_prob).to(torch.uint8)        # terminate is a subset of dones
+        # (the default CUDA generator: it is CUDA-graph safe, a private torch.Generator is not)
+        r = torch.rand(self.num_envs, device=self.device) if self.device.type == 'cuda' else torch.rand(self.num_envs, generator=self._gen)
+        torch.lt(r, self.done_prob, out=self._done_bool); torch.lt(r, 0.5 * self.done_prob, out=self._term_bool)
+        self.reset_buf.copy_(self._done_bool); self._terminate_buf.copy_(self._term_bool)        # terminate is a subset of dones
         self.extras['terminate'] = self._terminate_buf
         self.extras['amp_obs'] = self._amp_obs_buf.view(self.num_envs, -1)
         return self.obs_buf, self.rew_buf, self.reset_buf, self.extras
 
     def reset(self, env_ids=None):
         """vec_task_wrappers.py:24-26 -> task.reset(env_ids): obs + AMP history re-initialised for those envs
-        (humanoid_amp.py:146-166,206-218 default-state path: history := current frame)."""
-        if env_ids is not None and len(env_ids) > 0:
+        (humanoid_amp.py:146-166,206-218 default-state path: history := current frame).  env_ids None resets EVERY env
+        (humanoid.py:125-128), an empty list none."""
+        if env_ids is None:
+            env_ids = torch.arange(self.num_envs, device=self.device)
+        if len(env_ids) > 0:
             ids = env_ids.to(torch.int32)
             self.task.progress_buf[env_ids] = 0
             self._compute_observations(shift=False, env_ids=ids)
             self._amp_obs_buf[env_ids, 1:] = self._amp_obs_buf[env_ids, 0:1]
         return self.obs_buf
+
+    def reset_done(self, mask):
+        """The same reset driven by a uint8 [N] mask on the device: no index list, no host sync (the agents use it when the env offers it)."""
+        self.task.progress_buf.masked_fill_(mask.bool(), 0)
+        self._compute_observations(shift=False, env_mask=mask, fill_history=True)
+        return self.obs_buf
+
+    def on_graph_replay(self, steps):
+        """A captured rollout was replayed: advance the host-side step counter the capture baked in (the pool index pattern repeats
+        every `pool` steps, so a rollout of a multiple of `pool` steps replays identically)."""
+        assert steps % self._pool == 0, "CUDA-graph rollouts need horizon_length to be a multiple of the synthetic state pool"
+        self._t += steps

@@ -13,6 +13,13 @@ One "step" = one training epoch of the hot path on one batch of synthetic input:
   python bench.py --gpus 1 --steps 3 --warmup 3
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
   python bench.py --impl reference ...     # the reference's own algorithm on the host CPU cores (oracle port)
+  python bench.py --config 2|3|5           # BASELINE.json configs: 2 AMP-only (HumanoidAMP), 3 ASE pre-train (default, the metric's config),
+                                           # 5 HRL heading task over a frozen ASE low-level controller
+
+Measurement rules: `value` is timed with NO per-launch instrumentation (CUDA events around the K epochs only); the per-kernel GEMM time
+behind `roofline` comes from ONE extra, untimed epoch run with ase_gemm_tc_profile on.  The CPU arm (`cpu_baseline`, --impl reference) runs
+the oracle port on a FIXED thread count (min(32, cores in the affinity mask)) and times a step that is an exact 1/16 of an epoch in the
+epoch's own proportions (2 of 32 rollout steps, 8192 of 131072 reward rows, 3 of 48 minibatch updates): ms_per_step is real wall time.
 """
 import argparse
 import json
@@ -34,8 +41,15 @@ FLOP_PER_MINIBATCH = 0.9685e12      # algorithmic, fp32,
 FLOP_ROLLOUT_PER_EPOCH = 3.13e12
 
 
+CONFIG = 3
+WORKLOADS = {2: ("amp", "HumanoidAMP single-clip imitation (AMP-only: no encoder / latents / diversity, MLPs [1024, 512]), synthetic rigid-body states, Isaac Gym bypassed"),
+             3: ("ase", "HumanoidAMPGetup ASE pre-train (disc+encoder+diversity), synthetic rigid-body states, Isaac Gym bypassed"),
+             5: ("hrl", "HumanoidHeading HRL task-train (tanh-mu HLC [1024, 512], frozen full-size ASE LLC stepped 5x per action), synthetic rigid-body states, Isaac Gym bypassed")}
+CPU_FRACTION = 16                    # the CPU arm's step = 1 / 16 of an epoch
+
+
 def _workload_config(n_gpus):
-    return {"workload": "HumanoidAMPGetup ASE pre-train (disc+encoder+diversity), synthetic rigid-body states, Isaac Gym bypassed",
+    return {"workload": WORKLOADS[CONFIG][1], "baseline_config": CONFIG,
             "num_envs_per_gpu": NUM_ENVS, "horizon": HORIZON, "minibatch": MINIBATCH, "amp_minibatch": AMP_MINIBATCH,
             "mini_epochs": MINI_EPOCHS, "minibatches_per_step": MINI_EPOCHS * (NUM_ENVS * HORIZON // MINIBATCH),
             "env_steps_per_step_per_gpu": NUM_ENVS * HORIZON, "parallelism": f"env-sharded dp{n_gpus}",
@@ -80,13 +94,15 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------ ours
 def _make_agent(torch, rank, world, state_source, seed):
     from ase_b200 import configs
-    from ase_b200.agent import ASEAgent
+    from ase_b200.agent import ASEAgent, AMPAgent, HRLAgent
     from ase_b200.synthetic_env import SyntheticHumanoidEnv
     dev = f"cuda:{torch.cuda.current_device()}"
-    env = SyntheticHumanoidEnv(NUM_ENVS, device=dev, seed=seed + rank, state_source=state_source)   # seed += rank (run.py:36-50)
-    cfg = configs.make('ase', device=dev, vec_env=env, num_actors=NUM_ENVS, multi_gpu=world > 1, print_stats=False,
+    kind = WORKLOADS[CONFIG][0]
+    env = SyntheticHumanoidEnv(NUM_ENVS, device=dev, seed=seed + rank, state_source=state_source,    # seed += rank (run.py:36-50)
+                               local_root_obs=(kind != 'amp'), heading_task=(kind == 'hrl'))
+    cfg = configs.make(kind, device=dev, vec_env=env, num_actors=NUM_ENVS, multi_gpu=world > 1, print_stats=False,
                        seed=seed, gemm_backend=GEMM_BACKEND)
-    agent = ASEAgent('bench', cfg)
+    agent = {'ase': ASEAgent, 'amp': AMPAgent, 'hrl': HRLAgent}[kind]('bench', cfg)
     agent.init_tensors()
     agent.obs = agent.env_reset()
     if world > 1:
@@ -121,6 +137,8 @@ def _timed_epochs(torch, agent, steps, world, d2h=False):
     for _ in range(steps):
         agent.update_epoch()
         info = agent.train_epoch()
+        if world > 1:
+            agent._sync_stats()                        # the per-epoch RunningMeanStd averaging of agent.train() (hvd.sync_stats)
         if d2h:
             host.append(agent._tr_buf.cpu())           # the step's train_result series -> host (D2H inside the timed region)
     e1.record()
@@ -150,16 +168,21 @@ def run_ours(args):
         agent.update_epoch(); agent.train_epoch()
     torch.cuda.synchronize()
     launches0 = L.launch_count()
-    L.lib.ase_gemm_tc_profile(1)
     with ClockSampler(local) as clk:
         secs, _ = _timed_epochs(torch, agent, args.steps, world)
+    launches = L.launch_count() - launches0
+    play_t, upd_t, _ = agent.epoch_times()
+    # roofline numerator / denominator: ONE extra epoch, outside the timed region, with CUDA events around every tcgen05 GEMM launch
+    L.lib.ase_gemm_tc_profile(1)
+    agent.update_epoch(); agent.train_epoch()
+    torch.cuda.synchronize()
     tot_ms, nl, fl = C.c_double(), C.c_int64(), C.c_double()
     L.check(L.lib.ase_gemm_tc_profile_read(C.byref(tot_ms), C.byref(nl), C.byref(fl)), 'profile_read')
     L.lib.ase_gemm_tc_profile(0)
-    launches = L.launch_count() - launches0
-    play_t, upd_t, _ = agent.epoch_times()
+    prof_play_t, prof_upd_t, prof_tot = agent.epoch_times()
     plane_flags = _plane_flags(agent)      # FP16 operand-plane scale misses during the warm-up / timed epochs (read outside the timed region)
     tr = {k: float(v) for k, v in zip(L.TR_NAMES, agent._tr_buf[-1].tolist())}
+    graph_rollout = getattr(agent, '_rollout_graph', None) is not None
     env_steps = args.steps * NUM_ENVS * HORIZON * world
     value = env_steps / secs
     del agent, env
@@ -210,17 +233,19 @@ def run_ours(args):
         "roofline": {"bound": "tensor", "kernel": "gemm_tc256_kernel / gemm_tc_kernel (tcgen05.mma kind::f16, 3 MMAs per product on scaled FP16 hi/lo planes)" if GEMM_BACKEND == 2
                      else "gemm_tc_kernel (tcgen05.mma kind::tf32, 3xTF32)", "achieved": achieved_tf,
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
-                     "peak_source": peak_src, "launches_timed": int(nl.value), "kernel_ms_per_step": tot_ms.value / args.steps,
-                     "kernel_share_of_step": (tot_ms.value / 1e3) / secs,
+                     "peak_source": peak_src, "launches_timed": int(nl.value), "kernel_ms_per_step": tot_ms.value,
+                     "kernel_share_of_step": (tot_ms.value / 1e3) / prof_tot if prof_tot > 0 else None,
+                     "measured_in": "one extra untimed epoch with per-launch CUDA events (the timed epochs run uninstrumented)",
+                     "frac_of_step_algorithmic": (nmb / args.steps * FLOP_PER_MINIBATCH + FLOP_ROLLOUT_PER_EPOCH) / 1e12 / (secs / args.steps) / peak_tf if (peak_tf and CONFIG == 3) else None,
                      "note": "achieved = algorithmic 2*M*N*K FLOPs of the timed launches / summed CUDA-event kernel time; fp32 parity "
                              "forces 3 MMAs per product (hi.hi + lo.hi + hi.lo): the ceiling against the bf16 peak is 1/3 with FP16 planes "
                              "(backend 2), 1/6 with TF32 planes (backend 1)",
                      "learner_tflops_algorithmic": nmb * FLOP_PER_MINIBATCH / 1e12 / (upd_t * args.steps) if upd_t > 0 else None},
-        "split": {"play_time_s_last_step": play_t, "update_time_s_last_step": upd_t},
+        "split": {"play_time_s_last_step": play_t, "update_time_s_last_step": upd_t, "rollout_cuda_graph": graph_rollout},
         "plane_status": plane_flags,      # ase_learner_plane_status after both runs: 0 = every FP16 plane scale prediction held
         "train_result_last": tr,
     }
-    if world == 1:
+    if world == 1 and CONFIG == 3:
         line["cpu_baseline"] = cpu_baseline()
     print(json.dumps(line))
 
@@ -235,39 +260,43 @@ def _shutdown():
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
-def cpu_baseline():
+def _cpu_arm(reps, warm):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import torch
     import cpu_bench
-    cpu_bench.pick_threads()
-    r = cpu_bench.sample_epoch_seconds(NUM_ENVS, HORIZON, MINIBATCH, AMP_MINIBATCH, MINI_EPOCHS, warm=True)
-    return {"value": r["env_steps_per_s"], "unit": UNIT, "cores": r["threads"], "kind": "port",
-            "sample": r["sample"] + " (each call warmed once)", "minibatch_s": r["minibatch_s"], "rollout_step_s": r["rollout_step_s"]}
+    threads = cpu_bench.fixed_threads()
+    st = cpu_bench.make_state(NUM_ENVS, MINIBATCH, AMP_MINIBATCH)
+    for _ in range(warm):
+        cpu_bench.fraction_step(st, CPU_FRACTION)
+    times = [cpu_bench.fraction_step(st, CPU_FRACTION) for _ in range(reps)]
+    return threads, times, cpu_bench.fraction_description(NUM_ENVS, HORIZON, MINIBATCH, AMP_MINIBATCH, MINI_EPOCHS, CPU_FRACTION)
+
+
+def cpu_baseline():
+    threads, times, what = _cpu_arm(reps=2, warm=1)
+    t = statistics.median(times)
+    return {"value": NUM_ENVS * HORIZON / CPU_FRACTION / t, "unit": UNIT, "cores": threads, "kind": "port", "sample": what,
+            "step_wall_s": {"min": min(times), "median": t}, "thread_policy": "fixed: min(32, cores in the affinity mask)"}
 
 
 def run_reference(args):
-    """The reference's own algorithm (CPU torch fp32, all host threads) on the same workload: oracle port, since the
-    reference is Python and /root/reference does not exist on the GPU box.  Each step is a bounded sample."""
+    """The reference's own algorithm (CPU torch fp32) on the same workload: the oracle port (the reference is Python and /root/reference does
+    not exist on the GPU box).  One step = an exact 1/16 of an epoch, timed for real (no extrapolation): ms_per_step is wall time."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import torch
-    import cpu_bench
-    cpu_bench.pick_threads()
-    for _ in range(min(args.warmup, 1)):
-        cpu_bench.sample_epoch_seconds(NUM_ENVS, HORIZON, MINIBATCH, AMP_MINIBATCH, MINI_EPOCHS, warm=False)
-    vals, last = [], None
-    for _ in range(args.steps):
-        last = cpu_bench.sample_epoch_seconds(NUM_ENVS, HORIZON, MINIBATCH, AMP_MINIBATCH, MINI_EPOCHS, warm=False)
-        vals.append(last["env_steps_per_s"])
-    v = statistics.median(vals)
+    threads, times, what = _cpu_arm(reps=args.steps, warm=min(args.warmup, 1))
+    t = statistics.median(times)
+    v = NUM_ENVS * HORIZON / CPU_FRACTION / t
+    cfgd = _workload_config(args.gpus)
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * NUM_ENVS * HORIZON / v, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": _workload_config(args.gpus),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["threads"], "kind": "port", "sample": last["sample"]},
+            "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(times), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfgd,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": "port", "sample": what,
+                             "step_wall_s": {"min": min(times), "median": t, "all": times}, "thread_policy": "fixed: min(32, cores in the affinity mask)"},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "note": "CPU arm does not scale with --gpus: one host runs the reference algorithm for one env shard"}
+            "env_steps_per_step": NUM_ENVS * HORIZON // CPU_FRACTION,
+            "note": "CPU arm does not scale with --gpus: one host runs the reference algorithm for one env shard; a step is 1/16 of an epoch "
+                    "(value = 8192 env-steps / measured step time)"}
     print(json.dumps(line))
 
 
@@ -277,7 +306,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 5], help="BASELINE.json config (3 = the metric's config)")
     args = ap.parse_args()
+    global CONFIG
+    CONFIG = args.config
     if args.impl == "reference":
         run_reference(args)
     else:

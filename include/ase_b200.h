@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define ASE_ABI_VERSION 2
+#define ASE_ABI_VERSION 3
 #define ASE_MAX_LAYERS 4
 
 typedef enum {
@@ -57,6 +57,7 @@ typedef struct {
   int num_env_ids;
   float* obs;                 /* [N, obs_ld]; row e (or env_ids[i]) is written */
   int64_t obs_ld;             /* >= 1 + (J-1)*3 + J*6 + J*3 + J*3 */
+  const uint8_t* env_mask;    /* optional [N]: only envs with a non-zero flag are written (device-side reset without an index list) */
 } AseObsBuildParams;
 int ase_obs_build(const AseObsBuildParams* p, void* stream);
 
@@ -76,6 +77,8 @@ typedef struct {
   int hist_steps;              /* 10 */
   int step_dim;                /* 13 + 6*num_joints + num_dofs + 3*num_key_bodies = 140 */
   int shift_history;           /* 1: slots i -> i+1 first (post_physics_step path, humanoid_amp.py:50-59) */
+  const uint8_t* env_mask;     /* optional [N]: only envs with a non-zero flag are touched */
+  int fill_history;            /* 1: every history slot := the current frame (reset, humanoid_amp.py:206-218 default-state path) */
 } AseAmpObsBuildParams;
 int ase_amp_obs_build(const AseAmpObsBuildParams* p, void* stream);
 
@@ -144,6 +147,34 @@ int ase_heading_reward(const float* root_pos, int64_t root_pos_stride, const flo
  * sigma_out (optional) receives exp(logstd) broadcast to [rows, act_dim]. */
 int ase_policy_sample(const float* mu, const float* logstd, const float* noise, const float* rand_mask,
                       int rows, int act_dim, float* actions, float* neglogp, float* sigma_out, void* stream);
+/* ---- rollout step without host round trips (learning/ase_agent.py:36-115,366-381) ---------------------------------
+ * The reference draws action noise / the eps-greedy mask / fresh latents with eager torch calls and turns `dones` and
+ * `_latent_reset_steps <= progress_buf` into index lists with nonzero() (a host sync per sim step).  These entry points run the same
+ * arithmetic mask-driven, with a counter-based generator (Philox4x32-10) evaluated inside the kernels: `rng` is a 2-element device array
+ * {seed, call counter}; ase_rollout_post_step advances the counter, so a whole rollout can be captured in a CUDA graph.  Each takes
+ * optional injected draws (parity tests feed the reference's own draws). */
+/* get_action_values' sampling half (rl_games ModelA2CContinuousLogStd eval + amp_agent.py:164-167): a = mu + exp(logstd) * noise,
+ * rand_action_mask = bernoulli(rand_probs) (all ones when rand_probs is NULL), masked rows act deterministically. */
+int ase_policy_sample_rng(const float* mu, const float* logstd, const float* rand_probs, int rows, int act_dim,
+                          const uint64_t* rng, int stream_id, const float* noise_in, const float* mask_in,
+                          float* actions, float* neglogp, float* sigma_out, float* mask_out, void* stream);
+/* ASEAgent.env_reset's latent part (ase_agent.py:329-364) + _update_latents (:366-381): envs flagged in done_mask get a fresh latent and
+ * reset_steps = randint(min, max); otherwise envs with reset_steps <= progress get a fresh latent and reset_steps += randint(min, max).
+ * latent = normalize(randn(Z)) (ase_network_builder.py:221-225).  z_in [N, Z] (final latents) / steps_in [N] replace the draws. */
+int ase_latent_update(float* latents, int latent_dim, int32_t* reset_steps, const int64_t* progress, const uint8_t* done_mask, int num_envs,
+                      int steps_min, int steps_max, const uint64_t* rng, int stream_id, const float* z_in, const int32_t* steps_in, void* stream);
+/* after env.step (ase_agent.py:66-92): next_values = value_mean_std^-1(v) * (1 - terminate); current_rewards / current_lengths bookkeeping with
+ * the episode meters (meter[0..2] += sum of finished episodes' reward, length, count); rng[1] += 1.  next_values may be NULL. */
+int ase_rollout_post_step(const float* rewards, const uint8_t* dones, const uint8_t* terminate, const float* v_next_normed,
+                          const double* val_mean, const double* val_var, float eps, int num_envs, float* next_values,
+                          float* cur_rewards, float* cur_lengths, float* meter, uint64_t* rng, void* stream);
+/* compute_humanoid_reset, env/tasks/humanoid.py:645-670: contact forces [N, J, 3] (strides in floats), rigid-body state as in ase_obs_build,
+ * is_contact_body [J] flags the bodies allowed to touch the ground (contact_body_ids), termination_heights [J]. */
+int ase_humanoid_reset(const int64_t* progress, const float* contact, int64_t contact_env_stride, int64_t contact_body_stride,
+                       const float* body_state, int64_t env_stride, int64_t body_stride, int num_bodies, const uint8_t* is_contact_body,
+                       const float* termination_heights, float max_episode_length, int enable_early_termination, int num_envs,
+                       uint8_t* reset_out, uint8_t* terminate_out, void* stream);
+
 /* _calc_advs amp_agent.py:551-561 (+ torch_ext.normalization_with_masks); mask NULL => plain
  * mean / unbiased std (common_agent.py:536-546).  scratch >= 64 bytes. */
 int ase_adv_normalize(const float* returns, const float* values, const float* mask, int rows,
@@ -289,6 +320,10 @@ int ase_learner_params_changed(AseLearner* l);
  * tensor's max between two consecutive calls); bit 1: a tensor's max shrank by > 2^12 between two calls (its split lost
  * precision).  Either means the results of the flagged call are not fp32-accurate: the host mirror raises. */
 int ase_learner_plane_status(AseLearner* l, int* flags, void* stream);
+/* The same flag without a host round trip: dst[i * stride] = (float)flags for i < count, on the stream (the agent lets it ride in its
+ * per-epoch train_result record); ..._clear resets it after the host has dealt with a miss. */
+int ase_learner_plane_flag_to(AseLearner* l, float* dst, int count, int64_t stride, void* stream);
+int ase_learner_plane_flag_clear(AseLearner* l, void* stream);
 
 /* forward + losses + backward: fills state->grads (sum over local rows; no Adam) */
 int ase_learner_calc_gradients(AseLearner* l, const AseLearnerState* st, const AseMinibatch* mb,

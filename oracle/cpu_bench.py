@@ -41,6 +41,59 @@ def pick_threads():
     return best
 
 
+def fixed_threads():
+    """The CPU arm's thread policy: min(32, cores in the affinity mask) -- fixed, stated in the JSON line (round 1 picked the count with a
+    noisy probe: 16 / 32 / 64 across arms of one round, the number moved by 3x)."""
+    import os
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except Exception:
+        avail = os.cpu_count() or 1
+    n = max(1, min(32, avail))
+    torch.set_num_threads(n)
+    return n
+
+
+def make_state(num_envs=4096, minibatch=16384, amp_minibatch=4096, seed=0):
+    cfg = dict(O.DEFAULT_CFG); cfg['amp_minibatch_size'] = amp_minibatch
+    P = synth.params(O.ase_param_shapes(), seed=seed)
+    st = O.LearnerState(P, 253, 1400, 'ase')
+    s = synth.rigid_body_state(num_envs, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    z = torch.nn.functional.normalize(torch.randn(num_envs, 64, generator=g), dim=-1)
+    d, new_z = synth.minibatch(st, cfg, minibatch, amp_minibatch, seed=seed + 1)
+    return dict(cfg=cfg, st=st, s=s, z=z, noise=torch.randn(num_envs, 31, generator=g), mask=torch.ones(num_envs), hist=torch.zeros(num_envs, 10, 140),
+                amp_rows=torch.randn(2 * num_envs, 1400, generator=g), z2=torch.cat([z, z]), d=d, new_z=new_z, num_envs=num_envs)
+
+
+def fraction_step(S, fraction=16, horizon=32, mini_epochs=6, batches_per_epoch=8):
+    """An exact 1 / fraction of one training epoch in the epoch's own proportions (fraction = 16: 2 of the 32 rollout steps, 8192 of the
+    131072 reward rows, 3 of the 48 minibatch updates incl. Adam).  Returns its wall time in seconds."""
+    st, s, z, cfg = S['st'], S['s'], S['z'], S['cfg']
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        for _ in range(horizon // fraction):
+            obs = O.compute_humanoid_observations_max(s['body_pos'], s['body_rot'], s['body_vel'], s['body_ang_vel'], True, True)
+            kp = s['body_pos'][:, O.KEY_BODY_IDS_SWORD_SHIELD]
+            fr = O.build_amp_observations(s['body_pos'][:, 0], s['body_rot'][:, 0], s['body_vel'][:, 0], s['body_ang_vel'][:, 0],
+                                          s['dof_pos'], s['dof_vel'], kp, True, True, O.DOF_OFFSETS_SWORD_SHIELD)
+            O.amp_hist_step(S['hist'], fr)
+            O.get_action_values(st, obs, z, S['noise'], S['mask'])
+            O.eval_critic_unnorm(st, obs, z)
+        rows = S['num_envs'] * horizon // fraction
+        O.calc_amp_rewards(st, S['amp_rows'][:rows], S['z2'][:rows], cfg)
+    for _ in range(mini_epochs * batches_per_epoch // fraction):
+        O.calc_gradients(st, S['d'], cfg, S['new_z'])
+    return time.perf_counter() - t0
+
+
+def fraction_description(num_envs, horizon, minibatch, amp_minibatch, mini_epochs, fraction):
+    nmb = mini_epochs * (num_envs * horizon // minibatch)
+    return (f"1/{fraction} of an epoch, timed whole: {horizon // fraction} rollout steps ({num_envs} envs: obs + AMP obs build, actor + 2 critic passes), "
+            f"{num_envs * horizon // fraction}-row reward pass, {nmb // fraction} minibatch updates (B={minibatch}, Ba={amp_minibatch}, incl. Adam) "
+            f"= {num_envs * horizon // fraction} env-steps; no extrapolation")
+
+
 def _t(fn, reps=1):
     t0 = time.perf_counter()
     for _ in range(reps):

@@ -136,6 +136,139 @@ def gen_calc_gradients_full():
     print('calc_grad_amp_full', r['steps'][-1]['scalars'])
 
 
+def gen_rollout():
+    """The reference's own ASEAgent.play_steps + prepare_dataset (learning/ase_agent.py:36-156, common_agent.py:309-351) over a scripted
+    vec-env (ref_harness.FakeVecEnv) with every random draw RECORDED in call order: action noise (Normal.sample), the eps-greedy bernoulli
+    mask, the latents of _reset_latents and the randint_like step counts.  Small networks; 16 envs x 8 steps; dones / terminations /
+    latent horizons chosen so that resets, latent refreshes and the first-step `done_indices = []` rule all occur."""
+    import ref_harness
+    N, H, Z, A = 16, 8, 64, 31
+    small = dict(units=(64, 48, 32), disc_units=(48, 40, 24))
+    orig = ref_harness.load_train_cfg
+
+    def patched(name):
+        c = orig(name)
+        c['params']['network']['mlp']['units'] = list(small['units']); c['params']['network']['disc']['units'] = list(small['disc_units'])
+        return c
+    ref_harness.load_train_cfg = patched
+    try:
+        agent, params = rh.make_ref_agent('ase', num_envs=N, overrides={'minibatch_size': 64, 'amp_minibatch_size': 32, 'horizon_length': H,
+                                                                         'latent_steps_min': 1, 'latent_steps_max': 6})
+    finally:
+        ref_harness.load_train_cfg = orig
+    P = synth.params(O.ase_param_shapes(units=small['units'], disc_units=small['disc_units']), seed=31)
+    _load_params(agent, P, True)
+    g = torch.Generator().manual_seed(77)
+    # non-trivial normaliser statistics
+    for rms, dim in ((agent.running_mean_std, 253), (agent.value_mean_std, 1), (agent._amp_input_mean_std, 1400)):
+        rms.running_mean.copy_(torch.randn(dim, generator=g).double() * 0.3); rms.running_var.copy_((0.5 + torch.rand(dim, generator=g)).double())
+        rms.count.fill_(1000.0)
+    rms_state = {k: {'running_mean': r.running_mean.clone(), 'running_var': r.running_var.clone(), 'count': r.count.clone()}
+                 for k, r in (('running_mean_std', agent.running_mean_std), ('reward_mean_std', agent.value_mean_std), ('amp_input_mean_std', agent._amp_input_mean_std))}
+    # scripted env
+    obs_t = torch.randn(H + 1, N, 253, generator=g) * 1.5 + 0.3
+    reset_obs_t = torch.randn(H + 1, N, 253, generator=g) * 1.5 - 0.2
+    amp_t = torch.randn(H, N, 1400, generator=g)
+    rew_t = torch.rand(H, N, generator=g)
+    dones_t = (torch.rand(H, N, generator=g) < 0.25).to(torch.uint8)
+    dones_t[H - 1, 0] = 1                                   # a done on the LAST step: must not be reset at the start of the next rollout
+    term_t = (dones_t.bool() & (torch.rand(H, N, generator=g) < 0.5)).to(torch.uint8)
+    env = agent.vec_env
+    task = env.env.task
+    task.progress_buf = torch.randint(0, 4, (N,), generator=g)
+    progress0 = task.progress_buf.clone()
+    cur = {'obs': obs_t[0].clone()}
+
+    def script(t, actions):
+        cur['obs'] = obs_t[t + 1].clone()
+        return cur['obs'], rew_t[t].clone(), dones_t[t].clone(), {'amp_obs': amp_t[t].clone(), 'terminate': term_t[t].clone()}
+
+    def reset_fn(env_ids):
+        if env_ids is None:
+            env_ids = torch.arange(N)
+        if len(env_ids) > 0:
+            task.progress_buf[env_ids] = 0
+            cur['obs'][env_ids] = reset_obs_t[env.t][env_ids]
+        return cur['obs']
+    env.script, env.reset_fn = script, reset_fn
+    # recorded RNG
+    rec = {'normal': [], 'bernoulli': [], 'latents': [], 'randint': []}
+    real_sample, real_bern, real_randint_like = torch.distributions.Normal.sample, torch.bernoulli, torch.randint_like
+
+    def rec_sample(self, sample_shape=torch.Size()):
+        eps = torch.randn(self.loc.shape, generator=g)
+        rec['normal'].append(eps.clone())
+        return self.loc + self.scale * eps
+
+    def rec_bern(p, *a, **k):
+        m = (torch.rand(p.shape, generator=g) < p).float()
+        rec['bernoulli'].append(m.clone())
+        return m
+
+    def rec_randint_like(x, low=0, high=None, **k):
+        r = torch.randint(low, high, x.shape, generator=g, dtype=x.dtype)
+        rec['randint'].append(r.clone())
+        return r
+    real_lat = agent.model.a2c_network.sample_latents
+
+    def rec_latents(n):
+        z = torch.nn.functional.normalize(torch.randn(n, Z, generator=g), dim=-1)
+        rec['latents'].append(z.clone())
+        return z
+    torch.distributions.Normal.sample, torch.bernoulli, torch.randint_like = rec_sample, rec_bern, rec_randint_like
+    agent.model.a2c_network.sample_latents = rec_latents
+    try:
+        agent.init_tensors()
+        agent.obs = agent.env_reset()                    # train(): resets every env and every latent
+        latents0, steps0 = agent._ase_latents.clone(), agent._latent_reset_steps.clone()
+        n0 = {k: len(v) for k, v in rec.items()}
+        agent.set_eval()
+        with torch.no_grad():
+            batch_dict = agent.play_steps()
+        agent.set_train()
+        played = batch_dict.pop('played_frames')
+        # (train_epoch adds the demo / replay samples before prepare_dataset, amp_agent.py:194-202: not part of this fixture)
+        batch_dict['amp_obs_demo'] = torch.zeros_like(batch_dict['amp_obs']); batch_dict['amp_obs_replay'] = torch.zeros_like(batch_dict['amp_obs'])
+        agent.prepare_dataset(batch_dict)
+    finally:
+        torch.distributions.Normal.sample, torch.bernoulli, torch.randint_like = real_sample, real_bern, real_randint_like
+        agent.model.a2c_network.sample_latents = real_lat
+    eb = {k: v.clone() for k, v in agent.experience_buffer.tensor_dict.items()}
+    assert torch.equal(eb['amp_obs'], amp_t) and torch.equal(eb['next_obses'], obs_t[1:])
+    del eb['amp_obs'], eb['next_obses']             # (== the scripted inputs: the test checks them against those)
+    ds = {k: v.clone() for k, v in agent.dataset.values_dict.items() if torch.is_tensor(v) and not k.startswith('amp_obs') and k != 'obs'}
+    batch_dict = {k: v for k, v in batch_dict.items() if k in ('returns', 'disc_rewards', 'enc_rewards')}
+    out = dict(N=N, H=H, units=small['units'], disc_units=small['disc_units'], param_seed=31, rms_state=rms_state,
+               obs_t=obs_t, reset_obs_t=reset_obs_t, amp_t=amp_t, rew_t=rew_t, dones_t=dones_t, term_t=term_t, progress0=progress0,
+               latents0=latents0, steps0=steps0, rec={k: v[n0[k]:] for k, v in rec.items()}, rec_init={k: v[:n0[k]] for k, v in rec.items()},
+               eb=eb, batch={k: v.clone() for k, v in batch_dict.items() if torch.is_tensor(v)}, dataset=ds,
+               latents_end=agent._ase_latents.clone(), steps_end=agent._latent_reset_steps.clone(), progress_end=task.progress_buf.clone(),
+               value_rms_after={'running_mean': agent.value_mean_std.running_mean.clone(), 'running_var': agent.value_mean_std.running_var.clone(),
+                                'count': agent.value_mean_std.count.clone()},
+               cfg={k: agent.config[k] for k in ('gamma', 'tau', 'disc_reward_scale', 'enc_reward_scale', 'task_reward_w', 'disc_reward_w', 'enc_reward_w')})
+    torch.save(out, os.path.join(OUT, 'rollout_ase.pt'))
+    print('rollout_ase.pt', {k: tuple(v.shape) for k, v in eb.items()}, {k: len(v) for k, v in out['rec'].items()}, 'dones', int(dones_t.sum()))
+
+
+def gen_humanoid_reset():
+    """compute_humanoid_reset (env/tasks/humanoid.py:645-670) on seeded inputs incl. the progress_buf <= 1 guard and both early-termination settings."""
+    humanoid, _, _ = rh.import_env_fns()
+    g = torch.Generator().manual_seed(41)
+    N, J = 96, 17
+    contact = torch.randn(N, J, 3, generator=g) * 0.08
+    contact[torch.rand(N, J, generator=g) < 0.15] *= 40.0
+    pos = torch.randn(N, J, 3, generator=g); pos[..., 2] = torch.rand(N, J, generator=g) * 0.6
+    heights = torch.rand(J, generator=g) * 0.3
+    progress = torch.randint(0, 310, (N,), generator=g); progress[:6] = torch.tensor([0, 1, 2, 298, 299, 300])
+    ids = torch.tensor([13, 16, 7, 4])          # contact_body_ids (feet / hands)
+    out = dict(contact=contact, pos=pos, heights=heights, progress=progress, contact_body_ids=ids, max_episode_length=300.0)
+    for et in (True, False):
+        r, t = humanoid.compute_humanoid_reset(torch.zeros(N, dtype=torch.long), progress, contact, ids, pos, 300.0, et, heights)
+        out[f'reset_{int(et)}'], out[f'term_{int(et)}'] = r, t
+    torch.save(out, os.path.join(OUT, 'humanoid_reset.pt'))
+    print('humanoid_reset.pt', int(out['reset_1'].sum()), int(out['term_1'].sum()))
+
+
 def gen_motion_lib():
     """The reference's own MotionLib.get_motion_state + build_amp_observations on synthetic clip tables (the object is
     assembled field by field so no .npy clip has to travel; the real loader only fills these same tensors)."""

@@ -62,17 +62,23 @@ def _conditioned(k):
 
 
 def _three_way(mine, g32, g64, tag):
-    worst_ref, worst_me, rows = 0.0, 0.0, []
+    worst_ref, worst_me, rows, bad = 0.0, 0.0, [], []
     for k in g32:
         r = _stats(g32[k], g64[k]); m = _stats(mine[k], g64[k]); x = _stats(mine[k], g32[k])
         worst_ref, worst_me = max(worst_ref, r[3]), max(worst_me, m[3])
         rows.append((k, r, m, x))
-        assert m[0] <= 1.5 * r[0] + 2e-5, (tag, k, 'median error vs fp64', m[0], 'reference fp32', r[0])
-        assert m[1] <= 1.5 * r[1] + 1e-4, (tag, k, 'q95 error vs fp64', m[1], 'reference fp32', r[1])
+        if not m[0] <= 1.5 * r[0] + 2e-5:
+            bad.append((k, 'median error vs fp64', m[0], 'reference fp32', r[0]))
+        if not m[1] <= 1.5 * r[1] + 1e-4:
+            bad.append((k, 'q95 error vs fp64', m[1], 'reference fp32', r[1]))
         if _conditioned(k):
-            assert x[2] <= 1e-4, (tag, k, 'q99 vs the fp32 reference', x[2])
-            assert x[3] <= 5e-3, (tag, k, 'max vs the fp32 reference (decision-flip rows)', x[3])
-    assert worst_me <= 2.0 * worst_ref + 1e-4, (tag, 'worst element vs fp64', worst_me, 'reference', worst_ref)
+            if not x[2] <= 1e-4:
+                bad.append((k, 'q99 vs the fp32 reference', x[2]))
+            if not x[3] <= 5e-3:
+                bad.append((k, 'max vs the fp32 reference (decision-flip rows)', x[3]))
+    if not worst_me <= 2.0 * worst_ref + 1e-4:
+        bad.append(('all', 'worst element vs fp64', worst_me, 'reference', worst_ref))
+    assert not bad, (tag, bad)
     return rows, worst_ref, worst_me
 
 

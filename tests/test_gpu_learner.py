@@ -61,8 +61,12 @@ def _check_grads(ln, rec, when, exact=True):
             assert float(d.max()) <= 1e-4, (when, k, float(d.max()))
             assert abs(float(g.double().norm()) - rec['grad_norm'][k]) <= 1e-4 * max(rec['grad_norm'][k], 1e-9), (when, k)
         else:
-            frac = float((d > 1e-4).float().mean())
-            assert float(d.median()) <= 2e-5 and frac <= 0.05 and float(d.max()) <= 0.25, (when, k, float(d.median()), frac, float(d.max()))
+            # step 0 starts from identical parameters; later steps continue from the device's own Adam updates (lr * sign(g) on the first steps:
+            # where |g| is at the parity floor the sign is anybody's guess), and a 4e-5 parameter difference is amplified ~300x by the
+            # sigma = exp(-2.9) Gaussian head into the actor gradients: bulk at 1e-4, tails at 1e-3
+            first = 'step 0' in when
+            frac = float((d > (1e-4 if first else 1e-3)).float().mean())
+            assert float(d.median()) <= (2e-5 if first else 1e-4) and frac <= 0.05 and float(d.max()) <= 0.25, (when, k, float(d.median()), frac, float(d.max()))
             assert abs(float(g.double().norm()) - rec['grad_norm'][k]) <= 5e-3 * max(rec['grad_norm'][k], 1e-9), (when, k)
         if 'grads' in rec:
             full = rec['grads'][k].flatten()
@@ -113,13 +117,6 @@ def _run_golden(name, backend, exact=True):
         assert torch.allclose(ln.amp_input_mean_std.running_var.cpu(), r['amp_var'], rtol=1e-5, atol=1e-9)
         assert float(ln.amp_input_mean_std.count) == float(r['amp_count'])
         O.calc_gradients(st, d, cfg, new_z)        # advance the input generator's state in lock-step
-        if not exact:
-            # teacher forcing: continue from the reference's parameters (the oracle reproduces the reference's Adam bit for bit).  Adam's first
-            # steps are lr * sign(g): where |g| is at the parity floor the sign is anybody's guess, and a 4e-5 parameter difference is amplified
-            # ~300x by the sigma = exp(-2.9) Gaussian head into the next step's actor gradients.  Written without params_changed(), so the FP16
-            # plane scales keep being PREDICTED from the previous call.
-            for k, v in ln.named_parameters().items():
-                v.copy_(st.p[k].to(v.device).reshape(v.shape))
 
 
 @pytest.mark.parametrize('name', ['calc_grad_ase_small.pt', 'calc_grad_ase_cfg1.pt', 'calc_grad_amp_cfg.pt'])
