@@ -30,15 +30,17 @@
 
 namespace ase {
 
-constexpr int TC2_DRAIN_WARPS = 8;                     // WG0, WG1: drain + store warps, TMEM lane quadrant (warp & 3) x 128-column half (warp >> 2), 232 registers (setmaxnreg)
-constexpr int TC2_CW = 128;                            // accumulator columns per drain thread
-constexpr int TC2_THREADS = 32 * (TC2_DRAIN_WARPS + 4);  // + WG2: warp 8 TMA producer, warp 9 MMA issuer (leader) / TMEM owner (2 idle warps), 40 registers
-// registers: the file is 4 x 16 K per SM and a sub-partition hosts 3 of the 12 warps, so the launch allocation is capped at 168 per thread;
-// setmaxnreg moves WG2's share to the drain warps at run time (2 x 232 + 40 = 504 <= 512 per lane slot)
+constexpr int TC2_DRAIN_WARPS = 16;                    // WG0..WG3: drain + store warps, TMEM lane quadrant (warp & 3) x 64-column quarter (warp >> 2)
+constexpr int TC2_CW = 64;                             // accumulator columns per drain thread
+constexpr int TC2_THREADS = 32 * (TC2_DRAIN_WARPS + 4);  // + WG4: warp 16 TMA producer, warp 17 MMA issuer (leader) / TMEM owner (2 idle warps)
+// registers: the file is 4 x 16 K per SM and a sub-partition hosts 5 of the 20 warps, so the launch allocation is capped at 96 per thread.
+// setmaxnreg moves registers between warpgroups WITHIN the CTA's launch allocation (640 x 96): WG4 releases (96 - 24) x 128 = 9216, which buys
+// the 16 drain warps +16 each (112).  (Asking for 120 -- 3072 more than the pool holds -- parks the fourth warpgroup in setmaxnreg.inc
+// forever: that was the deadlock of the first 16-warp build, profiles/experiments_r02.md.)
 constexpr int TC2_STAGES = 3;
 constexpr int TC2_PLANE_BYTES = 128 * 128;             // 128 operand rows x one 128-byte k-block row
 constexpr int TC2_STAGE_BYTES = 4 * TC2_PLANE_BYTES;   // A_hi | A_lo | B_hi | B_lo of THIS CTA (its 128 rows of A, its 128 of the 256 B rows)
-constexpr int TC2_STG_WARP_BYTES = 4096;               // per drain warp: 32 rows x 128 bytes
+constexpr int TC2_STG_WARP_BYTES = 2048;               // per drain warp: 32 rows x 64 bytes
 constexpr int TC2_SMEM_TOTAL = TC2_STAGES * TC2_STAGE_BYTES + TC2_DRAIN_WARPS * TC2_STG_WARP_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
 static_assert(TC2_SMEM_TOTAL <= 232448, "exceeds the 227 KB a CTA can have");
 
@@ -50,13 +52,13 @@ __device__ __forceinline__ uint4 lds128u(const float* p) {
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(smem_u32(p)));
   return v;
 }
-// staging chunk: 32 rows x 8 pieces of 16 bytes; piece p of row r lives at physical piece p ^ (r & 7): a quarter warp writing one piece
-// of 8 consecutive rows, or reading the 8 pieces of one row, touches all 32 banks exactly once
-__device__ __forceinline__ float* stg_at(float* stg, int r, int p) { return stg + r * 32 + ((p ^ (r & 7)) << 2); }
+// staging chunk of a drain warp: 32 rows x 64 bytes (4 pieces of 16 bytes); piece p of row r lives at physical piece p ^ ((r >> 1) & 3):
+// a quarter warp writing one piece of 8 consecutive rows, or reading all pieces of 2 consecutive rows, touches all 32 banks exactly once
+__device__ __forceinline__ float* stg_at(float* stg, int r, int p) { return stg + r * 16 + ((p ^ ((r >> 1) & 3)) << 2); }
 
 // one stage of the column-sum butterfly: lanes whose `o` bit is clear keep columns [0, w), the others [w, 2w); partners exchange the rest
 template <int o, int w>
-__device__ __forceinline__ void colsum_stage(float (&a)[128], int lane) {
+__device__ __forceinline__ void colsum_stage(float (&a)[TC2_CW], int lane) {
   const bool up = (lane & o) != 0;
 #pragma unroll
   for (int i = 0; i < w; ++i) {
@@ -66,68 +68,67 @@ __device__ __forceinline__ void colsum_stage(float (&a)[128], int lane) {
   }
 }
 
-// activity words of this thread's row for the warp's 128 columns (mask_mode 1 with bits): loaded BEFORE the tile's mainloop
-__device__ __forceinline__ uint4 tc2_load_mask(const TcEpi& e, int64_t m, int nb) {
-  uint4 w = make_uint4(0u, 0u, 0u, 0u);
+// the two activity words of this thread's row for the warp's 64 columns (mask_mode 1 with bits): loaded BEFORE the tile's mainloop
+__device__ __forceinline__ uint2 tc2_load_mask(const TcEpi& e, int64_t m, int nb) {
+  uint2 w = make_uint2(0u, 0u);
   if (!(e.mask_mode == 1 && e.mask_bits) || nb >= e.N || m >= e.M) return w;
-  const int nw = (min(128, e.N - nb) + 31) >> 5;
+  const int nw = (min(TC2_CW, e.N - nb) + 31) >> 5;
   const uint32_t* mb = e.mask_bits + m * e.ldmb + (nb >> 5);
-  if (nw == 4 && (e.ldmb & 3) == 0 && (reinterpret_cast<uintptr_t>(e.mask_bits) & 15) == 0) return __ldg(reinterpret_cast<const uint4*>(mb));
+  if (nw == 2 && (e.ldmb & 1) == 0 && (reinterpret_cast<uintptr_t>(e.mask_bits) & 7) == 0) return __ldg(reinterpret_cast<const uint2*>(mb));
   w.x = __ldg(mb);
   if (nw > 1) w.y = __ldg(mb + 1);
-  if (nw > 2) w.z = __ldg(mb + 2);
-  if (nw > 3) w.w = __ldg(mb + 3);
   return w;
 }
-// bias of columns nb + 4 * lane .. + 3 (zero past N): loaded BEFORE the tile's mainloop, broadcast through the staging buffer at the end
-__device__ __forceinline__ float4 tc2_load_bias(const TcEpi& e, int nb, int lane, int z) {
-  if (!e.bias || (e.accumulate && z != 0) || nb + 4 * lane >= e.N) return make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  return __ldg(reinterpret_cast<const float4*>(e.bias + nb + 4 * lane));
+// bias of columns nb + 2 * lane, + 1 (zero past N): loaded BEFORE the tile's mainloop, broadcast through the staging buffer at the end
+__device__ __forceinline__ float2 tc2_load_bias(const TcEpi& e, int nb, int lane, int z) {
+  if (!e.bias || (e.accumulate && z != 0) || nb + 2 * lane >= e.N) return make_float2(0.0f, 0.0f);
+  return __ldg(reinterpret_cast<const float2*>(e.bias + nb + 2 * lane));
 }
 
-// Store phase of one drain warp.  acc[c] = raw accumulator of C[mw0 + lane][nb + c], c < 128 (thread = row).  Everything that is arithmetic
-// happens in this row layout, straight-line on registers (128 independent elements: full ILP, nothing from global memory in a dependency
-// chain -- bias, mask words and scales were fetched before the mainloop): scale -> bias -> ReLU -> activity bits (one 16-byte store per row)
-// -> mask bits -> max |C| -> FP16 hi/lo split.  Only finished BYTES go through the warp's 4 KB staging buffer (thread = row in, XOR-swizzled,
-// conflict-free; 4 rows x 128 bytes per global store instruction out): fp32 C in 32-column chunks (or RED for split-K), half planes in
-// 64-column chunks.  Column sums (bias gradients) use a 124-shuffle butterfly at the very end.  Same semantics and order as epilogue_rows /
+// Store phase of one drain warp.  acc[c] = raw accumulator of C[mw0 + lane][nb + c], c < 64 (thread = row).  Everything that is arithmetic
+// happens in this row layout, straight-line on registers (64 independent elements: full ILP, nothing from global memory in a dependency
+// chain -- bias, mask words and scales were fetched before the mainloop): scale -> bias -> ReLU -> activity bits (one 8-byte store per row)
+// -> mask bits -> max |C| -> FP16 hi/lo split.  Only finished BYTES go through the warp's 2 KB staging buffer (thread = row in, XOR-swizzled,
+// conflict-free; 8 rows x 64 bytes per global store instruction out): fp32 C in 16-column chunks (or RED for split-K), half planes in
+// 32-column chunks.  Column sums (bias gradients) use a 62-shuffle butterfly at the very end.  Same semantics and order as epilogue_rows /
 // epilogue_fast in gemm_tc.cu.  Columns >= N hold exact zeros and are never stored.
-// (History, profiles/experiments_r02.md: a fully unrolled first version that also loaded bias / masks here ran at 6 clocks per instruction
-// on serialised L2 latencies and instruction fetch; a rolled coalesced-layout version was bound by its dependency chains; a 16-warp x 64-column
-// variant (setmaxnreg 120 / 24) deadlocked on the device and was dropped.)
-__device__ __forceinline__ void tc2_store(const TcEpi& e, float (&acc)[128], float* stg, int mw0, int nb, int lane, const float4 bias4, const uint4 maskw,
+// (History, profiles/experiments_r02.md: 8 drain warps x 128 columns ran the store phase at 35 % issue efficiency -- 2 warps per scheduler,
+// spills at 128 accumulators + temporaries -- and it is serial with the next tile's drains (13.9 k of 39.3 k clocks per tile); 16 warps x 64
+// columns halve the per-thread work and double the latency hiding (10.5 k clocks).  Earlier still: a version that loaded bias / masks here ran at 6 clocks per instruction on serialised L2
+// latencies and instruction fetch; a rolled coalesced-layout version was bound by its dependency chains.)
+__device__ __forceinline__ void tc2_store(const TcEpi& e, float (&acc)[TC2_CW], float* stg, int mw0, int nb, int lane, const float2 bias2, const uint2 maskw,
                                           float s1, float s2, float cscale) {
-  const int ncols = min(128, e.N - nb);              // valid columns of this warp (a multiple of 8: the host requires N % 8 == 0)
+  const int ncols = min(TC2_CW, e.N - nb);           // valid columns of this warp (a multiple of 8: the host requires N % 8 == 0)
   if (ncols <= 0) return;
   const int64_t m = mw0 + lane;                      // this thread's row
-  const int rr = lane >> 3, pp = lane & 7;           // coalesced pass: row 4 * it + rr, 16-byte piece pp
+  const int rr = lane >> 2, pp = lane & 3;           // coalesced pass: row 8 * it + rr, 16-byte piece pp
   // undo the operands' power-of-two plane scales (two exact multiplies; their product alone could underflow)
 #pragma unroll
-  for (int c = 0; c < 128; ++c) acc[c] = s2 * (s1 * acc[c]);
-  if (e.bias) {                // uniform; bias4 is zero where it does not apply
-    sts128(stg + 4 * lane, bias4.x, bias4.y, bias4.z, bias4.w);
+  for (int c = 0; c < TC2_CW; ++c) acc[c] = s2 * (s1 * acc[c]);
+  if (e.bias) {                // uniform; bias2 is zero where it does not apply
+    reinterpret_cast<float2*>(stg)[lane] = bias2;
     __syncwarp();
 #pragma unroll
-    for (int c = 0; c < 128; c += 4) {
+    for (int c = 0; c < TC2_CW; c += 4) {
       const float4 b = lds128(stg + c);              // same address in every lane: a broadcast
       acc[c] += b.x; acc[c + 1] += b.y; acc[c + 2] += b.z; acc[c + 3] += b.w;
     }
     __syncwarp();
   }
-  if (e.accumulate) {          // split-K / accumulating GEMMs (dW): fp32 RED into C, 4 rows x 128 bytes per instruction
+  if (e.accumulate) {          // split-K / accumulating GEMMs (dW): fp32 RED into C, 8 rows x 64 bytes per instruction
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (q * 32 < ncols) {
+    for (int q = 0; q < TC2_CW / 16; ++q) {
+      if (q * 16 < ncols) {
 #pragma unroll
-        for (int p = 0; p < 8; ++p) sts128(stg_at(stg, lane, p), acc[q * 32 + 4 * p], acc[q * 32 + 4 * p + 1], acc[q * 32 + 4 * p + 2], acc[q * 32 + 4 * p + 3]);
+        for (int p = 0; p < 4; ++p) sts128(stg_at(stg, lane, p), acc[q * 16 + 4 * p], acc[q * 16 + 4 * p + 1], acc[q * 16 + 4 * p + 2], acc[q * 16 + 4 * p + 3]);
         __syncwarp();
-        const int col = q * 32 + pp * 4;
+        const int col = q * 16 + pp * 4;
         float* cp = e.C + (int64_t)(mw0 + rr) * e.ldc + nb + col;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const float4 v = lds128(stg_at(stg, it * 4 + rr, pp));
+        for (int it = 0; it < 4; ++it) {
+          const float4 v = lds128(stg_at(stg, it * 8 + rr, pp));
           if (col < ncols) asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-          cp += 4 * e.ldc;
+          cp += 8 * e.ldc;
         }
         __syncwarp();
       }
@@ -136,28 +137,28 @@ __device__ __forceinline__ void tc2_store(const TcEpi& e, float (&acc)[128], flo
   }
   if (e.act == 1) {            // (tanh outputs are 64 wide in every network of the path: they never reach this kernel, see gemm_tc2_epilogue_ok)
 #pragma unroll
-    for (int c = 0; c < 128; ++c) acc[c] = fmaxf(acc[c], 0.0f);
+    for (int c = 0; c < TC2_CW; ++c) acc[c] = fmaxf(acc[c], 0.0f);
   }
   const int nw = (ncols + 31) >> 5;                  // 32-column activity words this warp owns in its rows
   if (e.relu_bits) {
-    uint32_t w[4];
+    uint32_t w[2];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 2; ++q) {
       w[q] = 0u;
 #pragma unroll
       for (int i = 0; i < 32; ++i) w[q] |= (acc[q * 32 + i] > 0.0f) ? (1u << i) : 0u;
     }
     uint32_t* rb = e.relu_bits + m * e.ldrb + (nb >> 5);
-    if (nw == 4 && (e.ldrb & 3) == 0 && (reinterpret_cast<uintptr_t>(e.relu_bits) & 15) == 0) *reinterpret_cast<uint4*>(rb) = make_uint4(w[0], w[1], w[2], w[3]);
+    if (nw == 2 && (e.ldrb & 1) == 0 && (reinterpret_cast<uintptr_t>(e.relu_bits) & 7) == 0) *reinterpret_cast<uint2*>(rb) = make_uint2(w[0], w[1]);
     else {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) if (q < nw) rb[q] = w[q];
+      rb[0] = w[0];
+      if (nw > 1) rb[1] = w[1];
     }
   }
   if (e.mask_mode == 1 && e.mask_bits) {
-    const uint32_t w[4] = {maskw.x, maskw.y, maskw.z, maskw.w};
+    const uint32_t w[2] = {maskw.x, maskw.y};
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
+    for (int q = 0; q < 2; ++q) {
 #pragma unroll
       for (int i = 0; i < 32; ++i) acc[q * 32 + i] = ((w[q] >> i) & 1u) ? acc[q * 32 + i] : 0.0f;
     }
@@ -165,7 +166,7 @@ __device__ __forceinline__ void tc2_store(const TcEpi& e, float (&acc)[128], flo
   if (e.c_amax || (e.Chi && e.flag)) {
     float amax = 0.0f;
 #pragma unroll
-    for (int c = 0; c < 128; ++c) amax = fmaxf(amax, fabsf(acc[c]));
+    for (int c = 0; c < TC2_CW; ++c) amax = fmaxf(amax, fabsf(acc[c]));
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
     if (lane == 0 && amax > 0.0f) {
@@ -174,52 +175,52 @@ __device__ __forceinline__ void tc2_store(const TcEpi& e, float (&acc)[128], flo
       if (e.Chi && e.flag && cscale == 0.0f) atomicOr(e.flag, 2u);                    // the site only ever saw all-zero tensors, now there is data
     }
   }
-  if (!e.skip_c) {             // fp32 C: 32-column chunks
+  if (!e.skip_c) {             // fp32 C: 16-column chunks
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      if (q * 32 < ncols) {
+    for (int q = 0; q < TC2_CW / 16; ++q) {
+      if (q * 16 < ncols) {
 #pragma unroll
-        for (int p = 0; p < 8; ++p) sts128(stg_at(stg, lane, p), acc[q * 32 + 4 * p], acc[q * 32 + 4 * p + 1], acc[q * 32 + 4 * p + 2], acc[q * 32 + 4 * p + 3]);
+        for (int p = 0; p < 4; ++p) sts128(stg_at(stg, lane, p), acc[q * 16 + 4 * p], acc[q * 16 + 4 * p + 1], acc[q * 16 + 4 * p + 2], acc[q * 16 + 4 * p + 3]);
         __syncwarp();
-        const int col = q * 32 + pp * 4;
+        const int col = q * 16 + pp * 4;
         float* cp = e.C + (int64_t)(mw0 + rr) * e.ldc + nb + col;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const float4 v = lds128(stg_at(stg, it * 4 + rr, pp));
+        for (int it = 0; it < 4; ++it) {
+          const float4 v = lds128(stg_at(stg, it * 8 + rr, pp));
           if (col < ncols) *reinterpret_cast<float4*>(cp) = v;
-          cp += 4 * e.ldc;
+          cp += 8 * e.ldc;
         }
         __syncwarp();
       }
     }
   }
-  if (e.Chi) {                 // half planes of C: 64-column chunks (128 bytes per row per plane); the lo words wait in registers for the hi chunk
+  if (e.Chi) {                 // half planes of C: 32-column chunks (64 bytes per row per plane); the lo words wait in registers for the hi chunk
 #pragma unroll
-    for (int ch = 0; ch < 2; ++ch) {
-      if (ch * 64 < ncols) {
-        uint32_t lw[32];
+    for (int ch = 0; ch < TC2_CW / 32; ++ch) {
+      if (ch * 32 < ncols) {
+        uint32_t lw[16];
 #pragma unroll
-        for (int p = 0; p < 8; ++p) {
+        for (int p = 0; p < 4; ++p) {
           uint32_t hw[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i)
-            split_f16x2(acc[ch * 64 + 8 * p + 2 * i] * cscale, acc[ch * 64 + 8 * p + 2 * i + 1] * cscale, hw[i], lw[4 * p + i]);
+            split_f16x2(acc[ch * 32 + 8 * p + 2 * i] * cscale, acc[ch * 32 + 8 * p + 2 * i + 1] * cscale, hw[i], lw[4 * p + i]);
           sts128u(stg_at(stg, lane, p), hw[0], hw[1], hw[2], hw[3]);
         }
-        const int col = ch * 64 + pp * 8;
+        const int col = ch * 32 + pp * 8;
 #pragma unroll
         for (int pl = 0; pl < 2; ++pl) {
           if (pl == 1) {
 #pragma unroll
-            for (int p = 0; p < 8; ++p) sts128u(stg_at(stg, lane, p), lw[4 * p], lw[4 * p + 1], lw[4 * p + 2], lw[4 * p + 3]);
+            for (int p = 0; p < 4; ++p) sts128u(stg_at(stg, lane, p), lw[4 * p], lw[4 * p + 1], lw[4 * p + 2], lw[4 * p + 3]);
           }
           __syncwarp();
           __half* dp = reinterpret_cast<__half*>(pl == 0 ? e.Chi : e.Clo) + (int64_t)(mw0 + rr) * e.ldp + nb + col;
 #pragma unroll
-          for (int it = 0; it < 8; ++it) {
-            const uint4 v = lds128u(stg_at(stg, it * 4 + rr, pp));
+          for (int it = 0; it < 4; ++it) {
+            const uint4 v = lds128u(stg_at(stg, it * 8 + rr, pp));
             if (col < ncols) *reinterpret_cast<uint4*>(dp) = v;
-            dp += 4 * e.ldp;
+            dp += 8 * e.ldp;
           }
           __syncwarp();
         }
@@ -227,14 +228,14 @@ __device__ __forceinline__ void tc2_store(const TcEpi& e, float (&acc)[128], flo
     }
   }
   if (e.colsum) {              // bias gradient of the layer whose dZ this GEMM produces: sum over the warp's 32 rows, then one RED per column
-    colsum_stage<16, 64>(acc, lane);
-    colsum_stage<8, 32>(acc, lane);
-    colsum_stage<4, 16>(acc, lane);
-    colsum_stage<2, 8>(acc, lane);
-    colsum_stage<1, 4>(acc, lane);
-    const int cb = ((lane & 16) ? 64 : 0) + ((lane & 8) ? 32 : 0) + ((lane & 4) ? 16 : 0) + ((lane & 2) ? 8 : 0) + ((lane & 1) ? 4 : 0);
+    colsum_stage<16, 32>(acc, lane);
+    colsum_stage<8, 16>(acc, lane);
+    colsum_stage<4, 8>(acc, lane);
+    colsum_stage<2, 4>(acc, lane);
+    colsum_stage<1, 2>(acc, lane);
+    const int cb = ((lane & 16) ? 32 : 0) + ((lane & 8) ? 16 : 0) + ((lane & 4) ? 8 : 0) + ((lane & 2) ? 4 : 0) + ((lane & 1) ? 2 : 0);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) if (cb + j < ncols) atomicAdd(e.colsum + nb + cb + j, acc[j]);
+    for (int j = 0; j < 2; ++j) if (cb + j < ncols) atomicAdd(e.colsum + nb + cb + j, acc[j]);
   }
 }
 
@@ -264,7 +265,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
   uint64_t* full = bars;                       // [3]  leader only: TMA bytes of BOTH CTAs -> MMA issuer
   uint64_t* empty = bars + TC2_STAGES;         // [3]  both CTAs: MMAs done with the stage (multicast commit) -> both producers
   uint64_t* buf_full = bars + 2 * TC2_STAGES;  // [2]  both CTAs: the k-block partial in TMEM buffer b is complete (multicast commit) -> drain warps
-  uint64_t* buf_empty = buf_full + 2;          // [2]  leader only: the 16 drain warps of both CTAs pulled buffer b out of TMEM -> MMA issuer
+  uint64_t* buf_empty = buf_full + 2;          // [2]  leader only: the 32 drain warps of both CTAs pulled buffer b out of TMEM -> MMA issuer
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(buf_full + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -293,7 +294,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
   const uint32_t tmem_base = *tmem_slot;       // two 256-column accumulator buffers: k-block g lands in buffer g & 1
 
   if (warp >= TC2_DRAIN_WARPS) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (warp == TC2_DRAIN_WARPS && lane == 0) {
       // ---------------- TMA producer (one per CTA): this CTA's 128 rows of A and its 128 of the tile's 256 B rows, every k-block of every
       // item; completion bytes go to the LEADER's full barrier
@@ -370,8 +371,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
     }
     __syncwarp();
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    // ---------------- drain / store warps 0..7: TMEM lane quadrant lg, 128-column half cq of this CTA's 128 x 256 accumulator
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
+    // ---------------- drain / store warps 0..15: TMEM lane quadrant lg, 64-column quarter cq of this CTA's 128 x 256 accumulator
     const int lg = warp & 3, cq = warp >> 2;
     const uint32_t lane_off = (uint32_t)(lg * 32) << 16;
     float* stg = reinterpret_cast<float*>(stg_base + warp * TC2_STG_WARP_BYTES);
@@ -384,8 +385,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
     for (int j = 0; j < my_items; ++j) {
       const Tc2Item it = tc2_item(pair + j * npairs, tiles_n, tiles_m2, e);
       const int m0 = it.m0 + (int)rank * 128;
-      const uint4 maskw = tc2_load_mask(e, (int64_t)m0 + lg * 32 + lane, it.n0 + cq * TC2_CW);     // in flight under the whole mainloop
-      const float4 bias4 = tc2_load_bias(e, it.n0 + cq * TC2_CW, lane, it.z);
+      const uint2 maskw = tc2_load_mask(e, (int64_t)m0 + lg * 32 + lane, it.n0 + cq * TC2_CW);     // in flight under the whole mainloop
+      const float2 bias2 = tc2_load_bias(e, it.n0 + cq * TC2_CW, lane, it.z);
       float acc[TC2_CW];
 #pragma unroll
       for (int i = 0; i < TC2_CW; ++i) acc[i] = 0.0f;
@@ -405,7 +406,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(buf_empty_leader + 8u * b);
       }
-      if (m0 < e.M && !(e.debug & 1)) tc2_store(e, acc, stg, m0 + lg * 32, it.n0 + cq * TC2_CW, lane, bias4, maskw, s1, s2, cscale);
+      if (m0 < e.M && !(e.debug & 1)) tc2_store(e, acc, stg, m0 + lg * 32, it.n0 + cq * TC2_CW, lane, bias2, maskw, s1, s2, cscale);
     }
   }
   tc_fence_before();

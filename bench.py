@@ -190,7 +190,7 @@ def run_ours(args):
 
     # e2e: host-resident simulator state, H2D every sim step, D2H of the step's train_result
     agent, env = _make_agent(torch, rank, world, 'host', seed=0)
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(max(4, args.warmup)):       # >= 3: the rollout's CUDA graph is captured on the third play_steps call
         agent.update_epoch(); agent.train_epoch()
     e2e_secs, host = _timed_epochs(torch, agent, args.steps, world, d2h=True)
     e2e_value = env_steps / e2e_secs

