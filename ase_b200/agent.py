@@ -105,6 +105,9 @@ class CommonAgent:
         if self.multi_gpu:
             import torch.distributed as dist
             self.rank, self.rank_size = dist.get_rank(), dist.get_world_size()
+            if self.ppo_device.type == 'cuda':
+                from .dist_utils import init_comm
+                init_comm()            # the library's own NCCL communicator: the per-minibatch allreduce goes through the C ABI
         self._load_config_params(config)
         self.model = self._build_learner(config)
         self.dataset = AMPDataset(self.batch_size, self.minibatch_size, self.ppo_device)
@@ -120,6 +123,9 @@ class CommonAgent:
         # 'rollout_graph' (default True) additionally captures the whole rollout in one CUDA graph
         self._device_rollout = bool(config.get('device_rollout', True))
         self._rollout_graph_enabled = bool(config.get('rollout_graph', True))
+        # 'minibatch_graph' (default True): from the third epoch on, gather + calc_gradients of a minibatch are one CUDA graph launch
+        self._mb_graph_enabled = bool(config.get('minibatch_graph', True))
+        self._graphs_on = True
 
     # ------------------------------------------------------------------ construction helpers
     def _load_config_params(self, config):
@@ -395,7 +401,7 @@ class CommonAgent:
         pass
 
     def _play_steps_device(self):
-        if not self._rollout_graph_enabled:
+        if not (self._rollout_graph_enabled and self._graphs_on):
             self._rollout_loop()
             return
         if self._rollout_graph is None:
@@ -458,9 +464,96 @@ class CommonAgent:
             ops.gather_rows(items)
         return out
 
-    def _minibatch(self, i):
+    def _minibatch_pairs(self, i):
+        """[(key, source tensor, int64 row indices)] of minibatch i, and {alias key: key} for tensors that are the same rows twice."""
         idx = self.dataset.sample_indices(i)
-        return self._gather([(k, v, idx) for k, v in self.dataset.values_dict.items() if v is not None]), idx
+        return [(k, v, idx) for k, v in self.dataset.values_dict.items() if v is not None], {}
+
+    def _minibatch(self, i):
+        pairs, alias = self._minibatch_pairs(i)
+        mb = self._gather(pairs)
+        for k, src in alias.items():
+            mb[k] = mb[src]
+        return mb, pairs[0][2]
+
+    # ------------------------------------------------------------------ one minibatch update = one CUDA graph launch
+    def set_graphs(self, enabled):
+        """Switch the captured CUDA graphs (rollout, minibatch update) on / off; captured graphs are kept.  bench.py turns them off for the one
+        epoch it instruments per launch."""
+        self._graphs_on = bool(enabled)
+
+    def _static_dataset(self):
+        """The epoch's dataset tensors are fresh allocations every epoch; the captured gather needs stable addresses: copy them into
+        persistent buffers (~1 GB per epoch at config-3 sizes, 0.3 ms)."""
+        store = self.__dict__.setdefault('_ds_static', {})
+
+        def pin(k, v):
+            b = store.get(k)
+            if b is None or b.shape != v.shape or b.dtype != v.dtype:
+                b = store[k] = torch.empty(v.shape, dtype=v.dtype, device=v.device)
+            b.copy_(v)
+            return b
+        vd = self.dataset.values_dict
+        for k, v in list(vd.items()):
+            if v is not None and v.is_cuda:
+                vd[k] = pin(k, v)
+        if getattr(self, '_amp_obs_flat', None) is not None:
+            self._amp_obs_flat = pin('__amp_obs_flat', self._amp_obs_flat)
+
+    def _train_minibatch(self, i):
+        use_graph = self._mb_graph_enabled and self._graphs_on and self.ppo_device.type == 'cuda' and self.epoch_num >= 3
+        if not use_graph:
+            mb, _ = self._minibatch(i)
+            self.train_actor_critic(mb)
+            return
+        pairs, alias = self._minibatch_pairs(i)
+        sig = tuple((k, v.data_ptr(), tuple(v.shape), idx.shape[0]) for k, v, idx in pairs) + tuple(sorted(alias.items()))
+        st = self.__dict__.get('_mb_graph_state')
+        if st is None or st['sig'] != sig:
+            if st is not None and st.get('recaptures', 0) >= 3:        # sources keep moving (an env that reallocates): stay eager
+                mb, _ = self._minibatch(i)
+                self.train_actor_critic(mb)
+                return
+            st = self._capture_minibatch(pairs, alias, sig, (st or {}).get('recaptures', -1) + 1)
+        # feed the static index / latent buffers, replay, finish (allreduce + Adam + train_result row) eagerly
+        seen = {}
+        for (k, v, idx), sidx in zip(pairs, st['idx']):
+            if id(idx) not in seen:
+                sidx.copy_(idx); seen[id(idx)] = True
+        nz = self._new_latents(self.minibatch_size)
+        if nz is not None:
+            st['newz'].copy_(nz)
+        st['graph'].replay()
+        self._finish_update(st['out'])
+
+    def _capture_minibatch(self, pairs, alias, sig, recaptures):
+        by_idx, sidx_list, items, mb = {}, [], [], {}
+        bufs = self.__dict__.setdefault('_mb_bufs', {})
+        for k, v, idx in pairs:
+            assert v.dtype == torch.float32 and v.is_contiguous() and v.is_cuda, k
+            sidx = by_idx.get(id(idx))
+            if sidx is None:
+                sidx = by_idx[id(idx)] = idx.clone()
+            sidx_list.append(sidx)
+            shape = (idx.shape[0],) + tuple(v.shape[1:])
+            dst = bufs.get(k)
+            if dst is None or tuple(dst.shape) != shape:
+                dst = bufs[k] = torch.empty(shape, dtype=torch.float32, device=v.device)
+            items.append((v, dst, sidx))
+            mb[k] = dst
+        for k, src in alias.items():
+            mb[k] = mb[src]
+        nz = self._new_latents(self.minibatch_size)
+        newz = None if nz is None else nz.clone()
+        self.set_train()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            ops.gather_rows(items)
+            out = self.model.calc_gradients(mb, newz, update_rms=True)
+        st = {'sig': sig, 'graph': g, 'idx': sidx_list, 'newz': newz, 'out': out, 'recaptures': recaptures}
+        self._mb_graph_state = st
+        return st
 
     # ------------------------------------------------------------------ update (common_agent.py:353-435)
     def _new_latents(self, n):
@@ -469,6 +562,10 @@ class CommonAgent:
     def calc_gradients(self, input_dict):
         self.set_train()
         out = self.model.calc_gradients(input_dict, self._new_latents(input_dict['obs'].shape[0]), update_rms=True)
+        self._finish_update(out)
+
+    def _finish_update(self, out):
+        """Gradient averaging over ranks (one allreduce through the C ABI), Adam, and the train_result row of this minibatch."""
         scale = 1.0
         if self.multi_gpu:
             from .dist_utils import allreduce_grads
@@ -511,10 +608,11 @@ class CommonAgent:
             from .lib import TR_COUNT
             self._tr_buf = torch.zeros(nmb, TR_COUNT + 1, device=self.ppo_device)       # + the learner's plane-scale status
         self._tr_i = 0
+        if self._mb_graph_enabled and self._graphs_on and self.ppo_device.type == 'cuda' and self.epoch_num >= 3:
+            self._static_dataset()
         for _ in range(self.mini_epochs_num):
             for i in range(len(self.dataset)):
-                mb, idx = self._minibatch(i)
-                self.train_actor_critic(mb)
+                self._train_minibatch(i)
         self._post_update(batch_dict)
         self.model.plane_flag_to(self._tr_buf[:, -1])
         ev[2].record()
@@ -701,18 +799,18 @@ class AMPAgent(CommonAgent):
         vd['rand_action_mask'] = batch_dict['rand_action_mask']
         self._amp_obs_flat = batch_dict['amp_obs']
 
-    def _minibatch(self, i):
+    def _minibatch_pairs(self, i):
         idx = self.dataset.sample_indices(i)
         a = idx[:self._amp_minibatch_size].contiguous()      # only amp_minibatch_size rows are consumed (ase_agent.py:172-181)
         pairs = [(k, v, idx) for k, v in self.dataset.values_dict.items() if v is not None]
         pairs.append(('amp_obs', self._amp_obs_flat, a))
         pairs.append(('amp_obs_demo', self._amp_obs_demo_buffer._data_buf['amp_obs'], self._demo_idx[a]))
+        alias = {}
         if self._replay_idx is not None:
             pairs.append(('amp_obs_replay', self._amp_replay_buffer._data_buf['amp_obs'], self._replay_idx[a]))
-        mb = self._gather(pairs)
-        if self._replay_idx is None:
-            mb['amp_obs_replay'] = mb['amp_obs']
-        return mb, idx
+        else:
+            alias['amp_obs_replay'] = 'amp_obs'
+        return pairs, alias
 
     def _post_update(self, batch_dict):
         """amp_agent.py:579-593 _store_replay_amp_obs."""

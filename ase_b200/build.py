@@ -14,6 +14,16 @@ HEADERS = ['common.cuh', 'kernels.h', 'tc_common.cuh', os.path.join('..', '..', 
 NVCC_FLAGS = ['-O3', '-std=c++17', '-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-Xcompiler', '-fPIC']
 
 
+def _nccl_include():
+    """nccl.h of the NCCL build PyTorch ships (comm.cu resolves the library itself at run time with dlopen)."""
+    import importlib.util
+    for cand in ([os.path.join(os.path.dirname(os.path.dirname(importlib.util.find_spec('torch').origin)), 'nvidia', 'nccl', 'include')]
+                 if importlib.util.find_spec('torch') else []) + ['/usr/include']:
+        if os.path.exists(os.path.join(cand, 'nccl.h')):
+            return cand
+    return None
+
+
 def _nvcc():
     for c in (os.environ.get('NVCC'), '/usr/local/cuda/bin/nvcc', 'nvcc'):
         if c and (os.path.isabs(c) and os.path.exists(c) or not os.path.isabs(c)):
@@ -55,7 +65,8 @@ def build(force=False, verbose=False):
     todo = [s for s in _sources() if force or _stale(s)]
 
     def compile_one(src):
-        cmd = [_nvcc()] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', '-o', _obj(src), src]
+        inc = ['-I', _nccl_include()] if (src == 'comm.cu' and _nccl_include()) else []
+        cmd = [_nvcc()] + NVCC_FLAGS + inc + (['-Xptxas', '-v'] if verbose else []) + ['-c', '-o', _obj(src), src]
         return src, subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
 
     with ThreadPoolExecutor(max_workers=max(1, min(len(todo), os.cpu_count() or 1))) as ex:

@@ -90,7 +90,8 @@ EXPORTS = ['ase_abi_version', 'ase_last_error', 'ase_launch_count', 'ase_obs_bui
            'ase_gemm', 'ase_gemm_tc_workspace_bytes', 'ase_gemm_tc_profile', 'ase_gemm_tc_profile_read', 'ase_learner_num_params', 'ase_learner_param_desc',
            'ase_learner_arena_floats', 'ase_learner_workspace_bytes', 'ase_learner_create', 'ase_learner_destroy', 'ase_learner_params_changed', 'ase_learner_plane_status', 'ase_learner_plane_flag_to', 'ase_learner_plane_flag_clear',
            'ase_learner_calc_gradients', 'ase_learner_adam_step', 'ase_learner_eval_actor_critic',
-           'ase_learner_eval_disc_enc']
+           'ase_learner_eval_disc_enc', 'ase_comm_load', 'ase_comm_unique_id', 'ase_comm_create', 'ase_comm_destroy', 'ase_grad_allreduce',
+           'ase_comm_allreduce_f64']
 
 
 class AseError(RuntimeError):
@@ -143,6 +144,13 @@ def _load():
     lib.ase_learner_adam_step.argtypes = [vp, C.POINTER(LearnerState), i64, f32, vp]
     lib.ase_learner_eval_actor_critic.argtypes = [vp, C.POINTER(LearnerState), vp, vp, i32, vp, vp, vp]
     lib.ase_learner_eval_disc_enc.argtypes = [vp, C.POINTER(LearnerState), vp, i32, vp, vp, vp]
+    lib.ase_comm_load.argtypes = [C.c_char_p]
+    lib.ase_comm_unique_id.argtypes = [vp]
+    lib.ase_comm_create.argtypes = [vp, i32, i32, C.POINTER(vp)]
+    lib.ase_comm_destroy.argtypes = [vp]
+    lib.ase_comm_destroy.restype = None
+    lib.ase_grad_allreduce.argtypes = [vp, vp, i64, vp]
+    lib.ase_comm_allreduce_f64.argtypes = [vp, vp, i64, vp]
     return lib
 
 

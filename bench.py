@@ -173,9 +173,11 @@ def run_ours(args):
     launches = L.launch_count() - launches0
     play_t, upd_t, _ = agent.epoch_times()
     # roofline numerator / denominator: ONE extra epoch, outside the timed region, with CUDA events around every tcgen05 GEMM launch
+    agent.set_graphs(False)          # per-launch events need eager launches: this one epoch runs without the rollout / minibatch CUDA graphs
     L.lib.ase_gemm_tc_profile(1)
     agent.update_epoch(); agent.train_epoch()
     torch.cuda.synchronize()
+    agent.set_graphs(True)
     tot_ms, nl, fl = C.c_double(), C.c_int64(), C.c_double()
     L.check(L.lib.ase_gemm_tc_profile_read(C.byref(tot_ms), C.byref(nl), C.byref(fl)), 'profile_read')
     L.lib.ase_gemm_tc_profile(0)
@@ -183,6 +185,7 @@ def run_ours(args):
     plane_flags = _plane_flags(agent)      # FP16 operand-plane scale misses during the warm-up / timed epochs (read outside the timed region)
     tr = {k: float(v) for k, v in zip(L.TR_NAMES, agent._tr_buf[-1].tolist())}
     graph_rollout = getattr(agent, '_rollout_graph', None) is not None
+    mb_graph = getattr(agent, '_mb_graph_state', None) is not None
     env_steps = args.steps * NUM_ENVS * HORIZON * world
     value = env_steps / secs
     del agent, env
@@ -229,6 +232,8 @@ def run_ours(args):
                         "the timed region, overlapping compute on the copy engine), the epoch's train_result series is read back (D2H); it can "
                         "come out slightly ahead of `value`, whose synthetic env refreshes its state with device-to-device copies on the compute stream"},
         "gpu_launches": int(launches),
+        "gpu_launches_note": "kernels launched by libase_b200.so through host calls during the timed epochs; launches replayed from the captured CUDA "
+                             "graphs (rollout: ~60 per sim step; minibatch update: ~100) are NOT re-counted -- the instrumented epoch launches " + str(int(nl.value)) + " tcgen05 GEMMs eagerly",
         "clocks": clk.summary(),
         "roofline": {"bound": "tensor", "kernel": "gemm_tc256_kernel / gemm_tc_kernel (tcgen05.mma kind::f16, 3 MMAs per product on scaled FP16 hi/lo planes)" if GEMM_BACKEND == 2
                      else "gemm_tc_kernel (tcgen05.mma kind::tf32, 3xTF32)", "achieved": achieved_tf,
@@ -241,7 +246,8 @@ def run_ours(args):
                              "forces 3 MMAs per product (hi.hi + lo.hi + hi.lo): the ceiling against the bf16 peak is 1/3 with FP16 planes "
                              "(backend 2), 1/6 with TF32 planes (backend 1)",
                      "learner_tflops_algorithmic": nmb * FLOP_PER_MINIBATCH / 1e12 / (upd_t * args.steps) if upd_t > 0 else None},
-        "split": {"play_time_s_last_step": play_t, "update_time_s_last_step": upd_t, "rollout_cuda_graph": graph_rollout},
+        "split": {"play_time_s_last_step": play_t, "update_time_s_last_step": upd_t, "rollout_cuda_graph": graph_rollout,
+                  "minibatch_cuda_graph": mb_graph, "instrumented_epoch_s": {"play": prof_play_t, "update": prof_upd_t}},
         "plane_status": plane_flags,      # ase_learner_plane_status after both runs: 0 = every FP16 plane scale prediction held
         "train_result_last": tr,
     }

@@ -341,6 +341,21 @@ int ase_learner_eval_actor_critic(AseLearner* l, const AseLearnerState* st, cons
 int ase_learner_eval_disc_enc(AseLearner* l, const AseLearnerState* st, const float* amp_obs, int rows,
                               float* disc_logits, float* enc_pred, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU: env-sharded data parallelism, ONE fp32 sum-allreduce of the flat gradient arena per minibatch over NCCL (NVLink 5 / NVSwitch)
+ * between calc_gradients and adam_step (learning/amp_agent.py:348-363: Horovod averages inside optimizer.step; 1/world goes into
+ * ase_learner_adam_step's grad_scale).  The communicator is the library's own: rank 0 calls ase_comm_unique_id, the host ships the 128
+ * bytes to the other ranks (torch.distributed's store in the Python mirror), every rank calls ase_comm_create.  libnccl.so.2 is resolved at
+ * run time (ase_comm_load(path) or the default search path), never at link time.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct AseComm AseComm;
+int ase_comm_load(const char* libnccl_path);
+int ase_comm_unique_id(uint8_t* out128);
+int ase_comm_create(const uint8_t* id128, int rank, int world, AseComm** out);
+void ase_comm_destroy(AseComm* c);
+int ase_grad_allreduce(AseComm* c, float* buf, int64_t count, void* stream);
+int ase_comm_allreduce_f64(AseComm* c, double* buf, int64_t count, void* stream);   /* RunningMeanStd averaging once per epoch (hvd.sync_stats) */
+
 #ifdef __cplusplus
 }
 #endif
