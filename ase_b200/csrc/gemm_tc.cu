@@ -1434,7 +1434,7 @@ int PlaneRegistry::prep_weights(const float* const* src, const int* rows, const 
     touched[site] = true;
   }
   if (nb == 0) return ASE_OK;
-  dim3 grid(16, nb);
+  dim3 grid(48, nb);      // 28 MB of weights per optimizer step: 16 slices per tensor ran at 1 TB/s (ncu r02: 56 us), 48 x 16 tensors fill the 148 SMs 5 deep
   if (!all_known) {
     tc_amax_batch_kernel<<<grid, 256, 0, st>>>(batch, amax);
     ASE_LAUNCH_OK();

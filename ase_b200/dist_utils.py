@@ -20,6 +20,7 @@ def init_comm():
     import glob
     import os
     from . import lib as L
+    os.environ.setdefault('NCCL_DEBUG_FILE', '/dev/stderr')       # NCCL's own log lines go to stderr, not into the caller's stdout
     cands = glob.glob(os.path.join(os.path.dirname(os.path.dirname(torch.__file__)), 'nvidia', 'nccl', 'lib', 'libnccl.so.2'))
     L.check(L.lib.ase_comm_load(cands[0].encode() if cands else None), 'ase_comm_load')
     buf = (C.c_uint8 * 128)()
