@@ -12,7 +12,6 @@
 // accumulate it in fp32 registers with round-to-nearest adds -- the tensor core's own accumulation truncates):
 //   gemm_tc256_kernel  128 x 256 tile, 2-stage ring, 8 drain warps            (N >= 384; the workhorse)
 //   gemm_tc_kernel     128 x 128 / 128 x 64 tile, double-buffered main tile   (narrow N)
-//   gemm_tcp_kernel    persistent 128 x 128 ping-pong kernel                  (opt-in experiment, ASE_TC_PERSIST=1)
 // Store phase: registers -> shared staging tile -> coalesced pass with bias / ReLU / tanh / mask (fp32 or 1-bit), optional
 // fp32 C, half planes (predicted power-of-two scale), ReLU activity bits, max |C|, fused column sums, split-K fp32 RED.
 // Descriptor formats follow the PTX ISA "tcgen05 shared memory descriptor" / "instruction descriptor" tables
@@ -286,10 +285,7 @@ struct TcSmem {
 // accumulator), double buffered; the epilogue warps drain each k-block's partial tile with tcgen05.ld and add it
 // into fp32 registers with round-to-nearest FADDs while the tensor core works on the next k-block.  The two
 // correction terms (2^-11 smaller) accumulate across all of K in a third TMEM tile: their truncation is negligible.
-// CL = cluster size along N (1 or 2).  With CL = 2 the two CTAs of a cluster work on the same 128 rows of A: each
-// loads HALF of the A planes and multicasts it into both CTAs' shared memory, halving the A traffic out of L2
-// (the mainloop is operand-feed bound: 64 KB per k-block per CTA against ~768 MMA cycles).
-template <int BN, int STAGES, bool AMN, bool BMN, int CL, bool H>
+template <int BN, int STAGES, bool AMN, bool BMN, bool H>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const TcEpi e) {
@@ -312,7 +308,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
   const int nkb = min(e.kb_per_split, e.kb_total - kb_begin);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }   // every CTA of the cluster releases a stage
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int b = 0; b < 2; ++b) { mbar_init(&main_full[b], 1); mbar_init(&main_empty[b], 4); }   // 4 epilogue warps arrive
     mbar_init(corr_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -324,12 +320,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (CL > 1) cluster_sync_all();        // peers' barriers are initialised before any multicast / remote arrive
   pdl_sync();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_corr = tmem_base + 2 * BN;
-  const uint32_t crank = (CL > 1) ? cluster_rank() : 0u;
-  constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -340,29 +333,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
         mbar_expect_tx(&full[s], SM::STAGE_BYTES);
         uint8_t* st = smem + s * SM::STAGE_BYTES;
         const int k0 = (kb_begin + kb) * F::BK;
-        if (CL == 1) {
-          if (!AMN) {          // K-major planes [rows, K]: one box of 128 rows x one k-block
-            tma_load_2d(st, &tmAhi, &full[s], k0, m0);
-            tma_load_2d(st + SM::A_BYTES, &tmAlo, &full[s], k0, m0);
-          } else {             // MN-major planes [K, rows]: boxes of BK k-rows x 128 bytes of m
+        if (!AMN) {          // K-major planes [rows, K]: one box of 128 rows x one k-block
+          tma_load_2d(st, &tmAhi, &full[s], k0, m0);
+          tma_load_2d(st + SM::A_BYTES, &tmAlo, &full[s], k0, m0);
+        } else {             // MN-major planes [K, rows]: boxes of BK k-rows x 128 bytes of m
 #pragma unroll
-            for (int b = 0; b < TC_BM / F::MN_BOX; ++b) {
-              tma_load_2d(st + b * F::MN_BOX_BYTES, &tmAhi, &full[s], m0 + b * F::MN_BOX, k0);
-              tma_load_2d(st + SM::A_BYTES + b * F::MN_BOX_BYTES, &tmAlo, &full[s], m0 + b * F::MN_BOX, k0);
-            }
-          }
-        } else {               // this CTA's half of A, multicast to the whole cluster (the A maps have 128/CL-row boxes)
-          constexpr int HALF = TC_BM / CL;
-          if (!AMN) {
-            tma_load_2d_mc(st + crank * HALF * 128, &tmAhi, &full[s], k0, m0 + crank * HALF, MC_MASK);
-            tma_load_2d_mc(st + SM::A_BYTES + crank * HALF * 128, &tmAlo, &full[s], k0, m0 + crank * HALF, MC_MASK);
-          } else {
-#pragma unroll
-            for (int bb = 0; bb < HALF / 32; ++bb) {
-              const int b = crank * (HALF / 32) + bb;
-              tma_load_2d_mc(st + b * 4096, &tmAhi, &full[s], m0 + b * 32, k0, MC_MASK);
-              tma_load_2d_mc(st + SM::A_BYTES + b * 4096, &tmAlo, &full[s], m0 + b * 32, k0, MC_MASK);
-            }
+          for (int b = 0; b < TC_BM / F::MN_BOX; ++b) {
+            tma_load_2d(st + b * F::MN_BOX_BYTES, &tmAhi, &full[s], m0 + b * F::MN_BOX, k0);
+            tma_load_2d(st + SM::A_BYTES + b * F::MN_BOX_BYTES, &tmAlo, &full[s], m0 + b * F::MN_BOX, k0);
           }
         }
         if (!BMN) {
@@ -405,8 +383,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
           tc_mma<H>(tmem_corr, adesc(a_lo, k), bdesc(b_hi, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
           tc_mma<H>(tmem_corr, adesc(a_hi, k), bdesc(b_lo, k), idesc, 1u);
         }
-        if (CL == 1) tc_commit(&empty[s]);     // all 12 MMAs have read this smem stage
-        else tc_commit_mc(&empty[s], MC_MASK); // ... and tell every CTA that multicasts into it
+        tc_commit(&empty[s]);     // all 12 MMAs have read this smem stage
       }
       tc_commit(corr_full);
     }
@@ -471,7 +448,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (CL > 1) cluster_sync_all();        // nobody exits while a peer may still multicast into / arrive on this CTA
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS));
   }
@@ -490,27 +466,23 @@ constexpr int TC256_THREADS = 384;       // WG0: warp 0 TMA, warp 1 MMA (+2 idle
 constexpr int TC256_BN = 256;
 constexpr int TC256_STAGES = 2;
 
-// One k-block (SUB: one 32-wide k sub-block) of operand planes into the 128x256 kernel's ring (producer thread only); it is
-// called from two places (before and after the CTA-wide setup barrier).
-//   SUB = false: 2 stages x 96 KB, 64-wide k-blocks (default).
-//   SUB = true : 4 stages x 48 KB, 32-wide sub-blocks released one by one, so loads are issued 14-16 MMA slots ahead instead of 12.
-//                Built to test whether the mainloop (74 % of the MMA rate) waits on load LATENCY: it does not -- same slope, 3 % slower
-//                overall -- so the limit is the L2 -> SM operand bandwidth (1.6 GB per 32768x1024x1024 GEMM at ~13 TB/s).  Opt-in.
-template <bool AMN, bool BMN, bool H, bool SUB>
+// One k-block of operand planes into the 128x256 kernel's ring (2 stages x 96 KB; producer thread only); it is called from
+// two places (before and after the CTA-wide setup barrier).
+template <bool AMN, bool BMN, bool H>
 __device__ __forceinline__ void tc256_issue_kb(const CUtensorMap* tmAhi, const CUtensorMap* tmAlo, const CUtensorMap* tmBhi, const CUtensorMap* tmBlo,
                                                uint8_t* smem, uint64_t* full, uint64_t* empty, int kb, int kb_begin, int m0, int n0) {
-  constexpr int BN = 256, STAGES = SUB ? 4 : 2;
+  constexpr int BN = 256, STAGES = 2;
   using F = TcFmt<H>;
-  constexpr int KW = SUB ? 32 : F::BK;                       // k elements per ring slot
-  constexpr int ROWB = SUB ? 64 : 128;                        // bytes per K-major operand row in a slot
+  constexpr int KW = F::BK;                                   // k elements per ring slot
+  constexpr int ROWB = 128;                                   // bytes per K-major operand row in a slot
   constexpr int A_BYTES = TC_BM * ROWB, B_BYTES = BN * ROWB, STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-  constexpr int MN_BOX_BYTES = SUB ? 4096 : F::MN_BOX_BYTES;  // [KW k-rows x 64 mn] halfs
+  constexpr int MN_BOX_BYTES = F::MN_BOX_BYTES;
   const int s = kb % STAGES;
   const uint32_t ph = (kb / STAGES) & 1;
   mbar_wait(&empty[s], ph ^ 1);
   mbar_expect_tx(&full[s], STAGE_BYTES);
   uint8_t* st = smem + s * STAGE_BYTES;
-  const int k0 = (SUB ? 2 * kb_begin + kb : kb_begin + kb) * KW;
+  const int k0 = (kb_begin + kb) * KW;
   if (!AMN) {
     tma_load_2d(st, tmAhi, &full[s], k0, m0);
     tma_load_2d(st + A_BYTES, tmAlo, &full[s], k0, m0);
@@ -536,15 +508,12 @@ __device__ __forceinline__ void tc256_issue_kb(const CUtensorMap* tmAhi, const C
   }
 }
 
-template <bool AMN, bool BMN, bool H, bool SUB>
+template <bool AMN, bool BMN, bool H>
 __global__ void __launch_bounds__(TC256_THREADS, 1)
 gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
                   const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const TcEpi e) {
-  static_assert(!SUB || H, "32-wide k sub-blocks exist for the FP16 format only");
-  constexpr int BN = TC256_BN, STAGES = SUB ? 4 : TC256_STAGES;
-  using SM = TcSmem<BN, TC256_STAGES>;                      // total bytes are the same: 2 x 96 KB or 4 x 48 KB
-  constexpr int SLOT_BYTES = SM::STAGE_BYTES / (SUB ? 2 : 1);
-  constexpr int SA_BYTES = SM::A_BYTES / (SUB ? 2 : 1), SB_BYTES = SM::B_BYTES / (SUB ? 2 : 1);
+  constexpr int BN = TC256_BN, STAGES = TC256_STAGES;
+  using SM = TcSmem<BN, TC256_STAGES>;
   using F = TcFmt<H>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -562,9 +531,9 @@ gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
   const int nkb = min(e.kb_per_split, e.kb_total - kb_begin);
 
   auto issue_kb = [&](int kb) {
-    tc256_issue_kb<AMN, BMN, H, SUB>(&tmAhi, &tmAlo, &tmBhi, &tmBlo, smem, full, empty, kb, kb_begin, m0, n0);
+    tc256_issue_kb<AMN, BMN, H>(&tmAhi, &tmAlo, &tmBhi, &tmBlo, smem, full, empty, kb, kb_begin, m0, n0);
   };
-  const int nslots = SUB ? 2 * nkb : nkb;     // ring slots this CTA streams (32-wide sub-blocks / 64-wide k-blocks)
+  const int nslots = nkb;                     // ring slots this CTA streams
   const int kb_early = min(STAGES, nslots);   // slots whose loads are issued before the CTA-wide setup barrier
   if (threadIdx.x == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAhi)) : "memory");
@@ -598,57 +567,24 @@ gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
       auto adesc = [](uint32_t base, int k) { return tc_desc<H, AMN>(base, k); };
       auto bdesc = [](uint32_t base, int k) { return tc_desc<H, BMN>(base, k); };
       for (int kb = 0; kb < nkb; ++kb) {
-        if (!SUB) {
-          const int s = kb % STAGES;
-          const uint32_t ph = (kb / STAGES) & 1;
-          mbar_wait(&full[s], ph);
-          mbar_wait(main_empty, (uint32_t)((kb & 1) ^ 1));       // drain of k-block kb-1 (runs under its correction MMAs)
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
-          const uint32_t a_hi = sa, a_lo = sa + SM::A_BYTES, b_hi = sa + 2 * SM::A_BYTES, b_lo = b_hi + SM::B_BYTES;
+        const int s = kb % STAGES;
+        const uint32_t ph = (kb / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        mbar_wait(main_empty, (uint32_t)((kb & 1) ^ 1));       // drain of k-block kb-1 (runs under its correction MMAs)
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * SM::STAGE_BYTES);
+        const uint32_t a_hi = sa, a_lo = sa + SM::A_BYTES, b_hi = sa + 2 * SM::A_BYTES, b_lo = b_hi + SM::B_BYTES;
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma<H>(tmem_base, adesc(a_hi, k), bdesc(b_hi, k), idesc, k > 0 ? 1u : 0u);
-          tc_commit(main_full);
-          if (!(e.debug & 4))
+        for (int k = 0; k < 4; ++k)
+          tc_mma<H>(tmem_base, adesc(a_hi, k), bdesc(b_hi, k), idesc, k > 0 ? 1u : 0u);
+        tc_commit(main_full);
+        if (!(e.debug & 4))
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            tc_mma<H>(tmem_corr, adesc(a_lo, k), bdesc(b_hi, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            tc_mma<H>(tmem_corr, adesc(a_hi, k), bdesc(b_lo, k), idesc, 1u);
-          }
-          tc_commit(&empty[s]);
-        } else {
-          // two 32-wide sub-blocks per 64-wide k-block: main MMAs of both (the drain granularity stays 64), then each
-          // sub-block's correction MMAs followed by the release of its ring slot
-          const int g0 = 2 * kb, g1 = 2 * kb + 1;
-          const int s0 = g0 % STAGES, s1 = g1 % STAGES;
-          mbar_wait(&full[s0], (uint32_t)((g0 / STAGES) & 1));
-          mbar_wait(&full[s1], (uint32_t)((g1 / STAGES) & 1));
-          mbar_wait(main_empty, (uint32_t)((kb & 1) ^ 1));
-          tc_fence_after();
-          const uint32_t base0 = smem_u32(smem + s0 * SLOT_BYTES), base1 = smem_u32(smem + s1 * SLOT_BYTES);
-#pragma unroll
-          for (int x = 0; x < 2; ++x) {
-            const uint32_t sa = x ? base1 : base0;
-            const uint32_t a_hi = sa, b_hi = sa + 2 * SA_BYTES;
-#pragma unroll
-            for (int k = 0; k < 2; ++k)
-              tc_mma<H>(tmem_base, tc_desc_sub<AMN>(a_hi, k), tc_desc_sub<BMN>(b_hi, k), idesc, (x > 0 || k > 0) ? 1u : 0u);
-          }
-          tc_commit(main_full);
-#pragma unroll
-          for (int x = 0; x < 2; ++x) {
-            const uint32_t sa = x ? base1 : base0;
-            const uint32_t a_hi = sa, a_lo = sa + SA_BYTES, b_hi = sa + 2 * SA_BYTES, b_lo = b_hi + SB_BYTES;
-            if (!(e.debug & 4))
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              tc_mma<H>(tmem_corr, tc_desc_sub<AMN>(a_lo, k), tc_desc_sub<BMN>(b_hi, k), idesc, (kb > 0 || x > 0 || k > 0) ? 1u : 0u);
-              tc_mma<H>(tmem_corr, tc_desc_sub<AMN>(a_hi, k), tc_desc_sub<BMN>(b_lo, k), idesc, 1u);
-            }
-            tc_commit(&empty[x ? s1 : s0]);
-          }
+        for (int k = 0; k < 4; ++k) {
+          tc_mma<H>(tmem_corr, adesc(a_lo, k), bdesc(b_hi, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          tc_mma<H>(tmem_corr, adesc(a_hi, k), bdesc(b_lo, k), idesc, 1u);
         }
+        tc_commit(&empty[s]);
       }
       tc_commit(corr_full);
     }
@@ -705,214 +641,6 @@ gemm_tc256_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_consta
     if (e.colsum && !e.accumulate) {
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (n0 + et < e.N) atomicAdd(e.colsum + n0 + et, s_colsum[et]);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
-  }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Persistent ping-pong kernel: 128 x 128 tiles, one CTA per SM looping over tiles, store phase of tile j hidden under the
-// mainloop of tile j+1.  The one-tile-per-CTA kernels above serialise, per tile, CTA launch + barrier init + TMEM allocation
-// + first-load latency + mainloop + store phase (ncu r01: the tensor pipe is idle for ~60 % of a CTA's lifetime).  Here
-//   * TMEM holds TWO accumulator sets (main 128 + correction 128 columns each); the MMA warp alternates between them;
-//   * two sets of four drain / epilogue warps own one accumulator set each: while set x runs the store phase of tile j,
-//     set 1-x drains the k-block partials of tile j+1;
-//   * the TMA producer never stops: the operand ring (2 stages x 64 KB) is separate from the store-phase staging tile
-//     (68 KB), which the two sets hand to each other through an mbarrier;
-//   * barriers, TMEM and tensor maps are set up once per CTA.
-// A 128x128 tile needs 85 B/clk of operand planes against the ~64 B/clk an SM ingests, so its mainloop runs at the same
-// ~75 % of the MMA rate the 128x256 mainloop reaches -- but nothing else is left on the critical path.
-// Used for every non-split GEMM with N > 64 in the FP16 format (split-K dW keeps the 128x256 / 128x128 kernels).
-// ---------------------------------------------------------------------------------------------------------
-constexpr int TCP_THREADS = 384;       // WG0: warp 0 TMA, warp 1 MMA (+2 idle); WG1: drain set 0; WG2: drain set 1
-constexpr int TCP_BN = 128;
-constexpr int TCP_STAGES = 2;
-constexpr int TCP_STAGE_BYTES = 4 * TC_BM * 128;              // A_hi, A_lo, B_hi, B_lo: 16 KB each
-constexpr int TCP_CS_LD = TCP_BN + 4;
-constexpr int TCP_STAGING_BYTES = TC_BM * TCP_CS_LD * 4 + TCP_BN * 4;     // staged tile + per-tile column sums
-constexpr int TCP_SMEM_TOTAL = TCP_STAGES * TCP_STAGE_BYTES + TCP_STAGING_BYTES + 256 /*barriers*/ + 1024 /*align slack*/;
-
-template <bool AMN, bool BMN, bool H>
-__global__ void __launch_bounds__(TCP_THREADS, 1)
-gemm_tcp_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
-                const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, const TcEpi e, const int tiles_n, const int num_tiles) {
-  constexpr int BN = TCP_BN, STAGES = TCP_STAGES, A_BYTES = TC_BM * 128, B_BYTES = BN * 128;
-  using F = TcFmt<H>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* cs = reinterpret_cast<float*>(smem + STAGES * TCP_STAGE_BYTES);
-  float* s_colsum = cs + TC_BM * TCP_CS_LD;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * TCP_STAGE_BYTES + TCP_STAGING_BYTES);
-  uint64_t* full = bars;                 // [2]  TMA -> MMA
-  uint64_t* empty = bars + 2;            // [2]  MMA -> TMA
-  uint64_t* main_full = bars + 4;        // [2 sets] MMA -> drain: a k-block partial of A_hi.B_hi is complete
-  uint64_t* main_empty = bars + 6;       // [2 sets] drain -> MMA
-  uint64_t* corr_full = bars + 8;        // [2 sets] MMA -> drain: all MMAs of the tile are complete
-  uint64_t* tmem_free = bars + 10;       // [2 sets] drain -> MMA: the set's TMEM was read out (next tile may overwrite it)
-  uint64_t* stage_free = bars + 12;      // drain set -> other drain set: the staging tile was consumed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nkb = e.kb_total;
-  const int my_tiles = (num_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;     // tiles blockIdx.x, +gridDim.x, ...
-
-  if (threadIdx.x == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAhi)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmAlo)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBhi)) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmBlo)) : "memory");
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int x = 0; x < 2; ++x) { mbar_init(&main_full[x], 1); mbar_init(&main_empty[x], 4); mbar_init(&corr_full[x], 1); mbar_init(&tmem_free[x], 4); }
-    mbar_init(stage_free, 4);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  pdl_sync();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp < 4) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 0 && lane == 0) {
-      // ---------------- TMA producer: streams the k-blocks of all of this CTA's tiles through the ring
-      int g = 0;
-      for (int j = 0; j < my_tiles; ++j) {
-        const int t = (int)blockIdx.x + j * (int)gridDim.x;
-        const int m0 = (t / tiles_n) * TC_BM, n0 = (t % tiles_n) * BN;
-        for (int kb = 0; kb < nkb; ++kb, ++g) {
-          const int s = g % STAGES;
-          const uint32_t ph = (g / STAGES) & 1;
-          mbar_wait(&empty[s], ph ^ 1);
-          mbar_expect_tx(&full[s], TCP_STAGE_BYTES);
-          uint8_t* st = smem + s * TCP_STAGE_BYTES;
-          const int k0 = kb * F::BK;
-          if (!AMN) {
-            tma_load_2d(st, &tmAhi, &full[s], k0, m0);
-            tma_load_2d(st + A_BYTES, &tmAlo, &full[s], k0, m0);
-          } else {
-#pragma unroll
-            for (int b = 0; b < TC_BM / F::MN_BOX; ++b) {
-              tma_load_2d(st + b * F::MN_BOX_BYTES, &tmAhi, &full[s], m0 + b * F::MN_BOX, k0);
-              tma_load_2d(st + A_BYTES + b * F::MN_BOX_BYTES, &tmAlo, &full[s], m0 + b * F::MN_BOX, k0);
-            }
-          }
-          if (!BMN) {
-            tma_load_2d(st + 2 * A_BYTES, &tmBhi, &full[s], k0, n0);
-            tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tmBlo, &full[s], k0, n0);
-          } else {
-#pragma unroll
-            for (int b = 0; b < BN / F::MN_BOX; ++b) {
-              tma_load_2d(st + 2 * A_BYTES + b * F::MN_BOX_BYTES, &tmBhi, &full[s], n0 + b * F::MN_BOX, k0);
-              tma_load_2d(st + 2 * A_BYTES + B_BYTES + b * F::MN_BOX_BYTES, &tmBlo, &full[s], n0 + b * F::MN_BOX, k0);
-            }
-          }
-        }
-      }
-    } else if (warp == 1 && lane == 0) {
-      // ---------------- MMA issuer: tile j accumulates in TMEM set j & 1
-      const uint32_t idesc = tc_idesc<H>(AMN, BMN, BN);
-      int g = 0;
-      for (int j = 0; j < my_tiles; ++j) {
-        const int x = j & 1, u = j >> 1;
-        mbar_wait(&tmem_free[x], (uint32_t)((u & 1) ^ 1));        // the set's previous tile (j-2) was read out of TMEM
-        tc_fence_after();
-        const uint32_t tmem_main = tmem_base + (uint32_t)(x * 256), tmem_corr = tmem_main + 128;
-        for (int kb = 0; kb < nkb; ++kb, ++g) {
-          const int s = g % STAGES;
-          const uint32_t ph = (g / STAGES) & 1;
-          const int c = u * nkb + kb;                            // this set's running k-block count
-          mbar_wait(&full[s], ph);
-          mbar_wait(&main_empty[x], (uint32_t)((c & 1) ^ 1));     // the drain of the set's previous k-block partial
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + s * TCP_STAGE_BYTES);
-          const uint32_t a_hi = sa, a_lo = sa + A_BYTES, b_hi = sa + 2 * A_BYTES, b_lo = b_hi + B_BYTES;
-#pragma unroll
-          for (int k = 0; k < 4; ++k)
-            tc_mma<H>(tmem_main, tc_desc<H, AMN>(a_hi, k), tc_desc<H, BMN>(b_hi, k), idesc, k > 0 ? 1u : 0u);
-          tc_commit(&main_full[x]);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            tc_mma<H>(tmem_corr, tc_desc<H, AMN>(a_lo, k), tc_desc<H, BMN>(b_hi, k), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            tc_mma<H>(tmem_corr, tc_desc<H, AMN>(a_hi, k), tc_desc<H, BMN>(b_lo, k), idesc, 1u);
-          }
-          tc_commit(&empty[s]);
-        }
-        tc_commit(&corr_full[x]);
-      }
-    }
-    __syncwarp();
-  } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    // ---------------- drain / epilogue set x = (warp - 4) / 4 handles tiles x, x+2, ...
-    const int x = (warp - 4) >> 2;
-    const int lg = warp & 3;                 // TMEM lane quadrant
-    const uint32_t lane_off = (uint32_t)(lg * 32) << 16;
-    const uint32_t tmem_main = tmem_base + (uint32_t)(x * 256), tmem_corr = tmem_main + 128;
-    const int bar_id = 1 + x;
-    const int et = (warp & 3) * 32 + lane;   // 0..127 within the set
-    for (int j = x; j < my_tiles; j += 2) {
-      const int u = j >> 1;
-      const int t = (int)blockIdx.x + j * (int)gridDim.x;
-      const int m0 = (t / tiles_n) * TC_BM, n0 = (t % tiles_n) * BN;
-      float acc[BN];
-#pragma unroll
-      for (int i = 0; i < BN; ++i) acc[i] = 0.0f;
-      for (int kb = 0; kb < nkb; ++kb) {
-        const int c = u * nkb + kb;
-        mbar_wait(&main_full[x], (uint32_t)(c & 1));
-        tc_fence_after();
-#pragma unroll
-        for (int cc = 0; cc < BN; cc += 32) {
-          float v[32];
-          tc_ld_32x32(tmem_main + lane_off + (uint32_t)cc, v);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) acc[cc + i] += v[i];
-        }
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&main_empty[x]);
-      }
-      mbar_wait(&corr_full[x], (uint32_t)(u & 1));
-      tc_fence_after();
-      if (j > 0) mbar_wait(stage_free, (uint32_t)((j - 1) & 1));        // the other set finished reading the staging tile (tile j-1)
-      const float s1 = (H && e.a_inv) ? *e.a_inv : 1.0f;
-      const float s2 = e.alpha * ((H && e.b_inv) ? *e.b_inv : 1.0f);
-      {
-        float* crow_s = cs + (lg * 32 + lane) * TCP_CS_LD;
-#pragma unroll
-        for (int cc = 0; cc < BN; cc += 32) {
-          float v[32];
-          tc_ld_32x32(tmem_corr + lane_off + (uint32_t)cc, v);
-#pragma unroll
-          for (int i = 0; i < 32; i += 4)
-            sts128(crow_s + cc + i, s2 * (s1 * (acc[cc + i] + v[i])), s2 * (s1 * (acc[cc + i + 1] + v[i + 1])),
-                   s2 * (s1 * (acc[cc + i + 2] + v[i + 2])), s2 * (s1 * (acc[cc + i + 3] + v[i + 3])));
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_free[x]);          // both TMEM tiles of the set are in registers / shared memory now
-      if (e.colsum) s_colsum[et] = 0.0f;
-      asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-      if (!(e.debug & 1)) {
-        if (epilogue_fast_ok(e, m0, n0, BN, H) && !(e.debug & 256)) epilogue_fast<H, 4, 32>(e, cs, TCP_CS_LD, s_colsum, lg * 32, m0, n0, lane);
-        else epilogue_rows<H>(e, cs, TCP_CS_LD, s_colsum, lg * 32, 32, BN, m0, n0, lane);
-      }
-      if (e.colsum && !e.accumulate) {
-        asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
-        if (n0 + et < e.N) atomicAdd(e.colsum + n0 + et, s_colsum[et]);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(stage_free);             // this warp is done with the staging tile and the column sums
     }
   }
   tc_fence_before();
@@ -1112,10 +840,8 @@ static std::unordered_map<MapKey, CUtensorMap, MapKeyHash>& map_cache() { static
 
 // 2D map over [rows, cols] elements (cols contiguous, row stride ld elements); the box is one 128-byte row chunk
 // (32 fp32 words / 64 halfs) x box_rows
-// sub (halfs only): maps for the 32-wide k sub-block ring -- K-major boxes are 32 elements (64 bytes, SWIZZLE_64B) wide, MN-major boxes 32 k-rows tall
-static int encode_cached(CUtensorMap* tm, const void* base, int rows, int cols, int64_t ld, int box_rows, bool mn_major, bool half = false, bool sub = false) {
-  if (sub && mn_major) box_rows = 32;
-  MapKey k{base, rows, cols, ld, box_rows, (mn_major ? 1 : 0) | (half ? 2 : 0) | (sub ? 4 : 0)};
+static int encode_cached(CUtensorMap* tm, const void* base, int rows, int cols, int64_t ld, int box_rows, bool mn_major, bool half = false) {
+  MapKey k{base, rows, cols, ld, box_rows, (mn_major ? 1 : 0) | (half ? 2 : 0)};
   auto& c = map_cache();
   auto it = c.find(k);
   if (it != c.end()) { memcpy(tm, &it->second, sizeof(CUtensorMap)); return ASE_OK; }
@@ -1123,12 +849,11 @@ static int encode_cached(CUtensorMap* tm, const void* base, int rows, int cols, 
   if (!enc) { set_error("cuTensorMapEncodeTiled not available from the driver"); return ASE_ERR_UNSUPPORTED; }
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstr[1] = {(cuuint64_t)ld * (half ? 2 : 4)};
-  cuuint32_t box[2] = {half ? ((sub && !mn_major) ? 32u : 64u) : 32u, (cuuint32_t)box_rows};
-  const bool sw64 = half && sub && !mn_major;
+  cuuint32_t box[2] = {half ? 64u : 32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   // MN-major: fp32 words need the 32-byte-atom flavour of the 128B swizzle, halfs the plain one (see the smem descriptors)
   CUresult r = enc(tm, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstr, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw64 ? CU_TENSOR_MAP_SWIZZLE_64B : ((mn_major && !half) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B),
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, (mn_major && !half) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(%d x %d, ld %lld, box %d) failed with CUresult %d", rows, cols, (long long)ld, box_rows, (int)r); return ASE_ERR_CUDA; }
   if (c.size() > 8192) c.clear();
@@ -1137,8 +862,8 @@ static int encode_cached(CUtensorMap* tm, const void* base, int rows, int cols, 
 }
 
 // 2D tensor map over a zero-padded plane [rows_p, cols_p] (cols contiguous); box = [box_rows x 32 cols], 128B swizzle
-static int make_map(CUtensorMap* tm, const void* base, int rows_p, int cols_p, int box_rows, bool mn_major = false, bool half = false, bool sub = false) {
-  return encode_cached(tm, base, rows_p, cols_p, cols_p, box_rows, mn_major, half, sub);
+static int make_map(CUtensorMap* tm, const void* base, int rows_p, int cols_p, int box_rows, bool mn_major = false, bool half = false) {
+  return encode_cached(tm, base, rows_p, cols_p, cols_p, box_rows, mn_major, half);
 }
 
 static inline int pad_to(int x, int m) { return (x + m - 1) / m * m; }
@@ -1230,52 +955,46 @@ int tc_pdl() {   // env ASE_TC_PDL=0 launches the GEMMs fully stream-serialised
   return v;
 }
 
-template <int BN, int STAGES, bool AMN, bool BMN, int CL, bool H>
+template <int BN, int STAGES, bool AMN, bool BMN, bool H>
 static int launch_tc(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcEpi& e,
                      int splits, cudaStream_t st) {
   using SM = TcSmem<BN, STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    ASE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, AMN, BMN, CL, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    ASE_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES, AMN, BMN, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr_set = true;
   }
   dim3 grid(ceil_div(e.N, BN), ceil_div(e.M, TC_BM), splits);
-  grid.x = (grid.x + CL - 1) / CL * CL;       // whole clusters; a padding CTA computes an all-out-of-range tile and stores nothing
   const bool prof = g_prof.on;
   if (prof) prof_mark(st);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid; cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = SM::TOTAL; cfg.stream = st;
-  cudaLaunchAttribute attr[2];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[1].val.programmaticStreamSerializationAllowed = tc_pdl();
-  cfg.attrs = attr; cfg.numAttrs = 2;
-  ASE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, AMN, BMN, CL, H>, ah, al, bh, bl, e));
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = tc_pdl();
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  ASE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, STAGES, AMN, BMN, H>, ah, al, bh, bl, e));
   if (prof) { prof_mark(st); g_prof.flops += 2.0 * (double)e.M * (double)e.N * (double)e.K; }
   ASE_LAUNCH_OK();
   return ASE_OK;
 }
 
-template <int BN, int STAGES, int CL, bool H>
+template <int BN, int STAGES, bool H>
 static int launch_tc_major(bool amn, bool bmn, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                            const TcEpi& e, int splits, cudaStream_t st) {
-  if (!amn && !bmn) return launch_tc<BN, STAGES, false, false, CL, H>(ah, al, bh, bl, e, splits, st);
-  if (!amn && bmn) return launch_tc<BN, STAGES, false, true, CL, H>(ah, al, bh, bl, e, splits, st);
-  if (amn && !bmn) return launch_tc<BN, STAGES, true, false, CL, H>(ah, al, bh, bl, e, splits, st);
-  return launch_tc<BN, STAGES, true, true, CL, H>(ah, al, bh, bl, e, splits, st);
+  if (!amn && !bmn) return launch_tc<BN, STAGES, false, false, H>(ah, al, bh, bl, e, splits, st);
+  if (!amn && bmn) return launch_tc<BN, STAGES, false, true, H>(ah, al, bh, bl, e, splits, st);
+  if (amn && !bmn) return launch_tc<BN, STAGES, true, false, H>(ah, al, bh, bl, e, splits, st);
+  return launch_tc<BN, STAGES, true, true, H>(ah, al, bh, bl, e, splits, st);
 }
 
-// A-multicast clusters are OFF by default: measured on B200 (profiles/experiments_r01.md) they do not help -- the
-// mainloop is bound by the per-SM ingest port (~64 B/clk), which multicast does not relieve.  ASE_TC_CLUSTER=2|4 enables them
-// (TF32 format only).
-template <bool AMN, bool BMN, bool H, bool SUB>
+template <bool AMN, bool BMN, bool H>
 static int launch_tc256(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcEpi& e,
                         int splits, cudaStream_t st) {
   using SM = TcSmem<TC256_BN, TC256_STAGES>;
   static bool attr_set = false;
   if (!attr_set) {
-    ASE_CUDA_OK(cudaFuncSetAttribute(gemm_tc256_kernel<AMN, BMN, H, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
+    ASE_CUDA_OK(cudaFuncSetAttribute(gemm_tc256_kernel<AMN, BMN, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM::TOTAL));
     attr_set = true;
   }
   dim3 grid(ceil_div(e.N, TC256_BN), ceil_div(e.M, TC_BM), splits);
@@ -1287,56 +1006,18 @@ static int launch_tc256(const CUtensorMap& ah, const CUtensorMap& al, const CUte
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = tc_pdl();
   cfg.attrs = attr; cfg.numAttrs = 1;
-  ASE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc256_kernel<AMN, BMN, H, SUB>, ah, al, bh, bl, e));
+  ASE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc256_kernel<AMN, BMN, H>, ah, al, bh, bl, e));
   if (prof) { prof_mark(st); g_prof.flops += 2.0 * (double)e.M * (double)e.N * (double)e.K; }
   ASE_LAUNCH_OK();
   return ASE_OK;
 }
-template <bool H, bool SUB>
+template <bool H>
 static int launch_tc256_major(bool amn, bool bmn, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
                               const TcEpi& e, int splits, cudaStream_t st) {
-  if (!amn && !bmn) return launch_tc256<false, false, H, SUB>(ah, al, bh, bl, e, splits, st);
-  if (!amn && bmn) return launch_tc256<false, true, H, SUB>(ah, al, bh, bl, e, splits, st);
-  if (amn && !bmn) return launch_tc256<true, false, H, SUB>(ah, al, bh, bl, e, splits, st);
-  return launch_tc256<true, true, H, SUB>(ah, al, bh, bl, e, splits, st);
-}
-static int tc_sub() {   // env ASE_TC_SUB=1: 4 x 48 KB ring of 32-wide k sub-blocks instead of the 2 x 96 KB ring of 64-wide k-blocks (FP16 format).
-  const char* d = getenv("ASE_TC_SUB");     // OFF by default: measured 3 % slower (profiles/experiments_r01.md) -- the mainloop is bound by the
-  return d ? (atoi(d) != 0) : 0;            // L2 -> SM operand bandwidth, not by load latency.  Read per call so that the tests can cover both rings.
-}
-template <bool AMN, bool BMN, bool H>
-static int launch_tcp(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl, const TcEpi& e, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    ASE_CUDA_OK(cudaFuncSetAttribute(gemm_tcp_kernel<AMN, BMN, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, TCP_SMEM_TOTAL));
-    attr_set = true;
-  }
-  static int sms = 0;
-  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
-  const int tiles_n = ceil_div(e.N, TCP_BN), tiles_m = ceil_div(e.M, TC_BM), num_tiles = tiles_n * tiles_m;
-  const bool prof = g_prof.on;
-  if (prof) prof_mark(st);
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(min(num_tiles, sms)); cfg.blockDim = dim3(TCP_THREADS); cfg.dynamicSmemBytes = TCP_SMEM_TOTAL; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = tc_pdl();
-  cfg.attrs = attr; cfg.numAttrs = 1;
-  ASE_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tcp_kernel<AMN, BMN, H>, ah, al, bh, bl, e, tiles_n, num_tiles));
-  if (prof) { prof_mark(st); g_prof.flops += 2.0 * (double)e.M * (double)e.N * (double)e.K; }
-  ASE_LAUNCH_OK();
-  return ASE_OK;
-}
-static int launch_tcp_major(bool amn, bool bmn, const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& bh, const CUtensorMap& bl,
-                            const TcEpi& e, cudaStream_t st) {
-  if (!amn && !bmn) return launch_tcp<false, false, true>(ah, al, bh, bl, e, st);
-  if (!amn && bmn) return launch_tcp<false, true, true>(ah, al, bh, bl, e, st);
-  if (amn && !bmn) return launch_tcp<true, false, true>(ah, al, bh, bl, e, st);
-  return launch_tcp<true, true, true>(ah, al, bh, bl, e, st);
-}
-static int tc_persist() {   // env ASE_TC_PERSIST=1 routes non-split GEMMs to the persistent ping-pong kernel.  OFF by default: measured slower
-  const char* d = getenv("ASE_TC_PERSIST");     // (profiles/experiments_r01.md: its 128x128 mainloop is operand-ingest bound).  Read per call so
-  return d ? atoi(d) : 0;                       // the tests can switch it on for the kernel's own parity cases.
+  if (!amn && !bmn) return launch_tc256<false, false, H>(ah, al, bh, bl, e, splits, st);
+  if (!amn && bmn) return launch_tc256<false, true, H>(ah, al, bh, bl, e, splits, st);
+  if (amn && !bmn) return launch_tc256<true, false, H>(ah, al, bh, bl, e, splits, st);
+  return launch_tc256<true, true, H>(ah, al, bh, bl, e, splits, st);
 }
 int gemm_tc_tile_n(int N);
 static int tc_tile256();
@@ -1348,12 +1029,6 @@ bool gemm_tc_pair_candidate(int backend, int M, int N) { return backend == 2 && 
 static int tc_tile256() {   // env ASE_TC_TILE256=0 keeps every GEMM on the 128x128 kernel
   static int v = -1;
   if (v < 0) { const char* d = getenv("ASE_TC_TILE256"); v = d ? atoi(d) : 1; }
-  return v;
-}
-
-static int tc_cluster() {
-  static int v = -1;
-  if (v < 0) { const char* d = getenv("ASE_TC_CLUSTER"); v = d ? atoi(d) : 1; if (v != 1 && v != 2 && v != 4) v = 1; }
   return v;
 }
 
@@ -1499,8 +1174,8 @@ static int resolve_operand(PlaneRegistry* reg, const float* ptr, int64_t ld, int
 }
 
 // tensor map over a (sub-)view of a plane with TRUE extents: TMA zero-fills everything outside [rows, cols]
-static int make_view_map(CUtensorMap* tm, const void* base, int rows, int cols, int64_t ldp, int box_rows, bool mn_major, bool half, bool sub) {
-  return encode_cached(tm, base, rows, cols, ldp, box_rows, mn_major, half, sub);
+static int make_view_map(CUtensorMap* tm, const void* base, int rows, int cols, int64_t ldp, int box_rows, bool mn_major, bool half) {
+  return encode_cached(tm, base, rows, cols, ldp, box_rows, mn_major, half);
 }
 
 int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
@@ -1512,11 +1187,7 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   // persistent CTA-pair kernel (gemm_tc2.cu): the default for every wide GEMM whose rows come in whole 128-row tiles; its tensor maps
   // are those of the 128x256 kernel (128-row K-major boxes, 64x64 MN-major boxes), so the final choice can wait for the epilogue block
   const bool pair_shape = H && tc_pair() && use256 && (p.M % 128 == 0) && (p.N % 8 == 0);
-  const bool persist = H && !pair_shape && tc_persist() && !p.accumulate && !(p.split_k > 1) && BN == 128;
-  const bool sub = H && use256 && !pair_shape && !persist && tc_sub();          // 4 x 48 KB ring of 32-wide k sub-blocks
-  int CL = (!H && BN == 128 && p.N > 128 && !use256) ? tc_cluster() : 1;       // A-multicast groups need >= 2 N tiles
-  if (CL == 4 && p.N <= 384) CL = 2;
-  const int a_box = TC_BM / CL;
+  const int a_box = TC_BM;
   const int Mp = pad_to(p.M, 128), Np = pad_to(p.N, 128), Kp = pad_to(p.K, BK);
   int rc;
   // ---- operands: cached planes when the buffer is registered, else a split pass into the shared workspace
@@ -1554,8 +1225,8 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   unsigned* oflag = (H && reg) ? reg->flag : nullptr;
   char* wsp = ws + TC_WS_HEAD;
   if (va.ok) {
-    if ((rc = make_view_map(&ah, va.hi, a_rows, a_cols, va.ldp, p.a_trans ? BK : a_box, p.a_trans != 0, H, sub)) ||
-        (rc = make_view_map(&al, va.lo, a_rows, a_cols, va.ldp, p.a_trans ? BK : a_box, p.a_trans != 0, H, sub))) return rc;
+    if ((rc = make_view_map(&ah, va.hi, a_rows, a_cols, va.ldp, p.a_trans ? BK : a_box, p.a_trans != 0, H)) ||
+        (rc = make_view_map(&al, va.lo, a_rows, a_cols, va.ldp, p.a_trans ? BK : a_box, p.a_trans != 0, H))) return rc;
   } else {
     float* Ahi = (float*)wsp; float* Alo = (float*)(wsp + align_up((int64_t)Mp * Kp * 4, 1024));
     if (!H) { if ((rc = prep_operand(p.A, p.lda, p.a_trans, p.M, p.K, Mp, Kp, Ahi, Alo, st))) return rc; }
@@ -1563,12 +1234,12 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
       if ((rc = materialize_h(p.A, p.lda, a_rows, a_cols, p.a_trans ? Kp : Mp, p.a_trans ? Mp : Kp, Ahi, Alo, t_amax[0], t_scale[0], nullptr, t_pred[0], oflag, st, reg ? TOP_SITE : TOP_EXACT))) return rc;
       va.scale = t_scale[0];
     }
-    if (!p.a_trans) { if ((rc = make_map(&ah, Ahi, Mp, Kp, a_box, false, H, sub)) || (rc = make_map(&al, Alo, Mp, Kp, a_box, false, H, sub))) return rc; }
-    else            { if ((rc = make_map(&ah, Ahi, Kp, Mp, BK, true, H, sub)) || (rc = make_map(&al, Alo, Kp, Mp, BK, true, H, sub))) return rc; }
+    if (!p.a_trans) { if ((rc = make_map(&ah, Ahi, Mp, Kp, a_box, false, H)) || (rc = make_map(&al, Alo, Mp, Kp, a_box, false, H))) return rc; }
+    else            { if ((rc = make_map(&ah, Ahi, Kp, Mp, BK, true, H)) || (rc = make_map(&al, Alo, Kp, Mp, BK, true, H))) return rc; }
   }
   if (vb.ok) {
-    if ((rc = make_view_map(&bh, vb.hi, b_rows, b_cols, vb.ldp, p.b_trans ? BK : BN, p.b_trans != 0, H, sub)) ||
-        (rc = make_view_map(&bl, vb.lo, b_rows, b_cols, vb.ldp, p.b_trans ? BK : BN, p.b_trans != 0, H, sub))) return rc;
+    if ((rc = make_view_map(&bh, vb.hi, b_rows, b_cols, vb.ldp, p.b_trans ? BK : BN, p.b_trans != 0, H)) ||
+        (rc = make_view_map(&bl, vb.lo, b_rows, b_cols, vb.ldp, p.b_trans ? BK : BN, p.b_trans != 0, H))) return rc;
   } else {
     char* wb = wsp + 2 * align_up((int64_t)Mp * Kp * 4, 1024);
     float* Bhi = (float*)wb; float* Blo = (float*)(wb + align_up((int64_t)Np * Kp * 4, 1024));
@@ -1577,8 +1248,8 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
       if ((rc = materialize_h(p.B, p.ldb, b_rows, b_cols, p.b_trans ? Kp : Np, p.b_trans ? Np : Kp, Bhi, Blo, t_amax[1], t_scale[1], nullptr, t_pred[1], oflag, st, reg ? TOP_SITE : TOP_EXACT))) return rc;
       vb.scale = t_scale[1];
     }
-    if (!p.b_trans) { if ((rc = make_map(&bh, Bhi, Np, Kp, BN, false, H, sub)) || (rc = make_map(&bl, Blo, Np, Kp, BN, false, H, sub))) return rc; }
-    else            { if ((rc = make_map(&bh, Bhi, Kp, Np, BK, true, H, sub)) || (rc = make_map(&bl, Blo, Kp, Np, BK, true, H, sub))) return rc; }
+    if (!p.b_trans) { if ((rc = make_map(&bh, Bhi, Np, Kp, BN, false, H)) || (rc = make_map(&bl, Blo, Np, Kp, BN, false, H))) return rc; }
+    else            { if ((rc = make_map(&bh, Bhi, Kp, Np, BK, true, H)) || (rc = make_map(&bl, Blo, Kp, Np, BK, true, H))) return rc; }
   }
   TcEpi e;
   e.C = p.C; e.ldc = p.ldc; e.M = p.M; e.N = p.N; e.K = p.K; e.alpha = p.alpha; e.bias = p.bias; e.act = p.act;
@@ -1635,18 +1306,13 @@ int gemm_tc(const AseGemmParams& p, cudaStream_t st, PlaneRegistry* reg) {
   const bool amn = p.a_trans != 0, bmn = p.b_trans != 0;
   if (H) {
     if (pair_shape && gemm_tc2_epilogue_ok(e)) return launch_tc2(amn, bmn, ah, al, bh, bl, e, splits, st);
-    // non-split GEMMs with N > 64: persistent ping-pong kernel (128x128 tiles; the B maps already have 128-row boxes)
-    if (persist) return launch_tcp_major(amn, bmn, ah, al, bh, bl, e, st);
-    if (use256 && sub) return launch_tc256_major<true, true>(amn, bmn, ah, al, bh, bl, e, splits, st);
-    if (use256) return launch_tc256_major<true, false>(amn, bmn, ah, al, bh, bl, e, splits, st);
-    if (BN == 128) return launch_tc_major<128, 3, 1, true>(amn, bmn, ah, al, bh, bl, e, splits, st);
-    return launch_tc_major<64, 2, 1, true>(amn, bmn, ah, al, bh, bl, e, splits, st);      // 2 stages = 97 KB: two CTAs per SM hide each other's latencies
+    if (use256) return launch_tc256_major<true>(amn, bmn, ah, al, bh, bl, e, splits, st);
+    if (BN == 128) return launch_tc_major<128, 3, true>(amn, bmn, ah, al, bh, bl, e, splits, st);
+    return launch_tc_major<64, 2, true>(amn, bmn, ah, al, bh, bl, e, splits, st);      // 2 stages = 97 KB: two CTAs per SM hide each other's latencies
   }
-  if (use256) return launch_tc256_major<false, false>(amn, bmn, ah, al, bh, bl, e, splits, st);
-  if (BN == 128 && CL == 4) return launch_tc_major<128, 3, 4, false>(amn, bmn, ah, al, bh, bl, e, splits, st);
-  if (BN == 128 && CL == 2) return launch_tc_major<128, 3, 2, false>(amn, bmn, ah, al, bh, bl, e, splits, st);
-  if (BN == 128) return launch_tc_major<128, 3, 1, false>(amn, bmn, ah, al, bh, bl, e, splits, st);
-  return launch_tc_major<64, 4, 1, false>(amn, bmn, ah, al, bh, bl, e, splits, st);
+  if (use256) return launch_tc256_major<false>(amn, bmn, ah, al, bh, bl, e, splits, st);
+  if (BN == 128) return launch_tc_major<128, 3, false>(amn, bmn, ah, al, bh, bl, e, splits, st);
+  return launch_tc_major<64, 4, false>(amn, bmn, ah, al, bh, bl, e, splits, st);
 }
 
 }  // namespace ase

@@ -300,9 +300,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
       // item; completion bytes go to the LEADER's full barrier
       const uint32_t full_leader = mapa_u32(smem_u32(&full[0]), 0);
       int g = 0;
-      for (int j = 0; j < my_items; ++j) {
+      for (int j = 0; j < ((e.debug & 32) ? 0 : my_items); ++j) {
         const Tc2Item it = tc2_item(pair + j * npairs, tiles_n, tiles_m2, e);
-        const int m0 = it.m0 + (int)rank * 128, nb0 = it.n0 + (int)rank * 128;
+        const bool pin = (e.debug & 16) != 0;       // ablation: every load hits the same (L2-resident) boxes
+        const int m0 = (pin ? 0 : it.m0) + (int)rank * 128, nb0 = (pin ? 0 : it.n0) + (int)rank * 128;
         for (int kb = 0; kb < it.nkb; ++kb, ++g) {
           const int s = g % TC2_STAGES;
           const uint32_t ph = (uint32_t)(g / TC2_STAGES) & 1u;
@@ -310,7 +311,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
           if (rank == 0) mbar_expect_tx(&full[s], 2 * TC2_STAGE_BYTES);
           uint8_t* st = smem + s * TC2_STAGE_BYTES;
           const uint32_t bar = full_leader + 8u * (uint32_t)s;
-          const int k0 = (it.kb_begin + kb) * F::BK;
+          const int k0 = pin ? 0 : (it.kb_begin + kb) * F::BK;
           if (!AMN) {          // K-major planes [rows, K]: one box of 128 rows x one k-block
             tma_load_2d_pair(st, &tmAhi, bar, k0, m0);
             tma_load_2d_pair(st + TC2_PLANE_BYTES, &tmAlo, bar, k0, m0);
@@ -347,7 +348,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
           const uint32_t ph = (uint32_t)(g / TC2_STAGES) & 1u;
           const int b = g & 1;
           mbar_wait(&buf_empty[b], ((uint32_t)(g >> 1) & 1u) ^ 1u);     // both CTAs drained this buffer's previous partial (k-block g - 2)
-          mbar_wait(&full[s], ph);
+          if (!(e.debug & 32)) mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * TC2_STAGE_BYTES);
           const uint32_t a_hi = sa, a_lo = sa + TC2_PLANE_BYTES, b_hi = sa + 2 * TC2_PLANE_BYTES, b_lo = sa + 3 * TC2_PLANE_BYTES;
@@ -361,6 +362,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant
             tc_mma2_f16(tmem_d, tc_desc<true, AMN>(a_lo, k), tc_desc<true, BMN>(b_hi, k), idesc, k > 0 ? 1u : 0u);
             tc_mma2_f16(tmem_d, tc_desc<true, AMN>(a_hi, k), tc_desc<true, BMN>(b_lo, k), idesc, 1u);
           }
+          if (!(e.debug & 64))
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             tc_mma2_f16(tmem_d, tc_desc<true, AMN>(a_hi, k), tc_desc<true, BMN>(b_hi, k), idesc, (corr || k > 0) ? 1u : 0u);

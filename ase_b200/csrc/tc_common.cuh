@@ -51,15 +51,6 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, ui
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask) : "memory");
-}
-__device__ __forceinline__ void tc_commit_mc(uint64_t* bar, uint16_t mask) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
-}
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
@@ -138,19 +129,6 @@ __device__ __forceinline__ uint64_t make_smem_desc_mn(uint32_t saddr) {
 // two k groups.
 __device__ __forceinline__ uint64_t make_smem_desc_mn_h(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(8192 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-// FP16 format, 32-wide k sub-blocks (the 4-deep ring of the 128x256 kernel).  K-major rows are 64 bytes: SWIZZLE_64B (layout type 4,
-// ((8,n),2):((4,SBO),1) in 16-byte units: 8-row x 64 B atoms, SBO = 512).  MN-major boxes are [32 k-rows x 64 mn]: the same SWIZZLE_128B
-// layout as above with LBO = 4096 (one box per 64-wide MN block).
-__device__ __forceinline__ uint64_t make_smem_desc_k64(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
-}
-__device__ __forceinline__ uint64_t make_smem_desc_mn_h32(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)(4096 >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
-template <bool MN>
-__device__ __forceinline__ uint64_t tc_desc_sub(uint32_t base, int k) {      // k = 0, 1: the two K=16 MMAs of a 32-wide sub-block
-  return MN ? make_smem_desc_mn_h32(base + k * 2048) : make_smem_desc_k64(base + k * 32);
 }
 template <bool H, bool MN>
 __device__ __forceinline__ uint64_t tc_desc(uint32_t base, int k) {

@@ -147,21 +147,15 @@ def test_tc_relu_activity_bits_roundtrip(tc, M, N, K):
 
 
 @pytest.mark.parametrize('a_trans,b_trans', [(False, False), (False, True), (True, False), (True, True)])
-def test_tc_persistent_many_tiles_per_cta(a_trans, b_trans):
-    """ASE_TC_PERSIST=1 routes backend 2's non-split GEMMs to the persistent ping-pong kernel (kept as an opt-in experiment: correct,
-    but slower than the 128x256 kernel on B200): with more than 148 output tiles every CTA walks several tiles, alternating between
-    its two TMEM accumulator sets / drain warp sets and handing the staging tile back and forth.  Odd and even k-block counts per
-    tile exercise both parities of every barrier across tile boundaries."""
-    import os
+def test_tc_many_tiles_per_cta(a_trans, b_trans):
+    """More output tiles than resident CTAs / CTA pairs: the persistent pair kernel (M % 128 == 0 shapes) walks several work items per
+    pair, alternating its two TMEM buffers across item boundaries; the ragged shapes take the one-tile-per-CTA kernels in several
+    waves.  Odd and even k-block counts per tile exercise both parities of every barrier across tile boundaries."""
     from ase_b200 import ops
-    os.environ['ASE_TC_PERSIST'] = '1'
-    try:
-        _persistent_cases(a_trans, b_trans, ops)
-    finally:
-        os.environ['ASE_TC_PERSIST'] = '0'
+    _many_tile_cases(a_trans, b_trans, ops)
 
 
-def _persistent_cases(a_trans, b_trans, ops):
+def _many_tile_cases(a_trans, b_trans, ops):
     _run(8192, 1024, 192, a_trans, b_trans, 2, bias=True, act=1, tol=1e-5)       # 512 tiles, 3 k-blocks each
     _run(4096, 1024, 64, a_trans, b_trans, 2, tol=1e-5)                           # 256 tiles, 1 k-block each
     _run(5000, 900, 256, a_trans, b_trans, 2, mask_mode=1, tol=1e-5)              # 320 tiles, ragged M and N tails, 4 k-blocks
@@ -175,20 +169,6 @@ def _persistent_cases(a_trans, b_trans, ops):
     ref = A.double() @ B.double().t()
     assert float((C.double() - ref).abs().max() / ref.abs().max()) < 1e-5
     assert float((cs.double() - ref.sum(0)).abs().max() / ref.sum(0).abs().max()) < 1e-5
-
-
-@pytest.mark.parametrize('a_trans,b_trans', [(False, False), (False, True), (True, False), (True, True)])
-def test_tc_wide_tiles_sub_block_ring(a_trans, b_trans):
-    """ASE_TC_SUB=1 makes the 128x256 FP16 kernel stream 32-wide k sub-blocks through a 4 x 48 KB ring (K-major SWIZZLE_64B rows,
-    MN-major 32-row boxes) instead of 64-wide k-blocks through 2 x 96 KB (an opt-in experiment: correct, not faster)."""
-    import os
-    os.environ['ASE_TC_SUB'] = '1'
-    try:
-        _run(300, 1400, 317, a_trans, b_trans, 2, lda_pad=3, tol=1e-5)
-        _run(512, 1024, 2048, a_trans, b_trans, 2, mask_mode=1, tol=1e-5)
-        _run(1024, 512, 4096, True, True, 2, accumulate=True, split_k=5, tol=3e-5)
-    finally:
-        del os.environ['ASE_TC_SUB']
 
 
 def test_tc_fp16_planes_dynamic_range():
