@@ -185,6 +185,7 @@ class CommonAgent:
         st['optimizer'] = self._optimizer_state_dict()
         st['frame'] = self.frame
         st['last_mean_rewards'] = -100500
+        st['env_state'] = self.vec_env.get_env_state() if hasattr(self.vec_env, 'get_env_state') else None      # a2c_common.get_full_state_weights
         return st
 
     def set_full_state_weights(self, w):

@@ -212,26 +212,28 @@ colsum_kernel(const float* __restrict__ dz, int64_t ld, int rows, int cols, int 
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   const int r0 = blockIdx.y * rows_per_block, r1 = min(rows, r0 + rows_per_block);
-  float s = 0.0f;
-  for (int r = r0; r < r1; ++r) s += dz[(int64_t)r * ld + c];
-  atomicAdd(&db[c], s);
+  // fp64 partial sums: a 256-term fp32 chain loses ~1e-5 of sum|dz| per partial, which on bias gradients with heavy cancellation
+  // (critic trunk at B = 16384) showed up as 1e-4 of max|db| against the reference's tree reduction; the adds hide under the loads
+  double s = 0.0;
+  for (int r = r0; r < r1; ++r) s += (double)dz[(int64_t)r * ld + c];
+  atomicAdd(&db[c], (float)s);
 }
 
 // Narrow matrices (head gradients: 31 / 1 / 64 columns, contiguous rows): the column of a thread is fixed by making the grid stride a
 // multiple of cols, every thread streams the flat array (fully coalesced), per-column partial sums meet in shared memory.
 __global__ void __launch_bounds__(256)
 colsum_narrow_kernel(const float* __restrict__ dz, int64_t total, int cols, int64_t stride, float* __restrict__ db) {
-  __shared__ float sm[64];
-  if (threadIdx.x < 64) sm[threadIdx.x] = 0.0f;
+  __shared__ double sm[64];
+  if (threadIdx.x < 64) sm[threadIdx.x] = 0.0;
   __syncthreads();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t < stride) {
-    float s = 0.0f;
-    for (int64_t i = t; i < total; i += stride) s += dz[i];
+    double s = 0.0;
+    for (int64_t i = t; i < total; i += stride) s += (double)dz[i];
     atomicAdd(&sm[(int)(t % cols)], s);
   }
   __syncthreads();
-  if (threadIdx.x < cols) atomicAdd(&db[threadIdx.x], sm[threadIdx.x]);
+  if (threadIdx.x < cols) atomicAdd(&db[threadIdx.x], (float)sm[threadIdx.x]);
 }
 
 // grads += coef * w ; acc[idx] += sum w^2   (logit-weight regulariser and disc weight decay, amp_agent.py:448-466)

@@ -129,6 +129,58 @@ rms_normalize_kernel(const float* __restrict__ x, int64_t ldx, int rows, int col
   }
 }
 
+// 4 columns x NORM_ROWS_PER_BLOCK rows per thread: 16-byte loads / fp32 stores and 8-byte half-plane stores (cols, every leading dimension a
+// multiple of 4 and 16-byte aligned bases: the 1400-wide AMP observations; the 253-wide observations take the scalar kernel above).
+// Same arithmetic per element as rms_normalize_kernel.
+__global__ void __launch_bounds__(128)
+rms_normalize_vec4_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols,
+                          const float* __restrict__ meanf, const float* __restrict__ stdf, int unnorm, RmsDst dst) {
+  const int c = (blockIdx.x * 128 + threadIdx.x) * 4;
+  if (c >= cols) return;
+  const float4 mu = *reinterpret_cast<const float4*>(meanf + c), sd = *reinterpret_cast<const float4*>(stdf + c);
+  const bool planes = dst.hi[0] || dst.hi[1] || dst.hi[2];
+  const int r0 = blockIdx.y * NORM_ROWS_PER_BLOCK;
+  float4 xv[NORM_ROWS_PER_BLOCK];
+#pragma unroll
+  for (int i = 0; i < NORM_ROWS_PER_BLOCK; ++i)
+    xv[i] = (r0 + i < rows) ? __ldcs(reinterpret_cast<const float4*>(x + (int64_t)(r0 + i) * ldx + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < NORM_ROWS_PER_BLOCK; ++i) {
+    const int r = r0 + i;
+    if (r >= rows) break;
+    const float v[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+    const float m4[4] = {mu.x, mu.y, mu.z, mu.w}, s4[4] = {sd.x, sd.y, sd.z, sd.w};
+    float y[4], h[4], l[4];
+    __half hh[4], hl[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (unnorm) y[j] = s4[j] * fminf(fmaxf(v[j], -5.0f), 5.0f) + m4[j];
+      else y[j] = fminf(fmaxf((v[j] - m4[j]) / s4[j], -5.0f), 5.0f);
+      h[j] = l[j] = 0.0f; hh[j] = hl[j] = __float2half_rn(0.0f);
+      if (planes) {
+        if (!dst.half) split_tf32_rms(y[j], h[j], l[j]);
+        else { const float ys = y[j] * dst.pscale; hh[j] = __float2half_rn(ys); hl[j] = __float2half_rn(ys - __half2float(hh[j])); }
+      }
+    }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      if (dst.y[d]) *reinterpret_cast<float4*>(dst.y[d] + (int64_t)r * dst.ld[d] + c) = make_float4(y[0], y[1], y[2], y[3]);
+      if (dst.hi[d]) {
+        const int64_t o = (int64_t)r * dst.ldp[d] + c;
+        if (!dst.half) {
+          *reinterpret_cast<float4*>((float*)dst.hi[d] + o) = make_float4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<float4*>((float*)dst.lo[d] + o) = make_float4(l[0], l[1], l[2], l[3]);
+        } else {
+          const __half2 a = __halves2half2(hh[0], hh[1]), b = __halves2half2(hh[2], hh[3]);
+          const __half2 e = __halves2half2(hl[0], hl[1]), f = __halves2half2(hl[2], hl[3]);
+          *reinterpret_cast<uint2*>((__half*)dst.hi[d] + o) = make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+          *reinterpret_cast<uint2*>((__half*)dst.lo[d] + o) = make_uint2(*reinterpret_cast<const uint32_t*>(&e), *reinterpret_cast<const uint32_t*>(&f));
+        }
+      }
+    }
+  }
+}
+
 // just copy columns (used to place latents next to the normalised observations)
 __global__ void __launch_bounds__(256)
 copy_cols_kernel(const float* __restrict__ x, int64_t ldx, int rows, int cols, float* __restrict__ y, int64_t ldy,
@@ -185,6 +237,19 @@ int rms_update_batches(const RmsBatchList& bl, int nbatch, int cols, double* mea
 int rms_normalize(const float* x, int64_t ldx, int rows, int cols, const float* meanf, const float* stdf, int unnorm,
                   const RmsDst& dst, cudaStream_t st) {
   if (rows <= 0 || cols <= 0) return ASE_OK;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  bool vec = (cols % 4 == 0) && (ldx % 4 == 0) && al16(x) && al16(meanf) && al16(stdf);
+  for (int d = 0; d < 3 && vec; ++d) {
+    if (dst.y[d]) vec = vec && al16(dst.y[d]) && (dst.ld[d] % 4 == 0);
+    if (dst.hi[d]) vec = vec && (dst.ldp[d] % 4 == 0) && (dst.half ? ((reinterpret_cast<uintptr_t>(dst.hi[d]) | reinterpret_cast<uintptr_t>(dst.lo[d])) & 7) == 0
+                                                                  : (al16(dst.hi[d]) && al16(dst.lo[d])));
+  }
+  if (vec) {
+    dim3 grid(ceil_div(cols / 4, 128), ceil_div(rows, NORM_ROWS_PER_BLOCK));
+    rms_normalize_vec4_kernel<<<grid, 128, 0, st>>>(x, ldx, rows, cols, meanf, stdf, unnorm, dst);
+    ASE_LAUNCH_OK();
+    return ASE_OK;
+  }
   dim3 grid(ceil_div(cols, 128), ceil_div(rows, NORM_ROWS_PER_BLOCK));
   rms_normalize_kernel<<<grid, 128, 0, st>>>(x, ldx, rows, cols, meanf, stdf, unnorm, dst);
   ASE_LAUNCH_OK();

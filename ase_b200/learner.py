@@ -173,9 +173,11 @@ class Learner:
         sd = OrderedDict()
         sd['a2c_network.sigma'] = self.sigma
         for k, v in self._views.items():
+            if self.kind == 'ase' and k == '_enc.weight':      # enc.separate False: the encoder trunk IS the discriminator trunk -- the reference's
+                for kk, vv in self._views.items():             # state dict lists the same tensors again as _enc_mlp.* between _disc_logits and _enc
+                    if kk.startswith('_disc_mlp.'):
+                        sd['a2c_network.' + kk.replace('_disc_mlp', '_enc_mlp')] = vv
             sd['a2c_network.' + k] = v
-            if self.kind == 'ase' and k.startswith('_disc_mlp.'):
-                sd['a2c_network.' + k.replace('_disc_mlp', '_enc_mlp')] = v      # enc.separate False: same tensors
         return sd
 
     def load_state_dict(self, sd):

@@ -350,6 +350,31 @@ def gen_hrl_calc_gradients():
     print('calc_grad_hrl_small', steps[-1]['scalars'])
 
 
+def gen_checkpoint_layout():
+    """Layout (keys, shapes, dtypes, optimizer state indices, hyper-parameter keys -- NO weights) of the checkpoints the reference ships
+    (ase/data/models/*.pth, written by common_agent.py:157-170 save / a2c_common get_full_state_weights): what restore() and the HRL
+    llc_checkpoint path have to accept.  tests build a random checkpoint with exactly this layout."""
+    import json
+    ref = os.environ.get('ASE_REFERENCE', '/root/reference')
+    out = {}
+    for name in ('ase_llc_reallusion_sword_shield', 'ase_hlc_heading_reallusion_sword_shield'):
+        w = torch.load(os.path.join(ref, 'ase/data/models', name + '.pth'), map_location='cpu', weights_only=False)
+        lay = {}
+        for k, v in w.items():
+            if k == 'optimizer':
+                lay[k] = {'state': {str(i): {kk: (list(vv.shape), str(vv.dtype)) if torch.is_tensor(vv) else type(vv).__name__ for kk, vv in st.items()}
+                                    for i, st in v['state'].items()},
+                          'param_groups': [{kk: (type(vv).__name__ if kk != 'params' else list(vv)) for kk, vv in pg.items()} for pg in v['param_groups']]}
+            elif isinstance(v, dict):
+                lay[k] = {kk: (list(vv.shape), str(vv.dtype)) for kk, vv in v.items()}
+            else:
+                lay[k] = type(v).__name__
+        out[name] = lay
+    with open(os.path.join(OUT, 'checkpoint_layout.json'), 'w') as f:
+        json.dump(out, f, indent=0, sort_keys=False)
+    print('checkpoint_layout.json ok', {k: len(v['model']) for k, v in out.items()})
+
+
 def gen_rollout_math():
     agent, _ = rh.make_ref_agent('ase', num_envs=8, overrides={'minibatch_size': 256, 'amp_minibatch_size': 64})
     g = torch.Generator().manual_seed(21)

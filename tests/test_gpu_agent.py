@@ -138,3 +138,195 @@ def test_hrl_agent_epoch_config5_shapes():
     adv = O.discount_values(eb['dones'].float(), eb['values'], rew, eb['next_values'], 0.99, 0.95)
     assert torch.allclose(bd['returns'].cpu(), O.swap_and_flatten01(adv + eb['values']), rtol=1e-4, atol=1e-4)
     assert float(eb['disc_rewards'].min()) >= 0.0 and float(eb['rewards'].max()) <= 1.0 + 1e-6     # heading reward in [0,1]
+
+
+# ------------------------------------------------------------------------------------------------------------------------------------
+# drop-in surface: the rl_games factories of run.py and the checkpoints the reference ships
+# ------------------------------------------------------------------------------------------------------------------------------------
+def _checkpoint_from_layout(name, seed):
+    """A random checkpoint with EXACTLY the layout of a shipped reference checkpoint (tests/golden/checkpoint_layout.json, written by
+    oracle/gen_golden.py gen_checkpoint_layout from ase/data/models/*.pth): same keys, shapes, dtypes, optimizer state indices."""
+    import json, os
+    lay = json.load(open(os.path.join(os.path.dirname(__file__), 'golden', 'checkpoint_layout.json')))[name]
+    g = torch.Generator().manual_seed(seed)
+    dt = {'torch.float32': torch.float32, 'torch.float64': torch.float64}
+    w = {}
+    for k, v in lay.items():
+        if k == 'optimizer':
+            st = {}
+            for i, e in v['state'].items():
+                st[int(i)] = {'step': 6194400, 'exp_avg': 1e-3 * torch.randn(e['exp_avg'][0], generator=g),
+                              'exp_avg_sq': 1e-6 * torch.rand(e['exp_avg_sq'][0], generator=g) + 1e-9}
+            w[k] = {'state': st, 'param_groups': [{'lr': 2e-5, 'betas': (0.9, 0.999), 'eps': 1e-8, 'weight_decay': 0.0, 'amsgrad': False,
+                                                   'params': v['param_groups'][0]['params']}]}
+        elif isinstance(v, dict):
+            w[k] = {}
+            for kk, (shape, dtype) in v.items():
+                t = torch.randn(shape, generator=g, dtype=dt[dtype]) * (0.05 if dtype == 'torch.float32' else 1.0)
+                if kk in ('running_var', 'count'):
+                    t = t.abs() + 0.5
+                if kk.endswith('sigma'):
+                    t = torch.full(shape, -2.9)
+                w[k][kk] = t
+        else:
+            w[k] = {'epoch': 129050, 'frame': 8355840000, 'last_mean_rewards': -100500, 'env_state': None}[k]
+    # the ASE builder aliases the encoder trunk to the discriminator trunk (ase_network_builder.py:289-303): one storage, two names
+    for kk in list(w['model']):
+        if '._enc_mlp.' in kk:
+            w['model'][kk] = w['model'][kk.replace('._enc_mlp.', '._disc_mlp.')]
+    return w, lay
+
+
+def _same_layout(w, lay):
+    assert set(w.keys()) == set(lay.keys()), (sorted(w.keys()), sorted(lay.keys()))
+    for k, v in lay.items():
+        if k == 'optimizer':
+            assert sorted(w[k]['state'].keys()) == sorted(int(i) for i in v['state'])
+            for i, e in v['state'].items():
+                st = w[k]['state'][int(i)]
+                assert set(st.keys()) == set(e.keys()) and isinstance(st['step'], int)
+                assert list(st['exp_avg'].shape) == e['exp_avg'][0] and str(st['exp_avg_sq'].dtype) == e['exp_avg_sq'][1]
+            pg, pl = w[k]['param_groups'][0], v['param_groups'][0]
+            assert set(pg.keys()) == set(pl.keys()) and list(pg['params']) == pl['params']
+        elif isinstance(v, dict):
+            assert list(w[k].keys()) == list(v.keys()), k                      # same names in the same order
+            for kk, (shape, dtype) in v.items():
+                assert list(w[k][kk].shape) == shape and str(w[k][kk].dtype) == dtype, (k, kk)
+
+
+def _full_size_env_cfg(kind, n=64, h=8, **over):
+    from ase_b200 import configs
+    from ase_b200.synthetic_env import SyntheticHumanoidEnv
+    env = SyntheticHumanoidEnv(n, device='cuda', seed=3, done_prob=0.05, demo_pool=512, heading_task=(kind == 'hrl'))
+    kw = dict(device='cuda:0', vec_env=env, num_actors=n, horizon_length=h, minibatch_size=128, mini_epochs=1, print_stats=False)
+    if kind != 'hrl':
+        kw.update(amp_minibatch_size=32, amp_obs_demo_buffer_size=2048, amp_replay_buffer_size=2048, amp_batch_size=64)
+    kw.update(over)
+    return env, configs.make(kind, **kw)
+
+
+def test_restore_accepts_the_shipped_checkpoint_layout_and_save_writes_it_back(tmp_path):
+    """restore(fn) (common_agent.py:157-170, what run.py does for --checkpoint) on a file with the exact layout of the shipped
+    ase_llc_reallusion_sword_shield.pth: 39 model tensors incl. the `_enc_mlp` aliases and the frozen sigma, f64 RMS buffers, Adam state
+    1..32 with an int `step`; then save() must write the same layout back with the same numbers."""
+    from ase_b200.agent import ASEAgent
+    w, lay = _checkpoint_from_layout('ase_llc_reallusion_sword_shield', seed=7)
+    fn = str(tmp_path / 'shipped_layout.pth')
+    torch.save(w, fn)
+    env, cfg = _full_size_env_cfg('ase')
+    ag = ASEAgent('t', cfg)
+    ag.restore(fn)
+    assert ag.epoch_num == 129050 and ag.frame == 8355840000 and ag.model.step == 6194400
+    sd = ag.model.state_dict()
+    for k, v in w['model'].items():
+        assert torch.equal(sd[k].cpu(), v), k
+    assert torch.equal(ag.model.amp_input_mean_std.running_var.cpu(), w['amp_input_mean_std']['running_var'])
+    assert float(ag.model.value_mean_std.count) == float(w['reward_mean_std']['count'])
+    out = ag.save(str(tmp_path / 'resaved'))
+    w2 = torch.load(out, map_location='cpu', weights_only=False)
+    _same_layout(w2, lay)
+    for k in w['model']:
+        assert torch.equal(w2['model'][k], w['model'][k]), k
+    for i, st in w['optimizer']['state'].items():
+        assert torch.equal(w2['optimizer']['state'][i]['exp_avg'], st['exp_avg']) and w2['optimizer']['state'][i]['step'] == st['step']
+        assert torch.equal(w2['optimizer']['state'][i]['exp_avg_sq'], st['exp_avg_sq'])
+    for r in ('running_mean_std', 'reward_mean_std', 'amp_input_mean_std'):
+        for kk in w[r]:
+            assert torch.equal(w2[r][kk], w[r][kk]), (r, kk)
+    # and training continues from it
+    ag.init_tensors(); ag.obs = ag.env_reset(); ag._init_train()
+    ag.update_epoch(); info = ag.train_epoch()
+    assert all(torch.isfinite(v).all() for v in info.values()) and ag.model.step == 6194400 + 64 * 8 // 128
+
+
+def test_hrl_restores_llc_and_hlc_from_shipped_layouts(tmp_path):
+    """hrl_agent.py:28-41,202-213: the LLC comes from `llc_checkpoint` (an ASE checkpoint: model + running_mean_std + amp_input_mean_std are
+    used, frozen, eval mode); the HLC itself restores from an HLC checkpoint (13 model tensors, no AMP statistics)."""
+    from ase_b200.agent import HRLAgent
+    llc, _ = _checkpoint_from_layout('ase_llc_reallusion_sword_shield', seed=8)
+    hlc, hlay = _checkpoint_from_layout('ase_hlc_heading_reallusion_sword_shield', seed=9)
+    fl, fh = str(tmp_path / 'llc.pth'), str(tmp_path / 'hlc.pth')
+    torch.save(llc, fl); torch.save(hlc, fh)
+    env, cfg = _full_size_env_cfg('hrl', llc_checkpoint=fl)
+    cfg['llc_net_params'] = {'mlp': {'units': [1024, 1024, 512]}, 'disc': {'units': [1024, 1024, 512]}}
+    ag = HRLAgent('t', cfg)
+    sd = ag._llc.state_dict()
+    for k, v in llc['model'].items():
+        assert torch.equal(sd[k].cpu(), v), k
+    assert torch.equal(ag._llc.running_mean_std.running_mean.cpu(), llc['running_mean_std']['running_mean'])
+    assert torch.equal(ag._llc.amp_input_mean_std.running_var.cpu(), llc['amp_input_mean_std']['running_var'])
+    ag.restore(fh)
+    sd = ag.model.state_dict()
+    for k, v in hlc['model'].items():
+        assert torch.equal(sd[k].cpu(), v), k
+    w2 = torch.load(ag.save(str(tmp_path / 'hlc_resaved')), map_location='cpu', weights_only=False)
+    _same_layout(w2, hlay)
+    ag.init_tensors(); ag.obs = ag.env_reset()
+    ag.update_epoch(); info = ag.train_epoch()
+    assert all(torch.isfinite(v).all() for v in info.values())
+
+
+def test_agent_is_created_and_trained_through_the_rl_games_factories(tmp_path):
+    """The call sequence of ase/run.py:153-170 + rl_games Runner.run_train with the reference's registrations swapped for this package's
+    agent: the algo factory builds the agent from **kwargs (base_name, config); config['network'] is the model
+    object the model builder returns (its network_builder holds the YAML `network` section); there is no 'vec_env' key -- the agent creates
+    the env through rl_games.common.vecenv from config['env_name'] like A2CBase does; then restore(checkpoint) and train()."""
+    import os, sys
+    shims = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', 'shims')
+    if shims not in sys.path:
+        sys.path.insert(0, shims)
+    from rl_games.common import object_factory, vecenv
+    from rl_games.algos_torch import network_builder
+    from ase_b200 import configs
+    from ase_b200.agent import ASEAgent
+    from ase_b200.synthetic_env import SyntheticHumanoidEnv
+
+    # --- run.py:147-150: vec-env registration under the config's env_name
+    made = []
+    def create_env(config_name, num_actors, **kw):
+        made.append((config_name, num_actors, kw))
+        return SyntheticHumanoidEnv(num_actors, device='cuda', seed=kw.get('seed', 0), done_prob=0.05, demo_pool=512, demo_source='motion_lib')
+    vecenv.register('rlgpu', create_env)
+
+    # --- run.py:153-170 build_alg_runner: factories by name
+    algo_factory, model_factory, network_factory = object_factory.ObjectFactory(), object_factory.ObjectFactory(), object_factory.ObjectFactory()
+    algo_factory.register_builder('ase', lambda **kwargs: ASEAgent(**kwargs))
+
+    class ASEBuilderStub(network_builder.NetworkBuilder):       # stands in for learning/ase_network_builder.ASEBuilder: load() keeps the YAML section
+        def load(self, params):
+            self.params = params
+
+    class ModelStub:                                             # stands in for ase_models.ModelASEContinuous(network)
+        def __init__(self, network):
+            self.network_builder = network
+    network_factory.register_builder('ase', lambda **kwargs: ASEBuilderStub())
+    model_factory.register_builder('ase', lambda network, **kwargs: ModelStub(network))
+
+    # --- Runner.load: params = YAML `params`; ModelBuilder.load(params) -> config['network']
+    base = configs.make('ase')
+    yaml_params = {'algo': {'name': 'ase'}, 'model': {'name': 'ase'}, 'network': dict(base['net_params'], name='ase'),
+                   'config': {k: v for k, v in base.items() if k != 'net_params'}}
+    yaml_params['network']['mlp'] = dict(yaml_params['network']['mlp'], units=[128, 96, 64])
+    yaml_params['network']['disc'] = dict(yaml_params['network']['disc'], units=[128, 96, 64])
+    network = network_factory.create(yaml_params['network']['name'])
+    network.load(yaml_params['network'])
+    config = dict(yaml_params['config'])
+    config['network'] = model_factory.create(yaml_params['model']['name'], network=network)
+    config.update(env_name='rlgpu', env_config={'seed': 5}, num_actors=64, horizon_length=8, minibatch_size=128, amp_minibatch_size=32, mini_epochs=2,
+                  amp_obs_demo_buffer_size=2048, amp_replay_buffer_size=2048, amp_batch_size=64, print_stats=False, device='cuda:0',
+                  max_epochs=3, save_frequency=2, train_dir=str(tmp_path), full_experiment_name='dropin', name='Humanoid')
+    assert 'vec_env' not in config and 'net_params' not in config
+
+    # --- Runner.run_train
+    agent = algo_factory.create(yaml_params['algo']['name'], base_name='run', config=config)
+    assert made == [('rlgpu', 64, {'seed': 5})] and isinstance(agent, ASEAgent)
+    assert agent.model.named_parameters()['actor_mlp._dense_layers.0.weight'].shape == (128, 253 + 64)      # the builder object's YAML section was used
+    agent.train()
+    nn_dir = os.path.join(str(tmp_path), 'dropin', 'nn')
+    saved = sorted(os.listdir(nn_dir))
+    assert 'Humanoid.pth' in saved, saved
+    # a second agent created the same way resumes from the file (Runner: agent.restore(args['checkpoint']))
+    agent2 = algo_factory.create('ase', base_name='run', config=dict(config, max_epochs=5))
+    agent2.restore(os.path.join(nn_dir, 'Humanoid.pth'))
+    assert agent2.epoch_num == agent.epoch_num and agent2.model.step == agent.model.step
+    assert torch.equal(agent2.model.params, agent.model.params)

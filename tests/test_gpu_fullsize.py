@@ -67,7 +67,7 @@ def _three_way(mine, g32, g64, tag):
         r = _stats(g32[k], g64[k]); m = _stats(mine[k], g64[k]); x = _stats(mine[k], g32[k])
         worst_ref, worst_me = max(worst_ref, r[3]), max(worst_me, m[3])
         rows.append((k, r, m, x))
-        if not m[0] <= 1.5 * r[0] + 5e-5:
+        if not m[0] <= max(1e-4, 2.0 * r[0] + 5e-5):        # within the stated 1e-4 of the fp64 truth, or as close to it as the reference's fp32 is (x2)
             bad.append((k, 'median error vs fp64', m[0], 'reference fp32', r[0]))
         if not m[1] <= 1.5 * r[1] + 1e-4:
             bad.append((k, 'q95 error vs fp64', m[1], 'reference fp32', r[1]))

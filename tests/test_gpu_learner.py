@@ -61,13 +61,9 @@ def _check_grads(ln, rec, when, exact=True):
             assert float(d.max()) <= 1e-4, (when, k, float(d.max()))
             assert abs(float(g.double().norm()) - rec['grad_norm'][k]) <= 1e-4 * max(rec['grad_norm'][k], 1e-9), (when, k)
         else:
-            # step 0 starts from identical parameters; later steps continue from the device's own Adam updates (lr * sign(g) on the first steps:
-            # where |g| is at the parity floor the sign is anybody's guess), and a 4e-5 parameter difference is amplified ~300x by the
-            # sigma = exp(-2.9) Gaussian head into the actor gradients: bulk at 1e-4, tails at 1e-3
-            first = 'step 0' in when
-            frac = float((d > (1e-4 if first else 1e-3)).float().mean())
-            assert float(d.median()) <= (2e-5 if first else 1e-4) and frac <= (0.05 if first else 0.25) and float(d.max()) <= (0.25 if first else 0.05), \
-                (when, k, float(d.median()), frac, float(d.max()))
+            # every step starts from the reference's parameters (teacher forcing in _run_golden)
+            frac = float((d > 1e-4).float().mean())
+            assert float(d.median()) <= 2e-5 and frac <= 0.05 and float(d.max()) <= 0.25, (when, k, float(d.median()), frac, float(d.max()))
             assert abs(float(g.double().norm()) - rec['grad_norm'][k]) <= 5e-3 * max(rec['grad_norm'][k], 1e-9), (when, k)
         if 'grads' in rec:
             full = rec['grads'][k].flatten()
@@ -94,22 +90,44 @@ def _check_params(ln, rec, when):
         assert torch.allclose(p[idx], rec['param_sample'][k], rtol=1e-5, atol=2e-7), (when, k)
 
 
+def _check_vs_oracle_twin(ln, out, res, grads, when):
+    """Steps >= 1 of the tensor-core backends: against the oracle run live from the same (teacher-forced) parameters.  The oracle is pinned to
+    these very fixtures on the CPU (tests/test_oracle_cpu.py); the fixtures hold only SAMPLES of the reference's post-Adam parameters, so the
+    reference's own step-1 numbers cannot be reproduced from them to better than the 2 * lr the sampled-out parameters may differ by."""
+    tr = ln.train_result(out)
+    for k in tr:
+        if k in res:
+            v = float(res[k])
+            assert abs(tr[k] - v) <= 1e-4 * max(1.0, abs(v)), (when, k, tr[k], v)
+    if 'disc_agent_logit' in res:
+        assert torch.allclose(out['disc_agent_logit'].cpu(), res['disc_agent_logit'].flatten(), rtol=1e-4, atol=1e-4), when
+        assert torch.allclose(out['disc_demo_logit'].cpu(), res['disc_demo_logit'].flatten(), rtol=1e-4, atol=1e-4), when
+    for k, gv in ln.named_grads().items():
+        g, ref = gv.detach().cpu().flatten(), grads[k].flatten()
+        scale = max(float(ref.norm()) / max(g.numel(), 1) ** 0.5, float(ref.abs().max()), 1e-12)
+        d = (g - ref).abs() / scale
+        frac = float((d > 1e-4).float().mean())
+        assert float(d.median()) <= 2e-5 and frac <= 0.05 and float(d.max()) <= 0.25, (when, k, float(d.median()), frac, float(d.max()))
+
+
 def _run_golden(name, backend, exact=True):
     meta, steps, shapes, P = G.calc_grad_case(name)
     kind = meta['kind']
     ln = _make_learner(kind, meta, P, backend)
-    st = O.LearnerState(P, 253, 1400, kind)      # only used to regenerate the seeded inputs exactly as gen_golden did
+    st = O.LearnerState(P, 253, 1400, kind)      # regenerates the seeded inputs exactly as gen_golden did; the oracle twin of steps >= 1
     cfg = meta['cfg']
     for s, rec in enumerate(steps):
         d, new_z = synth.minibatch(st, cfg, meta['B'], meta['Ba'], seed=meta['seed'] * 100 + s, kind=kind)
         out = ln.calc_gradients(_cuda(d), None if new_z is None else new_z.cuda())
         torch.cuda.synchronize()
-        _check_step(ln, out, rec)
-        _check_grads(ln, rec, f'{name} step {s}', exact)
+        vs_fixture = exact or s == 0
+        if vs_fixture:
+            _check_step(ln, out, rec)
+            _check_grads(ln, rec, f'{name} step {s}', exact)
         ln.adam_step()
         if exact:
             _check_params(ln, rec, f'{name} step {s}')
-        else:
+        elif s == 0:
             _check_params_conditioned(ln, rec, meta['cfg']['lr'], s + 1, f'{name} step {s}')
         r = rec['rms']
         assert torch.allclose(ln.running_mean_std.running_mean.cpu(), r['obs_mean'], rtol=1e-6, atol=1e-7)
@@ -117,7 +135,15 @@ def _run_golden(name, backend, exact=True):
         assert torch.allclose(ln.amp_input_mean_std.running_mean.cpu(), r['amp_mean'], rtol=1e-6, atol=1e-7)
         assert torch.allclose(ln.amp_input_mean_std.running_var.cpu(), r['amp_var'], rtol=1e-5, atol=1e-9)
         assert float(ln.amp_input_mean_std.count) == float(r['amp_count'])
-        O.calc_gradients(st, d, cfg, new_z)        # advance the input generator's state in lock-step
+        res, grads = O.calc_gradients(st, d, cfg, new_z)        # advances the input generator's state (RMS, Adam) in lock-step
+        if not vs_fixture:
+            _check_vs_oracle_twin(ln, out, res, grads, f'{name} step {s}')
+        if not exact:
+            # teacher forcing: the next step starts from the oracle's parameters.  After lr * m_hat / sqrt(v_hat) with m_hat ~ 0 in places the
+            # device's own parameters differ by up to 2 * lr there, and the sigma = exp(-2.9) Gaussian head turns that into 1e-3 gradient
+            # differences one step later: that would test the chaotic map, not the kernels.  The FP16 plane scales stay the predicted ones.
+            for k, v in ln.named_parameters().items():
+                v.copy_(st.p[k].to(v.device).reshape(v.shape))
 
 
 @pytest.mark.parametrize('name', ['calc_grad_ase_small.pt', 'calc_grad_ase_cfg1.pt', 'calc_grad_amp_cfg.pt'])
@@ -259,6 +285,7 @@ def test_hrl_high_level_learner_vs_reference_golden(backend):
     meta = fx['meta']
     P = synth.params(O.amp_param_shapes(obs=258, act=64, amp=0, units=meta['units']), seed=meta['seed'])
     st = O.LearnerState(P, 258, 0, 'ppo')
+    st64 = O.LearnerState({k: v.double() for k, v in P.items()}, 258, 0, 'ppo')
     ln = Learner('ppo', 258, 64, meta['B'], units=tuple(meta['units']), hparams={'learning_rate': meta['cfg']['lr']}, gemm_backend=backend,
                  mu_activation='tanh')
     ln.load_named(P)
@@ -269,12 +296,21 @@ def test_hrl_high_level_learner_vs_reference_golden(backend):
         for k, v in rec['scalars'].items():
             if k in tr:
                 assert abs(tr[k] - v) <= 1e-4 * max(1.0, abs(v)), (k, tr[k], v)
-        # the sigma = exp(-2.9) Gaussian head amplifies fp32 rounding of mu ~100x into the ratio / surrogate gradient, so even two
-        # exact-fp32 implementations differ by 4e-5 of max|g| on the actor tensors; measured worst case here: SIMT 8e-5, tcgen05 1.1e-4
-        gtol = 1e-4 if backend == 0 else 1.5e-4
+        # 1e-4 of max|g| against the reference's fp32 gradients, every backend, every step (each step starts from the reference's own
+        # parameters, see the end of the loop).  Measured (tools/hrl_parity_probe.py, profiles/parity_r02.txt): <= 2e-5 on the actor
+        # tensors -- where the reference itself is 1.5e-5 from the same formulas in fp64 (the sigma = exp(-2.9) Gaussian head amplifies fp32
+        # rounding of mu ~100x) and the tensor-core backends are 2-7e-6 from fp64 -- and <= 5e-7 on the critic tensors.
+        for k in st.p:
+            st64.p[k] = st.p[k].double()
+        d64 = {k: (v.double() if torch.is_tensor(v) and v.is_floating_point() else v) for k, v in d.items()}
+        _, g64 = O.calc_gradients(st64, d64, meta['cfg'], None, apply_adam=False)
         for k, g in rec['grads'].items():
             mine = ln.named_grads()[k].cpu()
-            assert float((mine - g).abs().max()) <= gtol * max(float(g.abs().max()), 1e-9), k
+            scale = max(float(g.abs().max()), 1e-9)
+            e32 = float((mine - g).abs().max()) / scale
+            e_ref64 = float((g.double() - g64[k]).abs().max()) / scale
+            e_me64 = float((mine.double() - g64[k]).abs().max()) / scale
+            assert e32 <= 1e-4 and e_me64 <= 1e-4, (k, e32, e_me64, e_ref64)
         # Adam is checked in isolation (same gradients in, torch.optim.Adam formula on the CPU): comparing post-update parameters
         # against the reference run instead would test the chaotic map g -> lr * m_hat / sqrt(v_hat) at m_hat ~ 0, not the kernel
         p0, g0 = ln.params.cpu().clone(), ln.grads.cpu().clone()
@@ -293,3 +329,8 @@ def test_hrl_high_level_learner_vs_reference_golden(backend):
             ok = g.abs() > 0.05 * g.abs().max()
             assert torch.allclose(ln.named_parameters()[k].cpu()[ok], p[ok], rtol=1e-5, atol=1e-6), k
         O.calc_gradients(st, d, meta['cfg'], None)
+        # teacher forcing: the next step starts from the reference's parameters (after one Adam step lr * m_hat / sqrt(v_hat) with m_hat ~ 0 in
+        # places, the device's own parameters differ by up to 2 * lr there, which the Gaussian head turns into 1.1e-4 gradient differences)
+        for k, v in ln.named_parameters().items():
+            v.copy_(rec['params_after'][k].to(v.device).reshape(v.shape))
+        ln.params_changed()
