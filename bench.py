@@ -236,7 +236,7 @@ def run_ours(args):
         "gpu_launches_note": "kernels launched by libase_b200.so through host calls during the timed epochs; launches replayed from the captured CUDA "
                              "graphs (rollout: ~60 per sim step; minibatch update: ~100) are NOT re-counted -- the instrumented epoch launches " + str(int(nl.value)) + " tcgen05 GEMMs eagerly",
         "clocks": clk.summary(),
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc256_kernel / gemm_tc_kernel (tcgen05.mma kind::f16, 3 MMAs per product on scaled FP16 hi/lo planes)" if GEMM_BACKEND == 2
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel (persistent CTA pair, tcgen05.mma.cta_group::2 kind::f16, 3 MMAs per product on scaled FP16 hi/lo planes; ~80 % of the GEMM time) + gemm_tc256_kernel / gemm_tc_kernel for ragged and narrow shapes" if GEMM_BACKEND == 2
                      else "gemm_tc_kernel (tcgen05.mma kind::tf32, 3xTF32)", "achieved": achieved_tf,
                      "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf if peak_tf else None, "traffic": traffic,
                      "peak_source": peak_src, "launches_timed": int(nl.value), "kernel_ms_per_step": tot_ms.value,
