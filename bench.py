@@ -254,7 +254,7 @@ def run_ours(args):
     }
     if world == 1 and CONFIG == 3:
         line["cpu_baseline"] = cpu_baseline()
-    print(json.dumps(line))
+    _emit(line)
 
 
 def _shutdown():
@@ -304,7 +304,18 @@ def run_reference(args):
             "env_steps_per_step": NUM_ENVS * HORIZON // CPU_FRACTION,
             "note": "CPU arm does not scale with --gpus: one host runs the reference algorithm for one env shard; a step is 1/16 of an epoch "
                     "(value = 8192 env-steps / measured step time)"}
-    print(json.dumps(line))
+    _emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    fd = _REAL_STDOUT if _REAL_STDOUT is not None else 1
+    while data:
+        data = data[os.write(fd, data):]
 
 
 def main():
@@ -315,8 +326,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=3, choices=[2, 3, 5], help="BASELINE.json config (3 = the metric's config)")
     args = ap.parse_args()
-    global CONFIG
+    global CONFIG, _REAL_STDOUT
     CONFIG = args.config
+    # stdout carries exactly ONE line (the JSON).  Libraries print there too -- NCCL's "NCCL version ..." line under NCCL_DEBUG=VERSION ignores
+    # NCCL_DEBUG_FILE -- so file descriptor 1 points at stderr while the benchmark runs and _emit() writes the line to the real stdout.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
