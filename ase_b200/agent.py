@@ -110,6 +110,10 @@ class CommonAgent:
                 init_comm()            # the library's own NCCL communicator: the per-minibatch allreduce goes through the C ABI
         self._load_config_params(config)
         self.model = self._build_learner(config)
+        self.peer_adam = False
+        if self.multi_gpu and self.ppo_device.type == 'cuda' and config.get('peer_adam', True):
+            from .dist_utils import init_peer
+            self.peer_adam = init_peer(self.model)      # gradient sum + Adam as one kernel over NVLink peer memory (falls back to NCCL)
         self.dataset = AMPDataset(self.batch_size, self.minibatch_size, self.ppo_device)
         self.epoch_num = 0
         self.frame = 0

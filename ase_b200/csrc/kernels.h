@@ -122,5 +122,14 @@ int launch_weight_reg(const float* w, float* g, int64_t n, float coef, double* a
 int launch_finalize(const FinalizeArgs& f, cudaStream_t st);
 int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float grad_scale, float b1, float b2, float lr, float eps,
                 int64_t step, cudaStream_t st);
+// the fp32 constants torch.optim.Adam ends up with (evaluated in doubles from the decimal hyper-parameters, then rounded)
+struct AdamConsts { float b1, b2, omb1, omb2, step_size, bc2_sqrt, eps; };
+AdamConsts adam_consts(float b1, float b2, float lr, float eps, int64_t step);
+}  // namespace ase
+// allreduce + Adam over NVLink peer memory (peer.cu)
+struct AsePeer;
+namespace ase {
+int launch_peer_adam(AsePeer* pr, float* p, float* m, float* v, float grad_scale, float b1, float b2, float lr, float eps, int64_t step,
+                     unsigned* status, cudaStream_t st);
 
 }  // namespace ase

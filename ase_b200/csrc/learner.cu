@@ -679,6 +679,18 @@ extern "C" int ase_learner_adam_step(AseLearner* lp, const AseLearnerState* s, i
                      (cudaStream_t)stream);
 }
 
+// allreduce (sum over the ranks, in place in every rank's peer-visible gradient arena) + Adam in ONE kernel over NVLink peer memory
+// (peer.cu): replaces ase_grad_allreduce + ase_learner_adam_step.  s->grads must be the arena inside the rank's peer buffer (ase_peer_grads);
+// params / exp_avg / exp_avg_sq must be readable 16 bytes at a time up to the arena rounded up to 4 floats.
+extern "C" int ase_learner_peer_adam_step(AseLearner* lp, AsePeer* peer, const AseLearnerState* s, int64_t step, float grad_scale, void* stream) {
+  ASE_CHECK_ARG(lp && peer && s && s->params && s->grads && s->exp_avg && s->exp_avg_sq && step >= 1, "peer_adam_step: bad argument");
+  const AseLearnerConfig& c = lp->cfg;
+  if (lp->reg) lp->reg->invalidate_range(s->params, s->params + lp->net.arena);   // weight planes are stale after the update
+  lp->weights_split = false;
+  return launch_peer_adam(peer, s->params, s->exp_avg, s->exp_avg_sq, grad_scale, c.beta1, c.beta2, c.lr, c.adam_eps, step,
+                          lp->reg ? lp->reg->flag : nullptr, (cudaStream_t)stream);
+}
+
 extern "C" int ase_learner_eval_actor_critic(AseLearner* lp, const AseLearnerState* s, const float* obs, const float* latents, int rows,
                                              float* mu, float* value_normed, void* stream) {
   ASE_CHECK_ARG(lp && s && obs, "eval_actor_critic: null argument");

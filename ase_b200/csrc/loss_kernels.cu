@@ -344,15 +344,21 @@ int launch_finalize(const FinalizeArgs& f, cudaStream_t st) {
   finalize_scalars_kernel<<<1, 32, 0, st>>>(f);
   ASE_LAUNCH_OK(); return ASE_OK;
 }
-int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float grad_scale, float b1, float b2, float lr, float eps,
-                int64_t step, cudaStream_t st) {
+AdamConsts adam_consts(float b1, float b2, float lr, float eps, int64_t step) {
   // torch.optim.Adam evaluates 1-beta, the bias corrections and lr/bc1 in Python doubles from the decimal hyper-parameters
   // (0.9, 0.999, 2e-5) and only then rounds to fp32: recover those decimals from the fp32 config values
   auto dec = [](float x) { char buf[32]; snprintf(buf, sizeof(buf), "%.7g", (double)x); return strtod(buf, nullptr); };
   const double db1 = dec(b1), db2 = dec(b2), dlr = dec(lr), deps = dec(eps);
   const double bc1 = 1.0 - pow(db1, (double)step), bc2 = 1.0 - pow(db2, (double)step);
-  adam_kernel<<<ew_blocks(n), 256, 0, st>>>(p, g, m, v, n, grad_scale, (float)db1, (float)db2, (float)(1.0 - db1), (float)(1.0 - db2),
-                                           (float)(dlr / bc1), (float)sqrt(bc2), (float)deps);
+  AdamConsts c;
+  c.b1 = (float)db1; c.b2 = (float)db2; c.omb1 = (float)(1.0 - db1); c.omb2 = (float)(1.0 - db2);
+  c.step_size = (float)(dlr / bc1); c.bc2_sqrt = (float)sqrt(bc2); c.eps = (float)deps;
+  return c;
+}
+int launch_adam(float* p, const float* g, float* m, float* v, int64_t n, float grad_scale, float b1, float b2, float lr, float eps,
+                int64_t step, cudaStream_t st) {
+  const AdamConsts c = adam_consts(b1, b2, lr, eps, step);
+  adam_kernel<<<ew_blocks(n), 256, 0, st>>>(p, g, m, v, n, grad_scale, c.b1, c.b2, c.omb1, c.omb2, c.step_size, c.bc2_sqrt, c.eps);
   ASE_LAUNCH_OK(); return ASE_OK;
 }
 

@@ -95,10 +95,13 @@ class Learner:
         assert len(names) == n, (len(names), n)
         arena = lib.ase_learner_arena_floats(C.byref(cfg))
         dev = self.device
-        self.params = torch.zeros(arena, dtype=torch.float32, device=dev)
-        self.grads = torch.zeros_like(self.params)
-        self.exp_avg = torch.zeros_like(self.params)
-        self.exp_avg_sq = torch.zeros_like(self.params)
+        pad = (arena + 3) // 4 * 4          # the peer-memory optimizer step moves 16 bytes at a time: keep the arenas readable up to a multiple of 4 floats
+        self.params = torch.zeros(pad, dtype=torch.float32, device=dev)[:arena]
+        self.grads = torch.zeros(pad, dtype=torch.float32, device=dev)[:arena]
+        self.exp_avg = torch.zeros(pad, dtype=torch.float32, device=dev)[:arena]
+        self.exp_avg_sq = torch.zeros(pad, dtype=torch.float32, device=dev)[:arena]
+        self._peer = None                   # AsePeer* when the gradient arena lives in NVLink peer memory (dist_utils.init_peer)
+        self._param_slices = []
         self.sigma = torch.full((act_dim,), float(sigma_init), dtype=torch.float32, device=dev)   # frozen logstd parameter
         self.step = 0
         self._views = OrderedDict()
@@ -110,6 +113,7 @@ class Learner:
             sl = slice(off.value, off.value + rows.value * cols.value)
             self._views[name] = self.params[sl].view(shape)
             self._gviews[name] = self.grads[sl].view(shape)
+            self._param_slices.append((name, sl, shape))
         self.running_mean_std = RunningMeanStd(obs_dim, dev, hp['rms_eps'])          # common_agent.py:49
         self.value_mean_std = RunningMeanStd(1, dev, hp['rms_eps'])                  # rl_games A2CBase ('reward_mean_std')
         self.amp_input_mean_std = RunningMeanStd(cfg.amp_dim, dev, hp['rms_eps']) if kind != 'ppo' else None   # amp_agent.py:26
@@ -245,9 +249,25 @@ class Learner:
             out['disc_demo_logit'] = self._demo_logit
         return out
 
+    def use_grads_arena(self, flat):
+        """Accumulate the gradients into `flat` (a float32 CUDA tensor of at least the arena size, e.g. the rank's NVLink peer buffer) from now
+        on.  Call before the first calc_gradients (a captured minibatch graph bakes the address in)."""
+        n = self.grads.numel()
+        assert flat.is_cuda and flat.dtype == torch.float32 and flat.is_contiguous() and flat.numel() >= n
+        self._grads_store = flat
+        self.grads = flat[:n]
+        self.grads.zero_()
+        for name, sl, shape in self._param_slices:
+            self._gviews[name] = self.grads[sl].view(shape)
+
     def adam_step(self, grad_scale=1.0):
+        """torch.optim.Adam step on the flat arenas.  With a peer buffer attached (multi-GPU, dist_utils.init_peer) the SAME call first sums
+        the gradient arenas of all ranks over NVLink peer memory, inside the same kernel (ase_learner_peer_adam_step)."""
         self.step += 1
         st = self._state()
+        if self._peer is not None:
+            check(lib.ase_learner_peer_adam_step(self._h, self._peer, C.byref(st), self.step, float(grad_scale), _stream()), 'ase_learner_peer_adam_step')
+            return
         check(lib.ase_learner_adam_step(self._h, C.byref(st), self.step, float(grad_scale), _stream()), 'ase_learner_adam_step')
 
     def plane_status(self):

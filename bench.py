@@ -133,14 +133,16 @@ def _timed_epochs(torch, agent, steps, world, d2h=False):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     host = []
+    marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     e0.record()
-    for _ in range(steps):
+    for k in range(steps):
         agent.update_epoch()
         info = agent.train_epoch()
         if world > 1:
             agent._sync_stats()                        # the per-epoch RunningMeanStd averaging of agent.train() (hvd.sync_stats)
         if d2h:
             host.append(agent._tr_buf.cpu())           # the step's train_result series -> host (D2H inside the timed region)
+        marks[k].record()
     e1.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -148,7 +150,12 @@ def _timed_epochs(torch, agent, steps, world, d2h=False):
     ms = torch.tensor([e0.elapsed_time(e1)], device='cuda')
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    global _EPOCH_MS
+    _EPOCH_MS = [round((e0 if k == 0 else marks[k - 1]).elapsed_time(marks[k]), 2) for k in range(steps)]      # this rank's per-epoch times
     return float(ms) / 1e3, host
+
+
+_EPOCH_MS = []
 
 
 def run_ours(args):
@@ -167,10 +174,14 @@ def run_ours(args):
     agent, env = _make_agent(torch, rank, world, 'device', seed=0)
     for _ in range(args.warmup):
         agent.update_epoch(); agent.train_epoch()
+        if world > 1:
+            agent._sync_stats()        # part of every epoch of agent.train(); its first call also sets up NCCL's connections (~0.2 s): warm-up, not timed
     torch.cuda.synchronize()
     launches0 = L.launch_count()
     with ClockSampler(local) as clk:
         secs, _ = _timed_epochs(torch, agent, args.steps, world)
+    value_epoch_ms = list(_EPOCH_MS)
+    peer_adam = bool(getattr(agent, 'peer_adam', False))
     launches = L.launch_count() - launches0
     play_t, upd_t, _ = agent.epoch_times()
     # roofline numerator / denominator: ONE extra epoch, outside the timed region, with CUDA events around every tcgen05 GEMM launch
@@ -196,6 +207,8 @@ def run_ours(args):
     agent, env = _make_agent(torch, rank, world, 'host', seed=0)
     for _ in range(max(4, args.warmup)):       # >= 3: the rollout's CUDA graph is captured on the third play_steps call
         agent.update_epoch(); agent.train_epoch()
+        if world > 1:
+            agent._sync_stats()
     e2e_secs, host = _timed_epochs(torch, agent, args.steps, world, d2h=True)
     e2e_value = env_steps / e2e_secs
     plane_flags |= _plane_flags(agent)
@@ -249,6 +262,8 @@ def run_ours(args):
                      "learner_tflops_algorithmic": nmb * FLOP_PER_MINIBATCH / 1e12 / (upd_t * args.steps) if upd_t > 0 else None},
         "split": {"play_time_s_last_step": play_t, "update_time_s_last_step": upd_t, "rollout_cuda_graph": graph_rollout,
                   "minibatch_cuda_graph": mb_graph, "instrumented_epoch_s": {"play": prof_play_t, "update": prof_upd_t}},
+        "epoch_ms_rank0": value_epoch_ms,      # the K timed epochs one by one (rank 0's CUDA events): stationarity of the timed region
+        "gradient_sum": ("one kernel with Adam over NVLink peer memory (csrc/peer.cu)" if peer_adam else "NCCL allreduce (csrc/comm.cu) + Adam") if world > 1 else "none (1 GPU)",
         "plane_status": plane_flags,      # ase_learner_plane_status after both runs: 0 = every FP16 plane scale prediction held
         "train_result_last": tr,
     }

@@ -356,6 +356,26 @@ void ase_comm_destroy(AseComm* c);
 int ase_grad_allreduce(AseComm* c, float* buf, int64_t count, void* stream);
 int ase_comm_allreduce_f64(AseComm* c, double* buf, int64_t count, void* stream);   /* RunningMeanStd averaging once per epoch (hvd.sync_stats) */
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU, one NVSwitch node: gradient allreduce + Adam as ONE kernel over NVLink peer memory (csrc/peer.cu) -- replaces the pair
+ * ase_grad_allreduce + ase_learner_adam_step, i.e. Horovod's averaging inside optimizer.step (learning/amp_agent.py:348-363) plus
+ * torch.optim.Adam (common_agent.py:45).  Each rank allocates its gradient arena with ase_peer_alloc (cudaMalloc + CUDA IPC handle), the
+ * host gathers the 64-byte handles of all ranks in rank order, every rank calls ase_peer_open.  The learner then accumulates its gradients
+ * straight into ase_peer_grads(local) and calls ase_learner_peer_adam_step once per minibatch: barrier, in-place reduce-scatter + all-gather
+ * of the arena by direct peer loads / stores (rank r sums slice r in rank order 0..N-1: bit-identical results on every rank), barrier, Adam
+ * over the full local arena (optimizer state stays replicated).  A peer that does not show up within ~15 s raises bit 2 of the status word
+ * ase_learner_plane_status reports (and ase_peer_status): an error, never a hang.  2 <= world <= 8.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct AsePeer AsePeer;
+int64_t ase_peer_buffer_bytes(int64_t arena_floats);
+int ase_peer_alloc(int64_t arena_floats, void** local, uint8_t* handle64);
+int ase_peer_open(const uint8_t* handles /* world x 64 bytes */, int world, int rank, void* local, int64_t arena_floats, AsePeer** out);
+void ase_peer_close(AsePeer* p, int free_local);
+float* ase_peer_grads(void* local);
+int ase_peer_status(AsePeer* p, int* error, void* stream);
+int ase_learner_peer_adam_step(AseLearner* l, AsePeer* p, const AseLearnerState* st, int64_t step, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -375,6 +375,48 @@ def gen_checkpoint_layout():
     print('checkpoint_layout.json ok', {k: len(v['model']) for k, v in out.items()})
 
 
+def gen_inference_shipped_stats():
+    """SURVEY 8(c) "forward of the shipped LLC checkpoint on fixed inputs", without shipping 28 MB of weights: the reference's own inference
+    path (ASEAgent._preproc_obs / _preproc_amp_obs in eval mode, a2c_network.eval_actor / eval_critic / eval_disc / eval_enc, value un-normalisation,
+    _calc_disc_rewards / _calc_enc_rewards) with the SHIPPED checkpoint's RunningMeanStd statistics (f64; variances from 1.3e-11 to ~1e2 after
+    8.4e9 frames -- the realistic conditioning of the normaliser) and seeded synthetic full-size network weights.  Inputs are drawn around the
+    shipped means with 1.5 x the shipped standard deviations, plus rows far outside (the +-5 clamp) and exactly at the mean."""
+    ref = os.environ.get('ASE_REFERENCE', '/root/reference')
+    ck = torch.load(os.path.join(ref, 'ase/data/models/ase_llc_reallusion_sword_shield.pth'), map_location='cpu', weights_only=False)
+    agent, _ = rh.make_ref_agent('ase', num_envs=8, overrides={'minibatch_size': 256, 'amp_minibatch_size': 64})
+    P = synth.params(O.ase_param_shapes(), seed=31)
+    _load_params(agent, P, True)
+    agent.running_mean_std.load_state_dict(ck['running_mean_std'])
+    agent.value_mean_std.load_state_dict(ck['reward_mean_std'])
+    agent._amp_input_mean_std.load_state_dict(ck['amp_input_mean_std'])
+    agent.set_eval()
+    g = torch.Generator().manual_seed(77)
+    n = 96
+    def around(st):
+        m, sd = st['running_mean'].float(), st['running_var'].float().sqrt()
+        x = m + 1.5 * sd * torch.randn(n, m.numel(), generator=g)
+        x[0] = m; x[1] = m + 40.0 * sd; x[2] = m - 40.0 * sd; x[3] = m + 1e-3 * torch.randn(m.numel(), generator=g)
+        return x
+    obs, amp = around(ck['running_mean_std']), around(ck['amp_input_mean_std'])
+    z = torch.nn.functional.normalize(torch.randn(n, 64, generator=g), dim=-1)
+    net = agent.model.a2c_network
+    with torch.no_grad():
+        po = agent._preproc_obs(obs)
+        mu, _ = net.eval_actor(obs=po, ase_latents=z)
+        v_n = net.eval_critic(po, z)
+        v = agent.value_mean_std(v_n, True)
+        pa = agent._preproc_amp_obs(amp)
+        logit = net.eval_disc(pa)
+        enc = net.eval_enc(pa)
+        dr = agent._calc_disc_rewards(amp)
+        er = agent._calc_enc_rewards(amp, z)
+    out = dict(param_seed=31, obs=obs, amp=amp, z=z, obs_norm=po, amp_norm=pa, mu=mu, value_normed=v_n, value=v, disc_logit=logit, enc=enc,
+               disc_r=dr, enc_r=er,
+               rms={k: {kk: vv.clone() for kk, vv in ck[k].items()} for k in ('running_mean_std', 'reward_mean_std', 'amp_input_mean_std')})
+    torch.save(out, os.path.join(OUT, 'inference_shipped_stats.pt'))
+    print('inference_shipped_stats.pt ok', float(ck['amp_input_mean_std']['running_var'].min()), float(po.abs().max()))
+
+
 def gen_rollout_math():
     agent, _ = rh.make_ref_agent('ase', num_envs=8, overrides={'minibatch_size': 256, 'amp_minibatch_size': 64})
     g = torch.Generator().manual_seed(21)

@@ -225,6 +225,36 @@ def test_inference_paths_vs_oracle(backend):
         assert torch.allclose(dr.cpu(), dr_ref, rtol=1e-4, atol=1e-4) and torch.allclose(er.cpu(), er_ref, rtol=1e-4, atol=1e-5)
 
 
+@pytest.mark.parametrize('backend', [0, 1, 2])
+def test_inference_with_shipped_checkpoint_statistics_vs_reference_golden(backend):
+    """tests/golden/inference_shipped_stats.pt: the reference's own inference path (eval-mode RunningMeanStd with the SHIPPED checkpoint's
+    statistics -- variances from 1.3e-11 to ~1e2, counts ~1e11 -- a2c_network.eval_actor / eval_critic / eval_disc / eval_enc, value
+    un-normalisation, disc / enc rewards) on inputs around the shipped means incl. rows that hit the +-5 clamp and a row AT the mean.
+    Full-size networks, seeded weights (the 28 MB of shipped weights do not travel)."""
+    from ase_b200 import Learner, ops
+    fx = G.load('inference_shipped_stats.pt')
+    n = fx['obs'].shape[0]
+    P = synth.params(O.ase_param_shapes(), seed=fx['param_seed'])
+    ln = Learner('ase', 253, 31, 256, amp_dim=1400, latent_dim=64, amp_batch=64, gemm_backend=backend)
+    ln.load_named(P)
+    ln.set_stats_weights({k: {kk: vv.cuda() for kk, vv in v.items()} for k, v in fx['rms'].items()})
+    for r in (ln.running_mean_std, ln.amp_input_mean_std, ln.value_mean_std):
+        r.eval()
+    obs, amp, z = fx['obs'].cuda(), fx['amp'].cuda(), fx['z'].cuda()
+    assert torch.allclose(ln.running_mean_std(obs).cpu(), fx['obs_norm'], rtol=1e-5, atol=1e-5)
+    assert torch.allclose(ln.amp_input_mean_std(amp).cpu(), fx['amp_norm'], rtol=1e-5, atol=1e-5)
+    mu, val = ln.eval_actor_critic(obs, z)
+    assert torch.allclose(mu.cpu(), fx['mu'], rtol=1e-4, atol=1e-4)
+    assert torch.allclose(val.cpu(), fx['value_normed'], rtol=1e-4, atol=1e-4)
+    assert torch.allclose(ln.value_mean_std(val, unnorm=True).cpu(), fx['value'], rtol=1e-4, atol=1e-4)
+    logits, enc = ln.eval_disc_enc(amp)
+    assert torch.allclose(logits.cpu(), fx['disc_logit'], rtol=1e-4, atol=1e-4)
+    assert torch.allclose(enc.cpu(), fx['enc'], rtol=1e-4, atol=1e-5)
+    dr, er, _ = ops.amp_rewards(logits, enc, z)
+    assert torch.allclose(dr.cpu().view(n, -1), fx['disc_r'].view(n, -1), rtol=1e-4, atol=1e-4)
+    assert torch.allclose(er.cpu().view(n, -1), fx['enc_r'].view(n, -1), rtol=1e-4, atol=1e-5)
+
+
 def test_fp16_plane_scale_miss_is_reported():
     """gemm_backend 2 predicts each tensor's power-of-two scale from the previous call.  A tensor whose max jumps by more than
     2^9 between two calls cannot be represented: the library must say so (sticky flag -> AseError), never return silently wrong

@@ -99,3 +99,29 @@ def test_motion_lib_matches_reference_golden():
         assert torch.allclose(mine, ref, rtol=1e-5, atol=1e-5), name
     demo = O.build_amp_obs_demo(mt, fx['ids'], fx['t0'], fx['sim_dt'], fx['steps'])
     assert torch.allclose(demo, fx['demo'], rtol=1e-5, atol=1e-5)
+
+
+def _shipped_stats_state(fx):
+    P = synth.params(O.ase_param_shapes(), seed=fx['param_seed'])
+    st = O.LearnerState(P, 253, 1400, 'ase')
+    for r, k in ((st.obs_rms, 'running_mean_std'), (st.val_rms, 'reward_mean_std'), (st.amp_rms, 'amp_input_mean_std')):
+        r.mean, r.var, r.count = fx['rms'][k]['running_mean'].clone(), fx['rms'][k]['running_var'].clone(), fx['rms'][k]['count'].clone()
+    return st
+
+
+def test_inference_with_shipped_checkpoint_statistics_matches_reference_golden():
+    """The reference's inference path under the shipped checkpoint's RunningMeanStd statistics (variances down to 1.3e-11, counts of 1e11):
+    normalised inputs incl. the +-5 clamp rows, actor mu, critic value (normalised and un-normalised), disc logit, encoder output, rewards."""
+    fx = G.load('inference_shipped_stats.pt')
+    st = _shipped_stats_state(fx)
+    with torch.no_grad():
+        on, an = st.obs_rms.norm(fx['obs']), st.amp_rms.norm(fx['amp'])
+        assert torch.allclose(on, fx['obs_norm'], rtol=1e-6, atol=1e-6) and torch.allclose(an, fx['amp_norm'], rtol=1e-6, atol=1e-6)
+        assert float(on.abs().max()) == 5.0 and float(an.abs().max()) == 5.0
+        assert torch.allclose(O.eval_actor(st.p, on, fx['z']), fx['mu'], rtol=1e-5, atol=1e-5)
+        assert torch.allclose(O.eval_critic(st.p, on, fx['z']), fx['value_normed'], rtol=1e-5, atol=1e-5)
+        assert torch.allclose(O.eval_critic_unnorm(st, fx['obs'], fx['z']), fx['value'], rtol=1e-5, atol=1e-5)
+        assert torch.allclose(O.eval_disc(st.p, an), fx['disc_logit'], rtol=1e-5, atol=1e-5)
+        assert torch.allclose(O.eval_enc(st.p, an), fx['enc'], rtol=1e-5, atol=1e-6)
+        dr, er = O.calc_amp_rewards(st, fx['amp'], fx['z'], O.DEFAULT_CFG)
+        assert torch.allclose(dr, fx['disc_r'], rtol=1e-5, atol=1e-5) and torch.allclose(er, fx['enc_r'], rtol=1e-5, atol=1e-6)

@@ -16,6 +16,14 @@ g = torch.Generator(device='cuda').manual_seed(0)
 r = lambda *s: torch.randn(*s, device='cuda', generator=g)
 ln = Learner('ase', 253, 31, B, amp_dim=1400, latent_dim=64, amp_batch=Ba, gemm_backend=backend)
 ln.init_reference(0)
+if os.environ.get('ASE_GRADS_IPC', '0') == '1':       # experiment: gradient arena in a cudaMalloc'ed, IPC-exported allocation (what dist_utils.init_peer uses)
+    import ctypes as C
+    from ase_b200.dist_utils import _DeviceArray
+    local, handle = C.c_void_p(), (C.c_uint8 * 64)()
+    L.check(L.lib.ase_peer_alloc(ln.grads.numel(), C.byref(local), handle), 'ase_peer_alloc')
+    _arr = _DeviceArray(L.lib.ase_peer_grads(local), (ln.grads.numel() + 3) // 4 * 4)
+    ln.use_grads_arena(torch.as_tensor(_arr, device='cuda'))
+    print('gradient arena: IPC-exported cudaMalloc allocation')
 z = torch.nn.functional.normalize(r(B, 64), dim=-1)
 d = dict(obs=r(B, 253), actions=r(B, 31) * 0.1, old_logp_actions=r(B) * 0.1 - 46, advantages=r(B), mu=r(B, 31) * 0.1,
          sigma=torch.full((B, 31), 0.055, device='cuda'), returns=r(B, 1), old_values=r(B, 1), rand_action_mask=(torch.rand(B, device='cuda') < 0.9).float(),
