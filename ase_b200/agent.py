@@ -668,7 +668,11 @@ class CommonAgent:
                 r.pop('series', None)
                 # FP16 operand-plane scale status of the epoch (rides in the record: no extra sync).  A miss means the flagged updates
                 # were not fp32-accurate: stop right here instead of training on them
-                if r['scalars'].pop('plane_status', 0.0) != 0.0:
+                status = int(r['scalars'].pop('plane_status', 0.0))
+                if status & 4:
+                    raise RuntimeError(f"epoch {r['epoch']}: a peer rank did not reach the gradient barrier of the multi-GPU optimizer step within ~15 s "
+                                       "(csrc/peer.cu); that update was skipped -- restore() the last checkpoint")
+                if status != 0:
                     raise RuntimeError(f"epoch {r['epoch']}: FP16 operand-plane scale miss -- a tensor's max moved by more than 2^9 up / 2^12 down between "
                                        "two consecutive calls; rerun with gemm_backend=1 (restore() the last checkpoint)")
                 total_time += r.get('play_time', 0.0) + r.get('update_time', 0.0)

@@ -275,6 +275,8 @@ class Learner:
         ase_learner_plane_status) -- the flagged update would not be fp32-accurate.  One stream synchronisation."""
         f = C.c_int(0)
         check(lib.ase_learner_plane_status(self._h, C.byref(f), _stream()), 'ase_learner_plane_status')
+        if f.value & 4:
+            raise L.AseError("multi-GPU optimizer step: a peer rank did not reach the gradient barrier within ~15 s (csrc/peer.cu); the update was skipped")
         if f.value:
             raise L.AseError(f"FP16 operand-plane scale miss (flags {f.value}: bit0 overflow, bit1 underflow): a tensor's max moved by more "
                              "than 2^9 up / 2^12 down between two consecutive calls; rerun with gemm_backend=1")

@@ -92,7 +92,7 @@ EXPORTS = ['ase_abi_version', 'ase_last_error', 'ase_launch_count', 'ase_obs_bui
            'ase_learner_calc_gradients', 'ase_learner_adam_step', 'ase_learner_eval_actor_critic',
            'ase_learner_eval_disc_enc', 'ase_comm_load', 'ase_comm_unique_id', 'ase_comm_create', 'ase_comm_destroy', 'ase_grad_allreduce',
            'ase_comm_allreduce_f64', 'ase_peer_buffer_bytes', 'ase_peer_alloc', 'ase_peer_open', 'ase_peer_close', 'ase_peer_grads',
-           'ase_peer_status', 'ase_learner_peer_adam_step']
+           'ase_peer_status', 'ase_peer_debug', 'ase_learner_peer_adam_step']
 
 
 class AseError(RuntimeError):
@@ -158,6 +158,7 @@ def _load():
     lib.ase_peer_close.argtypes = [vp, i32]; lib.ase_peer_close.restype = None
     lib.ase_peer_grads.argtypes = [vp]; lib.ase_peer_grads.restype = vp
     lib.ase_peer_status.argtypes = [vp, C.POINTER(i32), vp]
+    lib.ase_peer_debug.argtypes = [vp, vp]
     lib.ase_learner_peer_adam_step.argtypes = [vp, vp, C.POINTER(LearnerState), i64, f32, vp]
     return lib
 

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define ASE_ABI_VERSION 3
+#define ASE_ABI_VERSION 4
 #define ASE_MAX_LAYERS 4
 
 typedef enum {
@@ -374,6 +374,7 @@ int ase_peer_open(const uint8_t* handles /* world x 64 bytes */, int world, int 
 void ase_peer_close(AsePeer* p, int free_local);
 float* ase_peer_grads(void* local);
 int ase_peer_status(AsePeer* p, int* error, void* stream);
+int ase_peer_debug(AsePeer* p, long long* out8);      /* clock64() stamps of block 0's phases in the last call: start, ready, reduced, fenced, done, end */
 int ase_learner_peer_adam_step(AseLearner* l, AsePeer* p, const AseLearnerState* st, int64_t step, float grad_scale, void* stream);
 
 #ifdef __cplusplus

@@ -33,7 +33,7 @@ def test_header_symbols_exported(aselib):
 
 def test_abi_version_and_layout_queries(aselib):
     L = aselib
-    assert L.lib.ase_abi_version() == 3
+    assert L.lib.ase_abi_version() == 4
     cfg = L.LearnerConfig()
     cfg.kind = L.KIND_ASE
     cfg.obs_dim, cfg.act_dim, cfg.amp_dim, cfg.latent_dim = 253, 31, 1400, 64
