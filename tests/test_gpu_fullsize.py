@@ -69,7 +69,7 @@ def _three_way(mine, g32, g64, tag):
         rows.append((k, r, m, x))
         if not m[0] <= max(1e-4, 2.0 * r[0] + 5e-5):        # within the stated 1e-4 of the fp64 truth, or as close to it as the reference's fp32 is (x2)
             bad.append((k, 'median error vs fp64', m[0], 'reference fp32', r[0]))
-        if not m[1] <= 1.5 * r[1] + 1e-4:
+        if not m[1] <= 2.0 * r[1] + 1e-4:
             bad.append((k, 'q95 error vs fp64', m[1], 'reference fp32', r[1]))
         if _conditioned(k):
             if not x[2] <= 2e-4:        # (a flip one layer up moves a whole bias-gradient vector by ~1e-4 of its max)
