@@ -99,6 +99,10 @@ class CommonAgent:
         self.nn_dir = os.path.join(self.train_dir, self.experiment_name, 'nn')
         self.print_stats = config.get('print_stats', True)
         self.writer = config.get('writer', None)          # optional tensorboardX-like object with add_scalar(tag, value, step)
+        # run.py hands its RLGPUAlgoObserver over as config['features']['observer'] (rl_games A2CBase): after_init / after_print_stats are
+        # honoured; process_infos(infos, done_indices) only by the reference-order rollout (the device rollout keeps no index lists)
+        self.algo_observer = (config.get('features') or {}).get('observer')
+        self.mean_rewards = None
         self.clip_actions = config.get('clip_actions', True)
         self.multi_gpu = config.get('multi_gpu', False)
         self.rank, self.rank_size = 0, 1
@@ -130,6 +134,8 @@ class CommonAgent:
         # 'minibatch_graph' (default True): from the third epoch on, gather + calc_gradients of a minibatch are one CUDA graph launch
         self._mb_graph_enabled = bool(config.get('minibatch_graph', True))
         self._graphs_on = True
+        if self.algo_observer is not None and hasattr(self.algo_observer, 'after_init'):
+            self.algo_observer.after_init(self)       # rl_games A2CBase.__init__
 
     # ------------------------------------------------------------------ construction helpers
     def _load_config_params(self, config):
@@ -364,6 +370,8 @@ class CommonAgent:
             done_indices = self.dones.nonzero(as_tuple=False)[:, 0]      # (host sync, as in the reference: ase_agent.py:78-79)
             self._episode_meter[0] += self.current_rewards[done_indices].sum(); self._episode_meter[1] += self.current_lengths[done_indices].sum()
             self._episode_meter[2] += done_indices.numel()
+            if self.algo_observer is not None and hasattr(self.algo_observer, 'process_infos'):
+                self.algo_observer.process_infos(infos, done_indices)          # amp_agent.py:107 / ase_agent.py:84
             not_dones = 1.0 - self.dones.float()
             self.current_rewards = self.current_rewards * not_dones.unsqueeze(1)
             self.current_lengths = self.current_lengths * not_dones
@@ -611,7 +619,8 @@ class CommonAgent:
         nmb = self.mini_epochs_num * len(self.dataset)
         if getattr(self, '_tr_buf', None) is None or self._tr_buf.shape[0] != nmb:
             from .lib import TR_COUNT
-            self._tr_buf = torch.zeros(nmb, TR_COUNT + 1, device=self.ppo_device)       # + the learner's plane-scale status
+            # + the learner's status word + the epoch's episode meter (sum of finished episodes' rewards, of their lengths, their count)
+            self._tr_buf = torch.zeros(nmb, TR_COUNT + 4, device=self.ppo_device)
         self._tr_i = 0
         if self._mb_graph_enabled and self._graphs_on and self.ppo_device.type == 'cuda' and self.epoch_num >= 3:
             self._static_dataset()
@@ -619,7 +628,12 @@ class CommonAgent:
             for i in range(len(self.dataset)):
                 self._train_minibatch(i)
         self._post_update(batch_dict)
-        self.model.plane_flag_to(self._tr_buf[:, -1])
+        from .lib import TR_COUNT
+        self.model.plane_flag_to(self._tr_buf[:, TR_COUNT])
+        # game_rewards / game_lengths of the reference (amp_agent.py:102-105), per epoch instead of over a 100-game window: the meter rides in
+        # the epoch's record (every row carries the same three numbers, so the record's row mean is the value) and starts again from zero
+        self._tr_buf[:, TR_COUNT + 1:TR_COUNT + 4] = self._episode_meter
+        self._episode_meter.zero_()
         ev[2].record()
         self._events = ev
         from .lib import TR_NAMES
@@ -657,7 +671,7 @@ class CommonAgent:
         # no per-epoch host sync -- the epoch's scalars and event timings come back through a pinned ring
         from .async_log import AsyncEpochLog
         from .lib import TR_NAMES
-        log = AsyncEpochLog(list(TR_NAMES) + ['plane_status'], depth=4)
+        log = AsyncEpochLog(list(TR_NAMES) + ['plane_status', 'ep_reward_sum', 'ep_length_sum', 'ep_count'], depth=4)
         self.last_mean_rewards = -100500
         self.epoch_log = []                       # [{'epoch', 'frames', 'scalars', 'play_time', 'update_time'}], an epoch or two behind
         total_time = 0.0
@@ -675,13 +689,20 @@ class CommonAgent:
                 if status != 0:
                     raise RuntimeError(f"epoch {r['epoch']}: FP16 operand-plane scale miss -- a tensor's max moved by more than 2^9 up / 2^12 down between "
                                        "two consecutive calls; rerun with gemm_backend=1 (restore() the last checkpoint)")
+                rs, ls, cnt = (r['scalars'].pop(k, 0.0) for k in ('ep_reward_sum', 'ep_length_sum', 'ep_count'))
+                if cnt > 0:       # common_agent.py:125-136 (mean over the episodes that finished in this epoch)
+                    r['mean_rewards'], r['mean_lengths'] = rs / cnt, ls / cnt
+                    self.mean_rewards = r['mean_rewards']
                 total_time += r.get('play_time', 0.0) + r.get('update_time', 0.0)
+                r['total_time'] = total_time
                 self.epoch_log.append(r)
                 if self.rank == 0 and self.print_stats and 'play_time' in r:
                     tot = r['play_time'] + r['update_time']
                     print(f"epoch {r['epoch']}: fps step: {r['frames'] / r['play_time']:.1f} fps total: {r['frames'] / tot:.1f}")
                 if self.writer is not None:       # performance/* and losses/* scalars of common_agent.py:119-152,551-564
                     self._write_stats(r)
+                if self.rank == 0 and self.algo_observer is not None and hasattr(self.algo_observer, 'after_print_stats'):
+                    self.algo_observer.after_print_stats(r['epoch'] * self.batch_size * self.rank_size, r['epoch'], total_time)     # common_agent.py:123
 
         model_output_file = os.path.join(self.nn_dir, self.config.get('name', self.name))
         while True:
@@ -712,8 +733,15 @@ class CommonAgent:
             w.add_scalar('performance/step_fps', r['frames'] * self.rank_size / r['play_time'], frame)
             w.add_scalar('performance/update_time', r['update_time'], frame)
             w.add_scalar('performance/play_time', r['play_time'], frame)
+        w.add_scalar('info/epochs', r['epoch'], frame)
         for k, v in r['scalars'].items():
             w.add_scalar(('info/' if k in ('kl', 'last_lr', 'lr_mul', 'e_clip') else 'losses/') + k, v, frame)
+        if 'mean_rewards' in r:            # common_agent.py:125-136
+            w.add_scalar('rewards0/frame', r['mean_rewards'], frame)
+            w.add_scalar('rewards0/iter', r['mean_rewards'], r['epoch'])
+            w.add_scalar('rewards0/time', r['mean_rewards'], r.get('total_time', 0.0))
+            w.add_scalar('episode_lengths/frame', r['mean_lengths'], frame)
+            w.add_scalar('episode_lengths/iter', r['mean_lengths'], r['epoch'])
 
 
 class AMPAgent(CommonAgent):

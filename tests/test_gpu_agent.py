@@ -104,8 +104,18 @@ def test_train_loop_logs_through_the_async_ring():
         def add_scalar(self, tag, value, step):
             tags.append(tag)
     agent.writer = W()
+    calls = []
+    class Observer:                                   # what run.py passes as config['features']['observer'] (RLGPUAlgoObserver)
+        def after_print_stats(self, frame, epoch_num, total_time):
+            calls.append((frame, epoch_num, total_time))
+    agent.algo_observer = Observer()
     agent.train()
     assert [r['epoch'] for r in agent.epoch_log] == [1, 2, 3, 4, 5, 6]      # stops when epoch_num > max_epochs (common_agent.py:149)
+    assert [c[1] for c in calls] == [1, 2, 3, 4, 5, 6] and all(b[2] >= a[2] for a, b in zip(calls, calls[1:]))
+    # episodes finish at 5 % per env-step here: the per-epoch episode meter (game_rewards / game_lengths) must have reported some
+    done = [r for r in agent.epoch_log if 'mean_rewards' in r]
+    assert done and all(r['mean_lengths'] >= 1.0 and r['mean_rewards'] == r['mean_rewards'] for r in done)
+    assert 'rewards0/frame' in tags and 'episode_lengths/iter' in tags and 'info/epochs' in tags
     for r in agent.epoch_log:
         assert r['play_time'] > 0 and r['update_time'] > 0 and r['frames'] == 64 * 8
         assert all(v == v and abs(v) < 1e9 for v in r['scalars'].values())
