@@ -18,7 +18,7 @@ def test_peer_allreduce_adam_is_bit_identical_to_nccl_allreduce_plus_adam():
     n = min(torch.cuda.device_count(), 8)
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', f'--nproc-per-node={n}', '--master-addr', '127.0.0.1',
            '--master-port', '29547', os.path.join(root, 'tools', 'peer_adam_check.py')]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=240, env=dict(os.environ, ASE_PEER_ADAM='1'))      # opt in beyond 4 ranks too
     out = r.stdout + r.stderr
     assert r.returncode == 0, out[-3000:]
     assert 'mismatches=0' in out and 'peer path ON' in out, out[-3000:]
