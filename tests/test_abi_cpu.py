@@ -80,3 +80,22 @@ def test_async_epoch_log_ring_cpu():
     assert [r['frames'] for r in got] == [10, 20, 30, 40, 50]
     assert all(abs(r['scalars']['a'] - (r['epoch'] + 1)) < 1e-6 and abs(r['scalars']['b'] - 2 * r['epoch']) < 1e-6 for r in got)
     assert log.poll() == [] and log.flush() == []
+
+
+def test_ctypes_signatures_have_the_declared_arity(aselib):
+    """Every prototype of include/ase_b200.h against the ctypes binding (ase_b200/lib.py): same number of parameters wherever argtypes are
+    set -- a binding that drifted from the header would otherwise corrupt the call silently."""
+    src = open(os.path.join(ROOT, 'include', 'ase_b200.h')).read()
+    src = re.sub(r'/\*.*?\*/', '', src, flags=re.S)
+    src = re.sub(r'//[^\n]*', '', src)
+    protos = re.findall(r'\b(ase_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;', src, flags=re.S)
+    assert len(protos) >= 40
+    checked = 0
+    for name, args in protos:
+        args = ' '.join(args.split())
+        n = 0 if args in ('', 'void') else args.count(',') + 1
+        fn = getattr(aselib.lib, name)
+        if fn.argtypes is not None:
+            assert len(fn.argtypes) == n, f"{name}: header has {n} parameters, ctypes binding {len(fn.argtypes)}"
+            checked += 1
+    assert checked >= 30
