@@ -454,3 +454,11 @@ if __name__ == '__main__':
     gen_rollout_math()
     gen_hrl_calc_gradients()
     gen_calc_gradients()
+    # round 2 (each can also be run by name, see above): the reference's own play_steps / prepare_dataset over a scripted env, the early-termination
+    # test, the inference path under the shipped checkpoint's statistics, the shipped checkpoints' layouts, and calc_gradients at the
+    # benchmarked size (minutes of CPU time)
+    gen_rollout()
+    gen_humanoid_reset()
+    gen_inference_shipped_stats()
+    gen_checkpoint_layout()
+    gen_calc_gradients_full()
